@@ -1,0 +1,125 @@
+/*
+ * include/s3r_b200.h — additional C-ABI entry points of the B200 renderer library.
+ *
+ * None of these exist in the reference (its only export is updateAndRender, include/render.h);
+ * SURVEY.md section 8(b) allows a replacement to add entry points the Swift loop never calls as long as
+ * updateAndRender's behaviour is unchanged.  They expose what the reference keeps in process
+ * statics (render-cpp/render.cpp:51-113) as explicit objects, so that a harness can (a) load a
+ * scene from an explicit path or from arrays, (b) step the camera on the host
+ * (update_camera, render.cpp:134-156) and render explicit camera matrices, (c) keep frames
+ * device-resident, (d) render many views per call (frame-parallel batches), and (e) render only a
+ * screen-space band [y0, y1) of the frame (multi-GPU partition).
+ *
+ * Plain pointers and sizes only.  Every function returns 0 on success or a negative S3R_E_* code;
+ * s3r_last_error() gives the text.  There is no CPU fallback: without a CUDA device every
+ * rendering entry point fails.
+ */
+#ifndef S3R_B200_H
+#define S3R_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3R_API __attribute__((visibility("default")))
+
+#define S3R_OK 0
+#define S3R_E_CUDA -1       /* CUDA runtime error (no device, launch failure, ...) */
+#define S3R_E_IO -2         /* data.bin missing / unreadable */
+#define S3R_E_SCENE -3      /* scene violates the format contract (w != 1, bad index, kind > 1, ...) */
+#define S3R_E_ARG -4        /* invalid argument */
+#define S3R_E_NOSCENE -5    /* no scene loaded */
+
+typedef struct S3RRenderer S3RRenderer;
+
+typedef struct {            /* same 24-byte layout as Input (render-cpp/render.hpp:15-21) */
+    float up, down, left, right, mouse_x, mouse_y;
+} S3RInput;
+
+typedef struct {            /* the reference's `state` static, render-cpp/render.cpp:51-65 */
+    float position[3];
+    float axis_x[3], axis_y[3], axis_z[3];
+    float matrix[12];       /* rows (axis, -axis . position), row-major 3x4 */
+    float mouse[2];
+    int32_t started;        /* 0 until the first update (which forces the matrix rebuild, :267-270) */
+} S3RCamera;
+
+typedef struct {            /* per-view pipeline counters of the last completed render */
+    uint32_t triangles_in;
+    uint32_t near_rejected;     /* max z <= near                        (render.cpp:306) */
+    uint32_t clipped;           /* straddled the near plane             (render.cpp:308-310) */
+    uint32_t spawned;           /* second triangle appended by clip()   (render.cpp:239-257) */
+    uint32_t culled;            /* off-screen bbox or area < 10         (render.cpp:311-317) */
+    uint32_t setups;            /* triangles handed to the rasteriser */
+    uint32_t bin_entries;       /* (triangle, tile) pairs */
+    uint32_t big_triangles;     /* binned cooperatively (more than S3R_BIG_TILES tiles) */
+    uint32_t overflow;          /* bit0 setup capacity, bit1 bin capacity, bit2 big-list capacity (auto-regrown) */
+    uint32_t reserved[7];
+} S3RStats;
+
+/* One surviving triangle as the rasteriser sees it; field-compatible with the oracle's dump. */
+typedef struct {
+    uint32_t order;             /* processing order key: index, or T + parent index for appended */
+    uint32_t xmin, xmax, ymin, ymax;
+    float area;
+    float wstart[3], dx[3], dy[3], rvz[3];
+    float cv[3][3], n[3][3];
+    uint32_t kind, texture;
+    float payload[3][3];
+    float dz[2], tpp[2];
+} S3RSetupDump;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+S3R_API int s3r_create(S3RRenderer **out, int device);
+S3R_API void s3r_destroy(S3RRenderer *r);
+S3R_API const char *s3r_last_error(void);
+
+/* ---- scene (data.bin: data-generator/main.swift:381-416, render-cpp/render.cpp:177-209) --- */
+S3R_API int s3r_load_scene_file(S3RRenderer *r, const char *data_bin_path);
+S3R_API int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices_xyzw, uint64_t vertex_count,
+                          const uint64_t *vertex_indices, const uint64_t *attribute_indices, uint64_t index_count,
+                          const void *attributes_48b, uint64_t attribute_count, const uint32_t *texels,
+                          uint64_t texel_count);
+S3R_API int s3r_scene_counts(const S3RRenderer *r, uint64_t *vertices, uint64_t *indices, uint64_t *attributes,
+                     uint64_t *texels);
+
+/* ---- camera on the host (update_camera, render-cpp/render.cpp:134-156) --------------------- */
+S3R_API void s3r_camera_reset(S3RCamera *cam);
+S3R_API void s3r_camera_update(S3RCamera *cam, const S3RInput *input);
+S3R_API float s3r_factor(uint32_t height);   /* near * H / (2 * scale), render-cpp/render.cpp:279 */
+
+/* ---- rendering ------------------------------------------------------------------------------
+ * cameras: n_views x 12 floats (S3RCamera.matrix).  Rows [y0, y1) of each width x height frame are
+ * produced (y0 = 0, y1 = height for a whole frame).  Output: n_views x (y1 - y0) x width uint32,
+ * 0x00RRGGBB, tightly packed.
+ *
+ * s3r_render_device: dev_out is DEVICE memory; work is enqueued on `stream` (a cudaStream_t, NULL =
+ *   the renderer's own stream) and NOT waited for.  Call s3r_finish before reading results; it
+ *   returns 1 when an internal capacity overflowed (buffers have been regrown — render again).
+ * s3r_render_host: host_out is HOST memory (pageable or pinned); synchronous, includes the
+ *   device->host copy and any capacity retry.
+ */
+S3R_API int s3r_render_device(S3RRenderer *r, const float *cameras, uint32_t n_views, uint32_t width, uint32_t height,
+                      uint32_t y0, uint32_t y1, uint32_t *dev_out, void *stream);
+S3R_API int s3r_finish(S3RRenderer *r);
+S3R_API int s3r_render_host(S3RRenderer *r, const float *cameras, uint32_t n_views, uint32_t width, uint32_t height,
+                    uint32_t y0, uint32_t y1, uint32_t *host_out);
+
+/* ---- introspection (tests, bench) -------------------------------------------------------- */
+S3R_API int s3r_get_stats(S3RRenderer *r, uint32_t view, S3RStats *out);
+/* raster-space vertices of the last render of `view` (V x 4 floats: x, y, z, unused), render.cpp:285-289 */
+S3R_API int s3r_dump_raster_vertices(S3RRenderer *r, uint32_t view, float *out_xyzw, uint64_t capacity_vertices);
+/* surviving triangles of the last render of `view`, sorted by order key; *count receives the total */
+S3R_API int s3r_dump_setups(S3RRenderer *r, uint32_t view, S3RSetupDump *out, uint64_t capacity, uint64_t *count);
+S3R_API uint64_t s3r_kernel_launches(const S3RRenderer *r);   /* kernels launched by this renderer so far */
+S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
+/* options: "tma_store" (1 = cp.async.bulk tile write-out, default; 0 = plain stores),
+ *          "fused_small" (1 = single-CTA geometry for small scenes, default), "views_per_chunk" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

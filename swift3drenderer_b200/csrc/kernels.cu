@@ -1,0 +1,721 @@
+// kernels.cu — hand-written sm_100a kernels of the frame pipeline.
+//
+//   frame_reset        zero per-view counters and tile histograms
+//   vertex_stage       K1  model/view/projection over planar float4 position streams   (render.cpp:285-289)
+//   triangle_setup     K2  gather, near reject, near-plane clip (0/1/2 out), cull, setup,
+//                          warp-ballot + block-scan compaction                          (render.cpp:297-359, 212-262)
+//   bin_small/bin_big  K3  sort-middle binning: count -> tile_scan -> fill              (no reference counterpart)
+//   tile_raster        K4  per-tile exact barycentric walk + depth test in registers, deferred
+//                          perspective-correct shading + rip-map fetch, colour tile in shared
+//                          memory, cp.async.bulk (TMA) write-out                        (render.cpp:360-382, 124-132)
+//
+// PARITY RULES: this translation unit is compiled with -fmad=false -prec-div=true
+// -prec-sqrt=true -ftz=false; every expression is written in the reference's evaluation order so
+// that each binary32 intermediate equals the CPU's.  Do not "simplify" arithmetic here.
+#include "pipeline.cuh"
+#include "walk.cuh"
+
+namespace s3r {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+struct Cam { float m[12]; };
+
+__device__ __forceinline__ Cam load_cam(const float *p) {
+    Cam c;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { c.m[i] = __ldg(p + i); }
+    return c;
+}
+
+// simd_mul(float4x3, float4) = ((c0*x + c1*y) + c2*z) + c3*w
+__device__ __forceinline__ float3 xform(const Cam &c, float x, float y, float z, float w) {
+    return make_float3(((c.m[0] * x + c.m[1] * y) + c.m[2] * z) + c.m[3] * w,
+                       ((c.m[4] * x + c.m[5] * y) + c.m[6] * z) + c.m[7] * w,
+                       ((c.m[8] * x + c.m[9] * y) + c.m[10] * z) + c.m[11] * w);
+}
+
+// render.cpp:288 — (v.x, -v.y, 0) * factor / -v.z + (W/2, H/2, -v.z)
+__device__ __forceinline__ float3 project(float3 cv, float factor, float half_w, float half_h) {
+    const float nz = -cv.z;
+    return make_float3(cv.x * factor / nz + half_w, -cv.y * factor / nz + half_h, 0.f * factor / nz + nz);
+}
+
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 scale3(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// simd_fast_normalize as pinned by the oracle shim: v * (1 / sqrt(dot(v, v)))
+__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, 1.0f / sqrtf(dot3(a, a))); }
+// EDGE_FUNCTION(a, b, c), render.cpp:9
+__device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by, float cx, float cy) {
+    return (cx - ax) * (ay - by) + (cy - ay) * (bx - ax);
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ------------------------------------------------------------------------------------------------
+// K0 — reset
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_reset(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C_COUNT) { f.counters[view * C_COUNT + i] = 0; }
+    for (uint32_t t = i; t < f.n_tiles; t += gridDim.x * blockDim.x) { f.tile_count[view * f.tile_stride + t] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 — vertex stage: 4 vertices per thread, float4 loads of the planar streams, float4 stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= f.Vpad) { return; }
+    const Cam cam = load_cam(f.cams + 12 * view);
+    const float4 x = __ldg(reinterpret_cast<const float4 *>(f.pos_x + i4));
+    const float4 y = __ldg(reinterpret_cast<const float4 *>(f.pos_y + i4));
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(f.pos_z + i4));
+    float4 *out = f.rv + (size_t)view * f.Vpad + i4;
+    const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float3 cv = xform(cam, xs[k], ys[k], zs[k], 1.0f);
+        const float3 rv = project(cv, f.factor, f.half_w, f.half_h);
+        out[k] = make_float4(rv.x, rv.y, rv.z, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 — triangle setup
+// ------------------------------------------------------------------------------------------------
+struct Corner {
+    float3 cv, rv, n;
+    uint4 pay;      // raw payload words: colour = floats 0..2; texture = {index, -, u, v}
+    uint32_t kind;
+};
+
+__device__ __forceinline__ float3 lerp3(float3 a, float3 b, float u, float t) {  // x*(1-a) + y*a
+    return add3(scale3(a, u), scale3(b, t));
+}
+
+// render.cpp:222-236 — the vertex where edge (a -> b) meets z = near
+__device__ __forceinline__ Corner clip_vertex(const Corner &a, const Corner &b, uint32_t kind0, const Frame &f) {
+    const float t = (kNear - a.rv.z) / (b.rv.z - a.rv.z);
+    const float u = 1 - t;
+    Corner c;
+    c.cv = lerp3(a.cv, b.cv, u, t);
+    c.rv = make_float3(c.cv.x * f.factor / kNear + f.half_w, -c.cv.y * f.factor / kNear + f.half_h,
+                       0.f * f.factor / kNear + kNear);
+    c.kind = kind0;
+    c.pay = make_uint4(0, 0, 0, 0);
+    if (kind0 == 0) {
+        const float3 ca = make_float3(__uint_as_float(a.pay.x), __uint_as_float(a.pay.y), __uint_as_float(a.pay.z));
+        const float3 cb = make_float3(__uint_as_float(b.pay.x), __uint_as_float(b.pay.y), __uint_as_float(b.pay.z));
+        const float3 col = lerp3(ca, cb, u, t);
+        c.pay.x = __float_as_uint(col.x); c.pay.y = __float_as_uint(col.y); c.pay.z = __float_as_uint(col.z);
+    } else if (kind0 == 1) {
+        c.pay.x = a.pay.x;  // texture index of the edge's first endpoint, render.cpp:233
+        c.pay.z = __float_as_uint(__uint_as_float(a.pay.z) * u + __uint_as_float(b.pay.z) * t);
+        c.pay.w = __float_as_uint(__uint_as_float(a.pay.w) * u + __uint_as_float(b.pay.w) * t);
+    }
+    c.n = lerp3(a.n, b.n, u, t);
+    return c;
+}
+
+// render.cpp:311-359.  Returns false when the triangle is culled.
+__device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, const Corner &d2, uint32_t order,
+                                           const Frame &f, SetupVis &v, SetupShade &s) {
+    const float max_x = fmaxf(fmaxf(d0.rv.x, d1.rv.x), d2.rv.x);
+    const float max_y = fmaxf(fmaxf(d0.rv.y, d1.rv.y), d2.rv.y);
+    if (max_x < 0 || max_y < 0) { return false; }
+    const float min_x = fminf(fminf(d0.rv.x, d1.rv.x), d2.rv.x);
+    const float min_y = fminf(fminf(d0.rv.y, d1.rv.y), d2.rv.y);
+    if (min_x >= f.fw || min_y >= f.fh) { return false; }
+    const float area = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, d2.rv.x, d2.rv.y);
+    if (area < 10) { return false; }
+    const float inv_area = 1 / area;
+    const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
+    const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+    const float px = (float)xmin + 0.5f, py = (float)ymin + 0.5f;
+    v.xmin = (uint16_t)xmin; v.xmax = (uint16_t)xmax; v.ymin = (uint16_t)ymin; v.ymax = (uint16_t)ymax;
+    v.order = order;
+    v.kind = d0.kind;
+    v.wstart[0] = edge_fn(d1.rv.x, d1.rv.y, d2.rv.x, d2.rv.y, px, py) * inv_area;
+    v.wstart[1] = edge_fn(d2.rv.x, d2.rv.y, d0.rv.x, d0.rv.y, px, py) * inv_area;
+    v.wstart[2] = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, px, py) * inv_area;
+    v.dx[0] = (d1.rv.y - d2.rv.y) * inv_area; v.dx[1] = (d2.rv.y - d0.rv.y) * inv_area; v.dx[2] = (d0.rv.y - d1.rv.y) * inv_area;
+    v.dy[0] = (d2.rv.x - d1.rv.x) * inv_area; v.dy[1] = (d0.rv.x - d2.rv.x) * inv_area; v.dy[2] = (d1.rv.x - d0.rv.x) * inv_area;
+    v.rvz[0] = 1 / d0.rv.z; v.rvz[1] = 1 / d1.rv.z; v.rvz[2] = 1 / d2.rv.z;
+    const Corner *d[3] = {&d0, &d1, &d2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float3 c = scale3(d[k]->cv, v.rvz[k]), n = scale3(d[k]->n, v.rvz[k]);
+        s.cv[3 * k] = c.x; s.cv[3 * k + 1] = c.y; s.cv[3 * k + 2] = c.z;
+        s.n[3 * k] = n.x; s.n[3 * k + 1] = n.y; s.n[3 * k + 2] = n.z;
+    }
+    s.kind = d0.kind;
+    s.texture = 0;
+    s.area = area;
+    s.tpp[0] = 0.f; s.tpp[1] = 0.f;
+    if (d0.kind == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            s.pay[3 * k] = __uint_as_float(d[k]->pay.x) * v.rvz[k];
+            s.pay[3 * k + 1] = __uint_as_float(d[k]->pay.y) * v.rvz[k];
+            s.pay[3 * k + 2] = __uint_as_float(d[k]->pay.z) * v.rvz[k];
+        }
+    } else {
+        s.texture = d0.pay.x;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            s.pay[2 * k] = __uint_as_float(d[k]->pay.z) * v.rvz[k];
+            s.pay[2 * k + 1] = __uint_as_float(d[k]->pay.w) * v.rvz[k];
+        }
+        s.pay[6] = (v.rvz[0] * v.dx[0] + v.rvz[1] * v.dx[1]) + v.rvz[2] * v.dx[2];  // dz.x = dot(rvz, dx)
+        s.pay[7] = (v.rvz[0] * v.dy[0] + v.rvz[1] * v.dy[1]) + v.rvz[2] * v.dy[2];  // dz.y = dot(rvz, dy)
+        s.pay[8] = 0.f;
+        s.tpp[0] = (s.pay[0] * v.dx[0] + s.pay[2] * v.dx[1]) + s.pay[4] * v.dx[2];
+        s.tpp[1] = (s.pay[1] * v.dy[0] + s.pay[3] * v.dy[1]) + s.pay[5] * v.dy[2];
+    }
+    return true;
+}
+
+struct SetupShared {
+    uint32_t list[256];
+    uint32_t count;
+    uint32_t stats[4];   // near, clipped, spawned, culled
+    uint32_t warp_sum[8];
+    uint32_t base;
+};
+
+// Block-wide ordered slot allocation for `keep` flags: warp ballot -> per-warp counts -> one
+// global atomicAdd per block -> slot.  All 256 threads must call.
+__device__ __forceinline__ uint32_t allocate_slots(bool keep, uint32_t *global_counter, SetupShared &sh) {
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (lane == 0) { sh.warp_sum[warp] = __popc(mask); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t c = sh.warp_sum[w]; sh.warp_sum[w] = total; total += c; }
+        sh.base = total ? atomicAdd(global_counter, total) : 0u;
+    }
+    __syncthreads();
+    const uint32_t slot = sh.base + sh.warp_sum[warp] + __popc(mask & ((1u << lane) - 1u));
+    __syncthreads();  // warp_sum/base reusable by the next call
+    return slot;
+}
+
+__device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint32_t slot, const SetupVis &v,
+                                            const SetupShade &s) {
+    uint4 *dv = reinterpret_cast<uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+    const uint4 *sv = reinterpret_cast<const uint4 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { dv[i] = sv[i]; }
+    uint4 *ds = reinterpret_cast<uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
+    const uint4 *ss = reinterpret_cast<const uint4 *>(&s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { ds[i] = ss[i]; }
+}
+
+__device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const Corner &d1, const Corner &d2,
+                                           uint32_t order, const Frame &f, uint32_t view, SetupShared &sh,
+                                           bool count_culled) {
+    SetupVis v;
+    SetupShade s;
+    const bool keep = valid && make_setup(d0, d1, d2, order, f, v, s);
+    if (count_culled) {
+        const uint32_t culled = __ballot_sync(0xFFFFFFFFu, valid && !keep);
+        if (lane_id() == 0 && culled) { atomicAdd(&sh.stats[3], __popc(culled)); }
+    }
+    const uint32_t slot = allocate_slots(keep, f.counters + view * C_COUNT + C_SETUPS, sh);
+    if (keep) {
+        if (slot < f.setup_cap) {
+            store_setup(f, view, slot, v, s);
+        } else {
+            atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ Corner gather_corner(const Frame &f, const Cam &cam, uint32_t view, uint32_t vi, uint32_t ai) {
+    Corner c;
+    c.cv = xform(cam, __ldg(f.pos_x + vi), __ldg(f.pos_y + vi), __ldg(f.pos_z + vi), 1.0f);
+    const float4 r = f.rv[(size_t)view * f.Vpad + vi];
+    c.rv = make_float3(r.x, r.y, r.z);
+    const uint4 a = __ldg(f.attr + 2 * (size_t)ai);
+    c.n = xform(cam, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), 0.0f);
+    c.kind = a.w;
+    c.pay = __ldg(f.attr + 2 * (size_t)ai + 1);
+    return c;
+}
+
+constexpr uint32_t ITEM_STRADDLE = 0x80000000u;
+
+// clip(), render.cpp:212-262.  On return d0..d2 hold the in-place triangle; when two corners were in
+// front, (s0, s1, s2) is the appended triangle (current, I_np, I_pc) and the function returns true.
+__device__ __forceinline__ bool clip_near(Corner &d0, Corner &d1, Corner &d2, Corner &s0, Corner &s1, Corner &s2,
+                                          const Frame &f) {
+    const bool f0 = d0.rv.z > kNear, f1 = d1.rv.z > kNear, f2 = d2.rv.z > kNear;
+    const uint32_t kind0 = d0.kind;  // render.cpp:225: the kind always comes from corner 0
+    // The edge whose endpoints lie on the same side fixes (current, next, preceding); the loop in
+    // the reference keeps the last such edge.
+    int cur = 0;
+    if (f0 == f1) { cur = 0; }
+    if (f1 == f2) { cur = 1; }
+    if (f2 == f0) { cur = 2; }
+    const Corner c = cur == 0 ? d0 : (cur == 1 ? d1 : d2);  // current
+    const Corner n = cur == 0 ? d1 : (cur == 1 ? d2 : d0);  // next
+    const Corner p = cur == 0 ? d2 : (cur == 1 ? d0 : d1);  // preceding
+    const bool two_in_front = c.rv.z > kNear;
+    const Corner i_np = clip_vertex(n, p, kind0, f);  // data_new[next]:      edge next -> preceding
+    const Corner i_pc = clip_vertex(p, c, kind0, f);  // data_new[preceding]: edge preceding -> current
+    Corner e0, e1, e2;                                // new (current, next, preceding)
+    if (two_in_front) {
+        e0 = c; e1 = n; e2 = i_np;                    // data[preceding] = data_new[next]       (:240)
+        s0 = c; s1 = i_np; s2 = i_pc;                 // appended (current, I_np, I_pc)         (:241-254)
+    } else {
+        e0 = i_pc; e1 = i_np; e2 = p;                 // data[current], data[next] replaced     (:259-260)
+    }
+    if (cur == 0) { d0 = e0; d1 = e1; d2 = e2; }
+    else if (cur == 1) { d1 = e0; d2 = e1; d0 = e2; }
+    else { d2 = e0; d0 = e1; d1 = e2; }
+    return two_in_front;
+}
+
+__global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Frame f) {
+    __shared__ SetupShared sh;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    const Cam cam = load_cam(f.cams + 12 * view);
+    if (tid == 0) { sh.count = 0; }
+    if (tid < 4) { sh.stats[tid] = 0; }
+    __syncthreads();
+
+    // ---- phase 1: classify one triangle per thread from raster-space vertices only ----------
+    const uint32_t t = blockIdx.x * 256u + tid;
+    uint32_t cls = 0;  // 0 rejected, 1 rasterisable as is, 2 straddles the near plane
+    bool near_rej = false, culled = false;
+    if (t < f.T) {
+        const float4 *rv = f.rv + (size_t)view * f.Vpad;
+        const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
+        if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
+            near_rej = true;
+        } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
+            cls = 2;
+        } else {
+            const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+            const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+            const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
+            if (off || edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) { culled = true; } else { cls = 1; }
+        }
+    }
+    {   // warp-ballot compaction of the work items into shared memory
+        const uint32_t m_near = __ballot_sync(0xFFFFFFFFu, near_rej), m_cull = __ballot_sync(0xFFFFFFFFu, culled);
+        const uint32_t m_clip = __ballot_sync(0xFFFFFFFFu, cls == 2), m_work = __ballot_sync(0xFFFFFFFFu, cls != 0);
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (m_near) { atomicAdd(&sh.stats[0], __popc(m_near)); }
+            if (m_clip) { atomicAdd(&sh.stats[1], __popc(m_clip)); }
+            if (m_cull) { atomicAdd(&sh.stats[3], __popc(m_cull)); }
+            if (m_work) { base = atomicAdd(&sh.count, __popc(m_work)); }
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (cls != 0) { sh.list[base + __popc(m_work & ((1u << lane) - 1u))] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
+    }
+    __syncthreads();
+
+    // ---- phase 2: dense full setup of the compacted work items (count <= 256: one pass) --------
+    const uint32_t count = sh.count;
+    if (count == 0 && sh.stats[0] == 0 && sh.stats[3] == 0) { return; }
+    const bool valid = tid < count;
+    Corner d0, d1, d2, s0, s1, s2;
+    bool spawn = false;
+    uint32_t tri = 0;
+    if (valid) {
+        const uint32_t item = sh.list[tid];
+        tri = item & ~ITEM_STRADDLE;
+        d0 = gather_corner(f, cam, view, __ldg(f.vi0 + tri), __ldg(f.ai0 + tri));
+        d1 = gather_corner(f, cam, view, __ldg(f.vi1 + tri), __ldg(f.ai1 + tri));
+        d2 = gather_corner(f, cam, view, __ldg(f.vi2 + tri), __ldg(f.ai2 + tri));
+        if (item & ITEM_STRADDLE) { spawn = clip_near(d0, d1, d2, s0, s1, s2, f); }
+    }
+    if (count) { emit_block(valid, d0, d1, d2, tri, f, view, sh, /*count_culled=*/true); }
+    if (__syncthreads_or(spawn)) {
+        const uint32_t m_sp = __ballot_sync(0xFFFFFFFFu, spawn);
+        if (lane == 0 && m_sp) { atomicAdd(&sh.stats[2], __popc(m_sp)); }
+        // appended triangles run after all originals, in parent order: key = T + parent index
+        emit_block(spawn, s0, s1, s2, f.T + tri, f, view, sh, /*count_culled=*/true);
+    }
+    __syncthreads();
+    if (tid < 4 && sh.stats[tid]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR + tid, sh.stats[tid]); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 — sort-middle binning (count -> scan -> fill).  Entries are (order << 32 | slot) so that each
+// tile can restore the reference's processing order with one sort.
+// ------------------------------------------------------------------------------------------------
+struct TileRange { uint32_t tx0, tx1, ty0, ty1; bool empty; };
+
+__device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
+    TileRange r;
+    const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
+    r.empty = ylo > yhi;
+    r.tx0 = xmin / TILE_W; r.tx1 = xmax / TILE_W;
+    r.ty0 = ylo / TILE_H - f.tile_row0; r.ty1 = yhi / TILE_H - f.tile_row0;
+    return r;
+}
+
+template <bool FILL>
+__device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot, uint32_t order) {
+    if (!FILL) {
+        atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
+    } else {
+        const uint32_t pos = atomicAdd(f.tile_cursor + view * f.tile_stride + tile, 1u);
+        if (pos < f.entry_cap) {
+            f.entries[(size_t)view * f.entry_cap + pos] = ((unsigned long long)order << 32) | slot;
+        }
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_small(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+        const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+        const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
+        if (r.empty) { continue; }
+        const uint32_t ntiles = (r.tx1 - r.tx0 + 1u) * (r.ty1 - r.ty0 + 1u);
+        if (ntiles > BIG_TILES) {
+            if (!FILL) {
+                const uint32_t pos = atomicAdd(f.counters + view * C_COUNT + C_BIG, 1u);
+                if (pos < f.big_cap) { f.big_list[(size_t)view * f.big_cap + pos] = slot; }
+                else { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 4u); }
+            }
+            continue;
+        }
+        for (uint32_t ty = r.ty0; ty <= r.ty1; ty++) {
+            for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) { bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z); }
+        }
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t n = min(f.counters[view * C_COUNT + C_BIG], f.big_cap);
+    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
+        const uint32_t slot = f.big_list[(size_t)view * f.big_cap + b];
+        const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+        const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+        const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
+        const uint32_t nx = r.tx1 - r.tx0 + 1u, ntiles = nx * (r.ty1 - r.ty0 + 1u);
+        for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) {
+            const uint32_t ty = r.ty0 + i / nx, tx = r.tx0 + i % nx;
+            bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z);
+        }
+    }
+}
+
+// exclusive scan of the tile histogram (one CTA per view); also seeds the fill cursors
+__global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame f) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const uint32_t view = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t *cnt = f.tile_count + view * f.tile_stride;
+    uint32_t *off = f.tile_offset + view * f.tile_stride, *cur = f.tile_cursor + view * f.tile_stride;
+    if (tid == 0) { carry = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < f.n_tiles; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t c = i < f.n_tiles ? cnt[i] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) { incl += o; } }
+        if (lane == 31) { warp_tot[warp] = incl; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) { wi += o; } }
+            warp_tot[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[warp] + incl - c;
+        if (i < f.n_tiles) { off[i] = excl; cur[i] = excl; }
+        __syncthreads();
+        if (tid == 1023) { carry = excl + c; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        off[f.n_tiles] = carry;
+        f.counters[view * C_COUNT + C_ENTRIES] = carry;
+        if (carry > f.entry_cap) { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 2u); }
+        // all overflow sources have been decided by now: fold them into the cross-chunk record
+        const uint32_t *c = f.counters + view * C_COUNT;
+        if (c[C_OVERFLOW]) { atomicOr(f.sticky + 0, c[C_OVERFLOW]); }
+        atomicMax(f.sticky + 1, c[C_SETUPS]);
+        atomicMax(f.sticky + 2, carry);
+        atomicMax(f.sticky + 3, c[C_BIG]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 — per-tile rasteriser
+// ------------------------------------------------------------------------------------------------
+struct RasterShared {
+    union {
+        unsigned long long entries[SORT_CAP];          // sorted bin list (32 KB) while walking ...
+        uint4 state[TILE_W * TILE_H];                  // ... then per-pixel winners (w0, w1, w2, slot)
+    } u;
+    uint32_t colour[TILE_H][TILE_W];                   // 8 KB, source of the bulk write-out
+    SetupVis batch[BATCH];                             // 1 KB
+    float rowstart[BATCH][TILE_H][3];                  // 6 KB: weights at each row's first walked pixel
+};
+
+// Ascending bitonic sort of a[0..n) (a may be shared or global); indices >= n act as +inf.
+__device__ __forceinline__ void block_sort(unsigned long long *a, uint32_t n) {
+    uint32_t N = 1;
+    while (N < n) { N <<= 1; }
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {  // flip stage
+            const uint32_t p = i ^ (k - 1u);
+            if (p > i && p < n) { const unsigned long long x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+                const uint32_t p = i ^ j;
+                if (p > i && p < n) { const unsigned long long x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115-122
+    i--; i |= i >> 1; i |= i >> 2; i |= i >> 4;
+    return i + 1;
+}
+
+// render.cpp:363-372 + getColor (:339-359) + getTextureColor (:124-132) for one winning pixel
+__device__ __forceinline__ uint32_t shade_pixel(const Frame &f, uint32_t view, uint32_t slot, float w0, float w1, float w2) {
+    const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
+    const float rz0 = vp->rvz[0], rz1 = vp->rvz[1], rz2 = vp->rvz[2];
+    const uint4 *sp = reinterpret_cast<const uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
+    SetupShade s;
+    uint4 *sd = reinterpret_cast<uint4 *>(&s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sd[i] = sp[i]; }
+    const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;
+    const float b0 = w0 / ooz, b1 = w1 / ooz, b2 = w2 / ooz;
+    const float3 c0 = make_float3(s.cv[0], s.cv[1], s.cv[2]), c1 = make_float3(s.cv[3], s.cv[4], s.cv[5]),
+                 c2 = make_float3(s.cv[6], s.cv[7], s.cv[8]);
+    const float3 n0 = make_float3(s.n[0], s.n[1], s.n[2]), n1 = make_float3(s.n[3], s.n[4], s.n[5]),
+                 n2 = make_float3(s.n[6], s.n[7], s.n[8]);
+    const float3 pu = unit3(add3(add3(scale3(c0, b0), scale3(c1, b1)), scale3(c2, b2)));
+    const float3 point = make_float3(-pu.x, -pu.y, -pu.z);
+    const float3 normal = unit3(add3(add3(scale3(n0, b0), scale3(n1, b1)), scale3(n2, b2)));
+    const float3 halfway = unit3(add3(point, normal));
+    const float shade = dot3(halfway, normal);
+    float3 base;
+    if (s.kind == 0) {
+        const float3 k0 = make_float3(s.pay[0], s.pay[1], s.pay[2]), k1 = make_float3(s.pay[3], s.pay[4], s.pay[5]),
+                     k2 = make_float3(s.pay[6], s.pay[7], s.pay[8]);
+        base = add3(add3(scale3(k0, b0), scale3(k1, b1)), scale3(k2, b2));
+    } else {
+        const float u = (s.pay[0] * b0 + s.pay[2] * b1) + s.pay[4] * b2;
+        const float v = (s.pay[1] * b0 + s.pay[3] * b1) + s.pay[5] * b2;
+        const float level_x = ooz / fabsf(s.tpp[0] - u * s.pay[6]);
+        const float level_y = ooz / fabsf(s.tpp[1] - v * s.pay[7]);
+        const uint32_t lx = next_pow2_8((uint32_t)fmaxf(fminf(level_x, 256.f), 1.f));
+        const uint32_t ly = next_pow2_8((uint32_t)fmaxf(fminf(level_y, 256.f), 1.f));
+        // fmodf(t, 1) == t - truncf(t) exactly for finite t (the fractional bits are representable)
+        const uint32_t x = (uint32_t)((u - truncf(u)) * (float)lx) + (511u & ~(2u * lx - 1u));
+        const uint32_t y = (uint32_t)((v - truncf(v)) * (float)ly) + (511u & ~(2u * ly - 1u));
+        const uint32_t idx = (x + (y << 9)) & 0x3FFFFu;  // stays inside the atlas even for hostile uv
+        const uint32_t rgb = __ldg(f.texels + ((size_t)(s.texture % f.n_tex) << 18) + idx);
+        base = make_float3((float)(rgb >> 16), (float)((rgb >> 8) & 255u), (float)(rgb & 255u));
+    }
+    const uint32_t r = (uint32_t)(int)(shade * base.x) & 255u, g = (uint32_t)(int)(shade * base.y) & 255u,
+                   b = (uint32_t)(int)(shade * base.z) & 255u;
+    return (((r << 8) + g) << 8) + b;  // RGB(), render.cpp:8
+}
+
+__device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_t j) {
+    return row * TILE_W + seg * SEG + (j ^ seg);  // spreads a thread's 8-pixel run over the 16-byte bank groups
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_constant__ Frame f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
+    const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y, tid = threadIdx.x;
+    const uint32_t tile = tile_y * f.tiles_x + tile_x;
+    const uint32_t tx0 = tile_x * TILE_W, ty0 = (tile_y + f.tile_row0) * TILE_H;
+    const uint32_t row = tid / SEGS_PER_ROW, seg = tid % SEGS_PER_ROW;
+    const uint32_t y = ty0 + row, sx0 = tx0 + seg * SEG;
+
+    const uint32_t *toff = f.tile_offset + view * f.tile_stride;
+    const uint32_t begin = toff[tile], n = toff[tile + 1] - begin;
+    unsigned long long *list = f.entries + (size_t)view * f.entry_cap + begin;
+
+    float depth[SEG], bw0[SEG], bw1[SEG], bw2[SEG];
+    uint32_t win[SEG];
+#pragma unroll
+    for (int j = 0; j < SEG; j++) { depth[j] = 0.f; bw0[j] = bw1[j] = bw2[j] = 0.f; win[j] = NO_TRI; }
+
+    if (n > 0) {
+        // ---- restore the reference's triangle order ------------------------------------------
+        const bool in_smem = n <= SORT_CAP;
+        if (in_smem) {
+            for (uint32_t i = tid; i < n; i += RASTER_THREADS) { sh.u.entries[i] = list[i]; }
+            __syncthreads();
+            block_sort(sh.u.entries, n);
+        } else {
+            block_sort(list, n);  // rare: longer than the shared buffer, sort in place in HBM/L2
+        }
+        const unsigned long long *sorted = in_smem ? sh.u.entries : list;
+
+        for (uint32_t base = 0; base < n; base += BATCH) {
+            const uint32_t nb = min((uint32_t)BATCH, n - base);
+            // ---- stage the batch's coverage records ---------------------------------------
+            if (tid < nb * 4u) {
+                const uint32_t b = tid >> 2, q = tid & 3u;
+                const uint32_t slot = (uint32_t)sorted[base + b];
+                reinterpret_cast<uint4 *>(&sh.batch[b])[q] =
+                    reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot)[q];
+            }
+            __syncthreads();
+            // ---- stage A: exact weights at the first walked pixel of every (triangle, row) ----
+            for (uint32_t item = tid; item < nb * TILE_H; item += RASTER_THREADS) {
+                const uint32_t b = item / TILE_H, r = item % TILE_H;
+                const SetupVis &v = sh.batch[b];
+                const uint32_t yy = ty0 + r;
+                if (yy >= v.ymin && yy <= v.ymax) {
+                    const uint32_t ny = yy - v.ymin;
+                    const uint32_t nx = max(tx0, (uint32_t)v.xmin) - v.xmin;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float wy = walk_jump(v.wstart[c], v.dy[c], ny);   // render.cpp:378-379
+                        sh.rowstart[b][r][c] = walk_jump(wy, v.dx[c], nx);      // render.cpp:374
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- stage B: every thread walks its 8 pixels through the batch, in order ---------
+            for (uint32_t b = 0; b < nb; b++) {
+                const SetupVis &v = sh.batch[b];
+                if (y < v.ymin || y > v.ymax) { continue; }
+                const uint32_t xa = max(sx0, (uint32_t)v.xmin), xb = min(sx0 + SEG - 1u, (uint32_t)v.xmax);
+                if (xa > xb) { continue; }
+                const uint32_t skip = xa - max(tx0, (uint32_t)v.xmin);
+                const float d0 = v.dx[0], d1 = v.dx[1], d2 = v.dx[2];
+                float w0 = walk_jump(sh.rowstart[b][row][0], d0, skip);
+                float w1 = walk_jump(sh.rowstart[b][row][1], d1, skip);
+                float w2 = walk_jump(sh.rowstart[b][row][2], d2, skip);
+                const float rz0 = v.rvz[0], rz1 = v.rvz[1], rz2 = v.rvz[2];
+                const uint32_t slot = (uint32_t)sorted[base + b];
+#pragma unroll
+                for (int j = 0; j < SEG; j++) {
+                    const uint32_t x = sx0 + j;
+                    if (x >= xa && x <= xb) {
+                        if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                         // render.cpp:362
+                            const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;      // render.cpp:363
+                            if (ooz > depth[j]) {                                    // render.cpp:364
+                                depth[j] = ooz; bw0[j] = w0; bw1[j] = w1; bw2[j] = w2; win[j] = slot;
+                            }
+                        }
+                        w0 = add_rn(w0, d0); w1 = add_rn(w1, d1); w2 = add_rn(w2, d2);   // render.cpp:374
+                    }
+                }
+            }
+            __syncthreads();  // batch / rowstart are rewritten by the next iteration
+        }
+    }
+
+    // ---- hand the winners to a pixel-per-lane layout for coherent shading ------------------
+    __syncthreads();  // the sorted list (aliased with state) is dead from here on
+#pragma unroll
+    for (int j = 0; j < SEG; j++) {
+        sh.u.state[swizzled(row, seg, j)] =
+            make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t it = 0; it < (TILE_W * TILE_H) / RASTER_THREADS; it++) {
+        const uint32_t p = it * RASTER_THREADS + tid, pr = p / TILE_W, pc = p % TILE_W;
+        const uint4 st = sh.u.state[swizzled(pr, pc / SEG, pc % SEG)];
+        uint32_t rgb = kBackground;
+        if (st.w != NO_TRI) {
+            rgb = shade_pixel(f, view, st.w, __uint_as_float(st.x), __uint_as_float(st.y), __uint_as_float(st.z));
+        }
+        sh.colour[pr][pc] = rgb;
+    }
+
+    // ---- write-out -------------------------------------------------------------------------
+    uint32_t *out = f.out + (size_t)view * f.out_view_stride;
+    const uint32_t cols = min((uint32_t)TILE_W, f.W - tx0);
+    if (f.use_tma) {
+        // make the generic-proxy writes to the colour tile visible to the async (TMA) proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < TILE_H) {
+            const uint32_t yy = ty0 + tid;
+            if (yy >= f.y0 && yy < f.y1) {
+                uint32_t *dst = out + (size_t)(yy - f.y0) * f.W + tx0;
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.colour[tid][0]);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"(cols * 4u) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        for (uint32_t p = tid; p < TILE_W * TILE_H; p += RASTER_THREADS) {
+            const uint32_t pr = p / TILE_W, pc = p % TILE_W, yy = ty0 + pr;
+            if (pc < cols && yy >= f.y0 && yy < f.y1) { out[(size_t)(yy - f.y0) * f.W + tx0 + pc] = sh.colour[pr][pc]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int g_sm_count = 148;
+
+cudaError_t configure_kernels() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { return e; }
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    return cudaFuncSetAttribute(tile_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared));
+}
+
+static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int launch_geometry(const Frame &f, cudaStream_t s) {
+    int launches = 0;
+    const uint32_t persistent = (uint32_t)g_sm_count * 4u;
+    frame_reset<<<dim3(ceil_div(max(f.n_tiles, (uint32_t)C_COUNT), 256), f.n_views), 256, 0, s>>>(f); launches++;
+    vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
+    triangle_setup<<<dim3(ceil_div(f.T, 256), f.n_views), 256, 0, s>>>(f); launches++;
+    const uint32_t bin_blocks = min(persistent, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
+    bin_small<false><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;
+    bin_big<false><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
+    tile_scan<<<f.n_views, 1024, 0, s>>>(f); launches++;
+    bin_small<true><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;
+    bin_big<true><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
+    return launches;
+}
+
+int launch_raster(const Frame &f, cudaStream_t s) {
+    tile_raster<<<dim3(f.tiles_x, f.tiles_y, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+    return 1;
+}
+
+int launch_geometry_small(const Frame &f, cudaStream_t s) { return launch_geometry(f, s); }
+
+}  // namespace s3r

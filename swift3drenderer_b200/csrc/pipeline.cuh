@@ -1,0 +1,105 @@
+// pipeline.cuh — device-side data layout and kernel parameter block of the B200 renderer.
+//
+// HBM layout (all arrays 256-byte aligned cudaMalloc blocks):
+//
+//   scene (immutable after load; converted once from data.bin's AoS records)
+//     pos_x/pos_y/pos_z   float[Vpad]        planar positions, streamed as float4 by the vertex stage
+//     vi0/vi1/vi2         uint32[T]          planar vertex-index streams (corner 0/1/2 of triangle t)
+//     ai0/ai1/ai2         uint32[T]          planar attribute-index streams
+//     attr                uint4[2*A]         per attribute: {nx, ny, nz, kind} , {payload words 0..3}
+//                                            (32-byte AoS on purpose: attributes are *gathered*)
+//     texels              uint32[nTex<<18]   512x512 rip-map atlases, 0x00RRGGBB
+//
+//   per view (frame scratch, strided by view)
+//     rv                  float4[Vpad]       raster-space vertices (x, y, z, -) from the vertex stage
+//     vis / shade         64 B + 128 B per surviving triangle (compacted)
+//     tile_count/offset/cursor, entries (u64 = order<<32 | slot), big_list, counters
+//
+// Screen tiles are TILE_W x TILE_H pixels, aligned to the full frame's origin (so a band-partitioned
+// render bins and rasterises exactly the tiles the whole-frame render would).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s3r {
+
+constexpr int TILE_W = 64;
+constexpr int TILE_H = 32;
+constexpr int RASTER_THREADS = 256;         // (TILE_W / SEG) * TILE_H
+constexpr int SEG = 8;                      // pixels per thread in the visibility pass
+constexpr int SEGS_PER_ROW = TILE_W / SEG;  // 8
+constexpr int BATCH = 16;                   // triangles staged per visibility batch
+constexpr int SORT_CAP = 4096;              // bin entries sorted in shared memory (longer lists: in HBM)
+constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
+constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
+
+constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
+constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.cpp:92 (binary32 value of the reference build)
+constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:96
+
+enum Counter : uint32_t {
+    C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7,
+    C_COUNT = 16
+};
+
+struct __align__(16) SetupVis {     // 64 bytes: everything the coverage/depth walk needs
+    uint16_t xmin, xmax, ymin, ymax;
+    uint32_t order;
+    uint32_t kind;
+    float wstart[3];
+    float dx[3];
+    float dy[3];
+    float rvz[3];
+};
+static_assert(sizeof(SetupVis) == 64, "SetupVis must be 64 bytes");
+
+struct __align__(16) SetupShade {   // 128 bytes: everything shading needs
+    float cv[9];    // camera-space corners / z        (render.cpp:337)
+    float n[9];     // camera-space normals / z        (render.cpp:338)
+    float pay[9];   // colour: rgb/z per corner;  texture: (u/z, v/z) per corner in [0..5], dz in [6..7]
+    float tpp[2];   // texture only                    (render.cpp:350-352)
+    uint32_t kind;
+    uint32_t texture;
+    float area;     // diagnostic (dumped to tests)
+};
+static_assert(sizeof(SetupShade) == 128, "SetupShade must be 128 bytes");
+
+struct Frame {
+    // scene
+    const float *pos_x, *pos_y, *pos_z;
+    const uint32_t *vi0, *vi1, *vi2, *ai0, *ai1, *ai2;
+    const uint4 *attr;
+    const uint32_t *texels;
+    uint32_t V, Vpad, T, A, n_tex;
+    // views
+    const float *cams;  // n_views x 12
+    uint32_t n_views;
+    uint32_t W, H, y0, y1;
+    float fw, fh, half_w, half_h, factor;
+    uint32_t tiles_x, tile_row0, tiles_y, n_tiles;
+    // per-view scratch
+    float4 *rv;
+    SetupVis *vis;
+    SetupShade *shade;
+    uint32_t setup_cap;
+    uint32_t *counters;
+    uint32_t *sticky;   // [4] across chunks: overflow bits (OR), max setups, max entries, max big
+    uint32_t *tile_count, *tile_offset, *tile_cursor;
+    uint32_t tile_stride;
+    unsigned long long *entries;
+    uint32_t entry_cap;
+    uint32_t *big_list;
+    uint32_t big_cap;
+    // output
+    uint32_t *out;
+    unsigned long long out_view_stride;  // pixels
+    int use_tma;
+};
+
+// Launchers (kernels.cu).  Each returns the number of kernels it enqueued.
+int launch_geometry(const Frame &f, cudaStream_t s);   // reset, vertex stage, clip/cull/setup, binning
+int launch_raster(const Frame &f, cudaStream_t s);     // per-tile visibility + shading + write-out
+int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry
+cudaError_t configure_kernels();
+
+}  // namespace s3r

@@ -1,0 +1,622 @@
+// renderer.cu — C++ host layer and the extern "C" boundary (include/render.h, include/s3r_b200.h).
+//
+// Owns: scene conversion data.bin -> HBM layout, per-view frame scratch with capacity regrowth,
+// host camera stepping (update_camera, render-cpp/render.cpp:134-156), frame orchestration on a
+// CUDA stream, the synchronous drop-in updateAndRender (render-cpp/render.cpp:264-384) with
+// data.bin discovery via dladdr (render.cpp:161-176).  There is no CPU rendering path in here.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/render.h"
+#include "../../include/s3r_b200.h"
+#include "pipeline.cuh"
+
+using namespace s3r;
+
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            return fail(S3R_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+        }                                                                                                \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) { return cudaSuccess; }
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) { n = count; }
+        return e;
+    }
+    void release() { if (p) { cudaFree(p); } p = nullptr; n = 0; }
+};
+
+struct HostPin { const void *ptr; size_t bytes; };
+
+struct S3RRenderer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool has_scene = false;
+    uint64_t V = 0, Vpad = 0, I = 0, T = 0, A = 0, n_texels = 0;
+    DevBuf<float> pos_x, pos_y, pos_z;
+    DevBuf<uint32_t> vi[3], ai[3];
+    DevBuf<uint4> attr;
+    DevBuf<uint32_t> texels;
+    // per-view scratch
+    uint32_t views_cap = 0, tile_stride = 0;
+    uint32_t setup_cap = 0, entry_cap = 0, big_cap = 0;
+    uint32_t views_per_chunk = 256;
+    DevBuf<float4> rv;
+    DevBuf<SetupVis> vis;
+    DevBuf<SetupShade> shade;
+    DevBuf<uint32_t> sticky;
+    float factor_override = 0.f;   // drop-in path: the reference's stale-factor rule (render.cpp:276-279)
+    DevBuf<uint32_t> counters, tile_count, tile_offset, tile_cursor, big_list;
+    DevBuf<unsigned long long> entries;
+    DevBuf<float> cams;
+    DevBuf<uint32_t> frame;   // internal device framebuffer for host renders
+    float *cams_pinned = nullptr;
+    size_t cams_pinned_floats = 0;
+    cudaEvent_t cams_event = nullptr;
+    bool cams_in_flight = false;
+    // last render (for finish / dumps)
+    uint32_t last_views = 0, last_W = 0, last_H = 0;
+    uint64_t launches = 0;
+    int opt_tma = 1, opt_pin_host = 1;
+    std::vector<HostPin> pins;
+};
+
+// --------------------------------------------------------------------------------------------------
+// lifetime
+// --------------------------------------------------------------------------------------------------
+extern "C" const char *s3r_last_error(void) { return g_error.c_str(); }
+
+extern "C" int s3r_create(S3RRenderer **out, int device) {
+    if (!out) { return fail(S3R_E_ARG, "out is null"); }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        return fail(S3R_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                    " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) { return fail(S3R_E_ARG, "device index out of range"); }
+    CUDA_TRY(cudaSetDevice(device));
+    S3RRenderer *r = new S3RRenderer();
+    r->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&r->cams_event, cudaEventDisableTiming));
+    CUDA_TRY(configure_kernels());
+    *out = r;
+    return S3R_OK;
+}
+
+static void unpin_all(S3RRenderer *r) {
+    for (auto &p : r->pins) { cudaHostUnregister(const_cast<void *>(p.ptr)); }
+    r->pins.clear();
+}
+
+extern "C" void s3r_destroy(S3RRenderer *r) {
+    if (!r) { return; }
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    unpin_all(r);
+    r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
+    for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
+    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release();
+    r->counters.release(); r->tile_count.release(); r->tile_offset.release(); r->tile_cursor.release();
+    r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
+    if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
+    if (r->cams_event) { cudaEventDestroy(r->cams_event); }
+    if (r->stream) { cudaStreamDestroy(r->stream); }
+    delete r;
+}
+
+// --------------------------------------------------------------------------------------------------
+// scene: data.bin (render-cpp/render.cpp:177-209) -> HBM layout (pipeline.cuh)
+// --------------------------------------------------------------------------------------------------
+extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint64_t V, const uint64_t *vidx,
+                                     const uint64_t *aidx, uint64_t I, const void *attributes, uint64_t A,
+                                     const uint32_t *texels, uint64_t n_texels) {
+    if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
+    if (I % 3) { return fail(S3R_E_SCENE, "index count is not a multiple of 3"); }
+    if (V >= 0xFFFFFFFFull || A >= 0xFFFFFFFFull || I >= 0xFFFFFFFFull) {
+        return fail(S3R_E_SCENE, "counts exceed the reference's uint32 loop counters (render.cpp:285,290,297)");
+    }
+    if (n_texels & 0x3FFFFull) { return fail(S3R_E_SCENE, "texel count is not a multiple of 512*512"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    const uint64_t T = I / 3, Vpad = (V + 3) & ~3ull;
+    std::vector<float> px(std::max<uint64_t>(Vpad, 4), 0.f), py(px.size(), 0.f), pz(px.size(), -1.f);
+    for (uint64_t i = 0; i < V; i++) {
+        if (vertices[4 * i + 3] != 1.0f) { return fail(S3R_E_SCENE, "vertex w != 1"); }
+        px[i] = vertices[4 * i]; py[i] = vertices[4 * i + 1]; pz[i] = vertices[4 * i + 2];
+    }
+    std::vector<uint32_t> v[3], a[3];
+    for (int k = 0; k < 3; k++) { v[k].resize(std::max<uint64_t>(T, 1)); a[k].resize(std::max<uint64_t>(T, 1)); }
+    for (uint64_t t = 0; t < T; t++) {
+        for (int k = 0; k < 3; k++) {
+            const uint64_t vv = vidx[3 * t + k], aa = aidx[3 * t + k];
+            if (vv >= V || aa >= A) { return fail(S3R_E_SCENE, "index out of range"); }
+            v[k][t] = (uint32_t)vv; a[k][t] = (uint32_t)aa;
+        }
+    }
+    const uint32_t n_tex = (uint32_t)(n_texels >> 18);
+    std::vector<uint4> at(std::max<uint64_t>(2 * A, 2));
+    const uint8_t *rec = static_cast<const uint8_t *>(attributes);
+    for (uint64_t i = 0; i < A; i++) {
+        uint32_t w[12];
+        memcpy(w, rec + 48 * i, 48);
+        float nw;
+        memcpy(&nw, &w[3], 4);
+        if (nw != 0.0f) { return fail(S3R_E_SCENE, "normal w != 0"); }
+        if (w[8] > 1) { return fail(S3R_E_SCENE, "attribute kind not in {0, 1}"); }
+        if (w[8] == 1 && w[4] >= n_tex) { return fail(S3R_E_SCENE, "texture index out of range"); }
+        at[2 * i] = make_uint4(w[0], w[1], w[2], w[8]);
+        at[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    CUDA_TRY(r->pos_x.ensure(px.size())); CUDA_TRY(r->pos_y.ensure(px.size())); CUDA_TRY(r->pos_z.ensure(px.size()));
+    CUDA_TRY(cudaMemcpy(r->pos_x.p, px.data(), px.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->pos_y.p, py.data(), py.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->pos_z.p, pz.data(), pz.size() * 4, cudaMemcpyHostToDevice));
+    for (int k = 0; k < 3; k++) {
+        CUDA_TRY(r->vi[k].ensure(v[k].size())); CUDA_TRY(r->ai[k].ensure(a[k].size()));
+        CUDA_TRY(cudaMemcpy(r->vi[k].p, v[k].data(), v[k].size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->ai[k].p, a[k].data(), a[k].size() * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(r->attr.ensure(at.size()));
+    CUDA_TRY(cudaMemcpy(r->attr.p, at.data(), at.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CUDA_TRY(r->texels.ensure(std::max<uint64_t>(n_texels, 1)));
+    if (n_texels) { CUDA_TRY(cudaMemcpy(r->texels.p, texels, n_texels * 4, cudaMemcpyHostToDevice)); }
+    r->V = V; r->Vpad = px.size(); r->I = I; r->T = T; r->A = A; r->n_texels = n_texels;
+    r->has_scene = true;
+    r->views_cap = 0;  // scratch is re-sized on the next render
+    return S3R_OK;
+}
+
+extern "C" int s3r_load_scene_file(S3RRenderer *r, const char *path) {
+    if (!r || !path) { return fail(S3R_E_ARG, "null argument"); }
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { return fail(S3R_E_IO, std::string("cannot open ") + path); }
+    fseek(fp, 0, SEEK_END);
+    const long size = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint64_t> raw((size_t)size / 8 + 2, 0);  // 8-byte aligned backing store
+    const size_t got = fread(raw.data(), 1, (size_t)size, fp);
+    fclose(fp);
+    if (got != (size_t)size) { return fail(S3R_E_IO, "short read"); }
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(raw.data());
+    size_t off = 0;
+    auto header = [&](uint64_t &n) -> bool {
+        if (off + 16 > (size_t)size) { return false; }
+        memcpy(&n, b + off, 8);  // second word ignored, render.cpp:178-179
+        off += 16;
+        return true;
+    };
+    uint64_t V, I, A, I2, NT;
+    if (!header(V) || off + V * 16 > (size_t)size) { return fail(S3R_E_IO, "truncated vertex section"); }
+    const float *vertices = reinterpret_cast<const float *>(b + off); off += V * 16;
+    if (!header(I) || off + (I + (I & 1)) * 8 > (size_t)size) { return fail(S3R_E_IO, "truncated index section"); }
+    const uint64_t *vidx = reinterpret_cast<const uint64_t *>(b + off); off += (I + (I & 1)) * 8;
+    if (!header(A) || off + A * 48 > (size_t)size) { return fail(S3R_E_IO, "truncated attribute section"); }
+    const void *attrs = b + off; off += A * 48;
+    if (!header(I2) || off + (I2 + (I2 & 1)) * 8 > (size_t)size) { return fail(S3R_E_IO, "truncated attribute-index section"); }
+    const uint64_t *aidx = reinterpret_cast<const uint64_t *>(b + off); off += (I2 + (I2 & 1)) * 8;
+    if (I2 != I) { return fail(S3R_E_SCENE, "index streams differ in length"); }
+    if (!header(NT) || off + NT * 4 > (size_t)size) { return fail(S3R_E_IO, "truncated texture section"); }
+    const uint32_t *texels = reinterpret_cast<const uint32_t *>(b + off);
+    return s3r_load_scene_arrays(r, vertices, V, vidx, aidx, I, attrs, A, texels, NT);
+}
+
+extern "C" int s3r_scene_counts(const S3RRenderer *r, uint64_t *v, uint64_t *i, uint64_t *a, uint64_t *t) {
+    if (!r || !r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
+    if (v) { *v = r->V; } if (i) { *i = r->I; } if (a) { *a = r->A; } if (t) { *t = r->n_texels; }
+    return S3R_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// camera — render-cpp/render.cpp:51-65 (initial state), :134-156 (update_camera); scalar binary32
+// in the reference's evaluation order (simd semantics as pinned by the oracle shim).
+// --------------------------------------------------------------------------------------------------
+namespace {
+struct V3 { float x, y, z; };
+inline V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 add(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 mul(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline V3 unit(V3 a) { return mul(a, 1.0f / sqrtf(dot(a, a))); }
+inline V3 ld(const float *p) { return mk(p[0], p[1], p[2]); }
+inline void st(float *p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+inline V3 rotate(V3 qv, float qw, V3 v) {  // simd_act
+    const V3 t = mul(cross(qv, v), 2.f);
+    return add(add(v, mul(t, qw)), cross(qv, t));
+}
+}  // namespace
+
+extern "C" void s3r_camera_reset(S3RCamera *cam) {
+    memset(cam, 0, sizeof(*cam));
+    cam->axis_x[0] = cam->axis_y[1] = cam->axis_z[2] = 1.f;
+    cam->matrix[0] = cam->matrix[5] = cam->matrix[10] = 1.f;
+}
+
+extern "C" void s3r_camera_update(S3RCamera *cam, const S3RInput *in) {
+    const float speed = 0.1f, rotation_speed = 0.3f;  // render.cpp:94-95
+    bool changed = false;
+    V3 pos = ld(cam->position), X = ld(cam->axis_x), Y = ld(cam->axis_y), Z = ld(cam->axis_z);
+    if (in->left > 0 || in->right > 0 || in->up > 0 || in->down > 0) {
+        changed = true;
+        const V3 step = add(mul(X, in->right - in->left), mul(Z, in->down - in->up));
+        pos = add(pos, mul(step, speed));
+    }
+    if (in->mouse_x != cam->mouse[0] || in->mouse_y != cam->mouse[1]) {
+        changed = true;
+        const V3 z = unit(add(add(mul(X, cam->mouse[0] - in->mouse_x), mul(Y, cam->mouse[1] - in->mouse_y)),
+                              mul(Z, 100 / rotation_speed)));
+        V3 qv;
+        float qw;
+        if (dot(Z, z) >= 0.f) {
+            const V3 half = unit(add(Z, z));
+            qv = cross(Z, half);
+            qw = dot(Z, half);
+        } else {  // obtuse turn in one frame: two half rotations
+            V3 half = unit(add(Z, z));
+            if (!(dot(half, half) > 0.f)) {
+                half = unit(cross(Z, fabsf(Z.x) < fabsf(Z.y) ? mk(1, 0, 0) : mk(0, 1, 0)));
+            }
+            const V3 pv = cross(half, z), sv = cross(Z, half);
+            const float pw = dot(half, z), sw = dot(Z, half);
+            qv = add(add(mul(sv, pw), mul(pv, sw)), cross(pv, sv));
+            qw = pw * sw - dot(pv, sv);
+        }
+        X = unit(rotate(qv, qw, X));
+        Y = unit(rotate(qv, qw, Y));
+        Z = z;
+        cam->mouse[0] = in->mouse_x;
+        cam->mouse[1] = in->mouse_y;
+    }
+    if (changed || !cam->started) {
+        st(cam->matrix + 0, X); cam->matrix[3] = -dot(X, pos);
+        st(cam->matrix + 4, Y); cam->matrix[7] = -dot(Y, pos);
+        st(cam->matrix + 8, Z); cam->matrix[11] = -dot(Z, pos);
+    }
+    cam->started = 1;
+    st(cam->position, pos); st(cam->axis_x, X); st(cam->axis_y, Y); st(cam->axis_z, Z);
+}
+
+extern "C" float s3r_factor(uint32_t height) { return kNear * (float)height / (2 * kScale); }
+
+// --------------------------------------------------------------------------------------------------
+// frame scratch
+// --------------------------------------------------------------------------------------------------
+static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
+    const uint32_t T = (uint32_t)r->T;
+    if (r->setup_cap == 0) {
+        // survivors are usually a small share of 2T; start at T/4 (min 4096) and regrow on demand
+        r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * T + 16, std::max<uint64_t>(4096, T / 4));
+        r->entry_cap = std::max<uint32_t>(16384, r->setup_cap * 4u);
+        r->big_cap = std::max<uint32_t>(1024, r->setup_cap / 16u);
+    }
+    const uint32_t tile_stride = ((n_tiles + 1 + 63) / 64) * 64;
+    if (views > r->views_cap || tile_stride > r->tile_stride) {
+        r->views_cap = std::max(views, r->views_cap);
+        r->tile_stride = std::max(tile_stride, r->tile_stride);
+    }
+    const size_t vc = r->views_cap;
+    CUDA_TRY(r->rv.ensure(vc * r->Vpad));
+    CUDA_TRY(r->vis.ensure(vc * r->setup_cap));
+    CUDA_TRY(r->shade.ensure(vc * r->setup_cap));
+    CUDA_TRY(r->counters.ensure(vc * C_COUNT));
+    if (!r->sticky.p) { CUDA_TRY(r->sticky.ensure(4)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 16)); }
+    CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
+    CUDA_TRY(r->tile_offset.ensure(vc * r->tile_stride));
+    CUDA_TRY(r->tile_cursor.ensure(vc * r->tile_stride));
+    CUDA_TRY(r->entries.ensure(vc * r->entry_cap));
+    CUDA_TRY(r->big_list.ensure(vc * r->big_cap));
+    CUDA_TRY(r->cams.ensure(vc * 12));
+    if (r->cams_pinned_floats < vc * 12) {
+        if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
+        CUDA_TRY(cudaMallocHost(&r->cams_pinned, vc * 12 * sizeof(float)));
+        r->cams_pinned_floats = vc * 12;
+    }
+    return S3R_OK;
+}
+
+static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H, uint32_t y0,
+                        uint32_t y1, uint32_t *dev_out, cudaStream_t s) {
+    Frame f;
+    memset(&f, 0, sizeof(f));
+    f.tiles_x = (W + TILE_W - 1) / TILE_W;
+    f.tile_row0 = y0 / TILE_H;
+    f.tiles_y = (y1 - 1) / TILE_H - f.tile_row0 + 1;
+    f.n_tiles = f.tiles_x * f.tiles_y;
+    int rc = ensure_scratch(r, n_views, f.n_tiles);
+    if (rc) { return rc; }
+    if (r->cams_in_flight) { CUDA_TRY(cudaEventSynchronize(r->cams_event)); }
+    memcpy(r->cams_pinned, cams, (size_t)n_views * 12 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(r->cams.p, r->cams_pinned, (size_t)n_views * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(r->cams_event, s));
+    r->cams_in_flight = true;
+
+    f.pos_x = r->pos_x.p; f.pos_y = r->pos_y.p; f.pos_z = r->pos_z.p;
+    f.vi0 = r->vi[0].p; f.vi1 = r->vi[1].p; f.vi2 = r->vi[2].p;
+    f.ai0 = r->ai[0].p; f.ai1 = r->ai[1].p; f.ai2 = r->ai[2].p;
+    f.attr = r->attr.p; f.texels = r->texels.p;
+    f.V = (uint32_t)r->V; f.Vpad = (uint32_t)r->Vpad; f.T = (uint32_t)r->T; f.A = (uint32_t)r->A;
+    f.n_tex = std::max<uint32_t>(1, (uint32_t)(r->n_texels >> 18));
+    f.cams = r->cams.p; f.n_views = n_views;
+    f.W = W; f.H = H; f.y0 = y0; f.y1 = y1;
+    f.fw = (float)W; f.fh = (float)H; f.half_w = f.fw / 2; f.half_h = f.fh / 2;  // screen_size / 2, render.cpp:284,288
+    f.factor = r->factor_override != 0.f ? r->factor_override : s3r_factor(H);
+    f.rv = r->rv.p; f.vis = r->vis.p; f.shade = r->shade.p; f.setup_cap = r->setup_cap;
+    f.counters = r->counters.p;
+    f.sticky = r->sticky.p;
+    f.tile_count = r->tile_count.p; f.tile_offset = r->tile_offset.p; f.tile_cursor = r->tile_cursor.p;
+    f.tile_stride = r->tile_stride;
+    f.entries = r->entries.p; f.entry_cap = r->entry_cap;
+    f.big_list = r->big_list.p; f.big_cap = r->big_cap;
+    f.out = dev_out; f.out_view_stride = (unsigned long long)W * (y1 - y0);
+    f.use_tma = r->opt_tma && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
+    r->launches += (uint64_t)launch_geometry(f, s);
+    r->launches += (uint64_t)launch_raster(f, s);
+    CUDA_TRY(cudaGetLastError());
+    return S3R_OK;
+}
+
+extern "C" int s3r_render_device(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
+                                 uint32_t y0, uint32_t y1, uint32_t *dev_out, void *stream) {
+    if (!r || !cams || !dev_out) { return fail(S3R_E_ARG, "null argument"); }
+    if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
+    if (W == 0 || H == 0 || W > 65535 || H > 65535 || y0 >= y1 || y1 > H || n_views == 0) {
+        return fail(S3R_E_ARG, "bad frame geometry");
+    }
+    CUDA_TRY(cudaSetDevice(r->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
+    const size_t view_px = (size_t)W * (y1 - y0);
+    for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
+        const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
+        int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, dev_out + view_px * v0, s);
+        if (rc) { return rc; }
+        r->last_views = nv;
+    }
+    r->last_W = W; r->last_H = H;
+    return S3R_OK;
+}
+
+// Waits for the renderer's work, reads the per-view counters back and regrows capacities.
+// Returns 1 if something overflowed (the frame(s) of the last chunk must be rendered again).
+static int finish_on(S3RRenderer *r, cudaStream_t s) {
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (r->last_views == 0 || !r->sticky.p) { return S3R_OK; }
+    uint32_t sticky[4];
+    CUDA_TRY(cudaMemcpy(sticky, r->sticky.p, sizeof(sticky), cudaMemcpyDeviceToHost));
+    const uint32_t overflow = sticky[0], need_setups = sticky[1], need_entries = sticky[2], need_big = sticky[3];
+    if (!overflow) { return S3R_OK; }
+    CUDA_TRY(cudaMemset(r->sticky.p, 0, sizeof(sticky)));
+    if (overflow & 1u) {
+        r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * r->T + 16, (uint64_t)need_setups + need_setups / 2 + 1024);
+        r->entry_cap = std::max(r->entry_cap, r->setup_cap * 4u);
+        r->big_cap = std::max(r->big_cap, r->setup_cap / 16u);
+        // vis/shade are view-strided by setup_cap: force reallocation
+        r->vis.release(); r->shade.release(); r->entries.release(); r->big_list.release();
+    }
+    if (overflow & 2u) { r->entry_cap = std::max(r->entry_cap, need_entries + need_entries / 2 + 1024); r->entries.release(); }
+    if (overflow & 4u) { r->big_cap = std::max(r->big_cap, need_big + need_big / 2 + 64); r->big_list.release(); }
+    return 1;
+}
+
+extern "C" int s3r_finish(S3RRenderer *r) {
+    if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
+    return finish_on(r, r->stream);
+}
+
+static bool pin_host(S3RRenderer *r, const void *ptr, size_t bytes) {
+    if (!r->opt_pin_host) { return false; }
+    for (auto &p : r->pins) {
+        if (p.ptr == ptr && p.bytes >= bytes) { return true; }
+    }
+    // a new buffer (or a resize, main.swift:156-165): drop stale registrations that overlap it
+    for (size_t i = 0; i < r->pins.size();) {
+        const char *a = static_cast<const char *>(r->pins[i].ptr), *b = static_cast<const char *>(ptr);
+        if (a < b + bytes && b < a + r->pins[i].bytes) {
+            cudaHostUnregister(const_cast<void *>(r->pins[i].ptr));
+            r->pins.erase(r->pins.begin() + (long)i);
+        } else {
+            i++;
+        }
+    }
+    if (r->pins.size() >= 8) { unpin_all(r); }
+    if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();  // clear; fall back to a pageable copy
+        return false;
+    }
+    r->pins.push_back(HostPin{ptr, bytes});
+    return true;
+}
+
+extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
+                               uint32_t y0, uint32_t y1, uint32_t *host_out) {
+    if (!r || !cams || !host_out) { return fail(S3R_E_ARG, "null argument"); }
+    if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
+    if (W == 0 || H == 0 || y0 >= y1 || y1 > H) { return fail(S3R_E_ARG, "bad frame geometry"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    const size_t view_px = (size_t)W * (y1 - y0);
+    pin_host(r, host_out, view_px * n_views * 4);
+    for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
+        const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
+        CUDA_TRY(r->frame.ensure(view_px * nv));
+        for (int attempt = 0; attempt < 8; attempt++) {
+            int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream);
+            if (rc) { return rc; }
+            r->last_views = nv; r->last_W = W; r->last_H = H;
+            CUDA_TRY(cudaMemcpyAsync(host_out + view_px * v0, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost, r->stream));
+            rc = finish_on(r, r->stream);
+            if (rc < 0) { return rc; }
+            if (rc == 0) { break; }
+        }
+    }
+    return S3R_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// introspection
+// --------------------------------------------------------------------------------------------------
+extern "C" int s3r_get_stats(S3RRenderer *r, uint32_t view, S3RStats *out) {
+    if (!r || !out) { return fail(S3R_E_ARG, "null argument"); }
+    if (view >= r->last_views) { return fail(S3R_E_ARG, "view out of range"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    uint32_t c[C_COUNT];
+    CUDA_TRY(cudaMemcpy(c, r->counters.p + (size_t)view * C_COUNT, sizeof(c), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->triangles_in = (uint32_t)r->T;
+    out->near_rejected = c[C_NEAR]; out->clipped = c[C_CLIPPED]; out->spawned = c[C_SPAWNED]; out->culled = c[C_CULLED];
+    out->setups = c[C_SETUPS]; out->bin_entries = c[C_ENTRIES]; out->big_triangles = c[C_BIG]; out->overflow = c[C_OVERFLOW];
+    return S3R_OK;
+}
+
+extern "C" int s3r_dump_raster_vertices(S3RRenderer *r, uint32_t view, float *out, uint64_t cap) {
+    if (!r || !out) { return fail(S3R_E_ARG, "null argument"); }
+    if (view >= r->last_views || cap < r->V) { return fail(S3R_E_ARG, "view/capacity out of range"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaMemcpy(out, r->rv.p + (size_t)view * r->Vpad, r->V * sizeof(float4), cudaMemcpyDeviceToHost));
+    return S3R_OK;
+}
+
+extern "C" int s3r_dump_setups(S3RRenderer *r, uint32_t view, S3RSetupDump *out, uint64_t cap, uint64_t *count) {
+    if (!r || !count) { return fail(S3R_E_ARG, "null argument"); }
+    if (view >= r->last_views) { return fail(S3R_E_ARG, "view out of range"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    uint32_t n = 0;
+    CUDA_TRY(cudaMemcpy(&n, r->counters.p + (size_t)view * C_COUNT + C_SETUPS, 4, cudaMemcpyDeviceToHost));
+    n = std::min(n, r->setup_cap);
+    *count = n;
+    if (!out || n == 0) { return S3R_OK; }
+    std::vector<SetupVis> v(n);
+    std::vector<SetupShade> s(n);
+    CUDA_TRY(cudaMemcpy(v.data(), r->vis.p + (size_t)view * r->setup_cap, n * sizeof(SetupVis), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s.data(), r->shade.p + (size_t)view * r->setup_cap, n * sizeof(SetupShade), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> idx(n);
+    for (uint32_t i = 0; i < n; i++) { idx[i] = i; }
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return v[a].order < v[b].order; });
+    for (uint64_t k = 0; k < std::min<uint64_t>(n, cap); k++) {
+        const SetupVis &a = v[idx[k]];
+        const SetupShade &b = s[idx[k]];
+        S3RSetupDump &o = out[k];
+        memset(&o, 0, sizeof(o));
+        o.order = a.order; o.xmin = a.xmin; o.xmax = a.xmax; o.ymin = a.ymin; o.ymax = a.ymax; o.area = b.area;
+        for (int c = 0; c < 3; c++) {
+            o.wstart[c] = a.wstart[c]; o.dx[c] = a.dx[c]; o.dy[c] = a.dy[c]; o.rvz[c] = a.rvz[c];
+            for (int e = 0; e < 3; e++) { o.cv[c][e] = b.cv[3 * c + e]; o.n[c][e] = b.n[3 * c + e]; }
+        }
+        o.kind = b.kind; o.texture = b.texture;
+        if (b.kind == 0) {
+            for (int c = 0; c < 3; c++) { for (int e = 0; e < 3; e++) { o.payload[c][e] = b.pay[3 * c + e]; } }
+        } else {
+            for (int c = 0; c < 3; c++) { o.payload[c][0] = b.pay[2 * c]; o.payload[c][1] = b.pay[2 * c + 1]; }
+            o.dz[0] = b.pay[6]; o.dz[1] = b.pay[7]; o.tpp[0] = b.tpp[0]; o.tpp[1] = b.tpp[1];
+        }
+    }
+    return S3R_OK;
+}
+
+extern "C" uint64_t s3r_kernel_launches(const S3RRenderer *r) { return r ? r->launches : 0; }
+
+extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
+    if (!r || !name) { return fail(S3R_E_ARG, "null argument"); }
+    if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
+    if (!strcmp(name, "pin_host")) { r->opt_pin_host = value != 0; if (!value) { unpin_all(r); } return S3R_OK; }
+    if (!strcmp(name, "views_per_chunk")) {
+        if (value < 1) { return fail(S3R_E_ARG, "views_per_chunk < 1"); }
+        r->views_per_chunk = (uint32_t)value;
+        return S3R_OK;
+    }
+    if (!strcmp(name, "setup_capacity")) {  // test hook: force the regrow path
+        if (value < 1) { return fail(S3R_E_ARG, "setup_capacity < 1"); }
+        cudaStreamSynchronize(r->stream);
+        r->setup_cap = (uint32_t)value; r->entry_cap = std::max<uint32_t>(64, (uint32_t)value); r->big_cap = 4;
+        r->vis.release(); r->shade.release(); r->entries.release(); r->big_list.release();
+        return S3R_OK;
+    }
+    return fail(S3R_E_ARG, std::string("unknown option ") + name);
+}
+
+// --------------------------------------------------------------------------------------------------
+// the drop-in entry point — render-cpp/render.cpp:264-384
+// --------------------------------------------------------------------------------------------------
+namespace {
+S3RRenderer *g_renderer = nullptr;
+S3RCamera g_camera;
+uint32_t g_depth_bytes = 0;   // depth_buffer.buffer_size, render.cpp:67-73
+
+void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared object)
+    int device = 0;
+    if (const char *env = getenv("S3R_DEVICE")) { device = atoi(env); }
+    if (s3r_create(&g_renderer, device) != S3R_OK) {
+        fprintf(stderr, "render.so: %s\n", s3r_last_error());
+        exit(70);
+    }
+    Dl_info info;
+    char path[PATH_MAX + 64];
+    path[0] = 0;
+    if (dladdr(reinterpret_cast<const void *>(&updateAndRender), &info) && info.dli_fname) {
+        strncpy(path, info.dli_fname, PATH_MAX);
+        path[PATH_MAX] = 0;
+    }
+    char *slash = strrchr(path, '/');
+    if (!slash) { strcpy(path, "./"); slash = path + 1; }
+    const char *candidates[3] = {"/data.bin", "/Resources/data.bin", "/../data-generator/data.bin"};
+    for (const char *c : candidates) {
+        strcpy(slash, c);
+        FILE *fp = fopen(path, "rb");
+        if (fp) {
+            fclose(fp);
+            if (s3r_load_scene_file(g_renderer, path) != S3R_OK) {
+                fprintf(stderr, "render.so: %s: %s\n", path, s3r_last_error());
+                exit(70);
+            }
+            s3r_camera_reset(&g_camera);
+            return;
+        }
+    }
+    exit(666);  // render.cpp:173
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) void updateAndRender(const PixelData *pixel_data, const Input *input) {
+    if (!g_renderer) { drop_in_initialize(); }
+    S3RInput in{input->up, input->down, input->left, input->right, input->mouse[0], input->mouse[1]};
+    s3r_camera_update(&g_camera, &in);  // the first call forces the matrix rebuild (render.cpp:267-270)
+    // render.cpp:275-280: factor is refreshed only when width * height * 4 changes (hazard H8)
+    const uint32_t depth_bytes = pixel_data->width * pixel_data->height * (uint32_t)sizeof(float);
+    if (g_depth_bytes != depth_bytes) {
+        g_depth_bytes = depth_bytes;
+        g_renderer->factor_override = s3r_factor(pixel_data->height);
+    }
+    // render.cpp:281-282 clears bufferSize bytes; we write width * height pixels (== bufferSize / 4, main.swift:163)
+    if (s3r_render_host(g_renderer, g_camera.matrix, 1, pixel_data->width, pixel_data->height, 0, pixel_data->height,
+                        pixel_data->buffer) != S3R_OK) {
+        fprintf(stderr, "render.so: %s\n", s3r_last_error());
+        exit(70);
+    }
+}
