@@ -115,9 +115,20 @@ S3R_API int s3r_dump_raster_vertices(S3RRenderer *r, uint32_t view, float *out_x
 /* surviving triangles of the last render of `view`, sorted by order key; *count receives the total */
 S3R_API int s3r_dump_setups(S3RRenderer *r, uint32_t view, S3RSetupDump *out, uint64_t capacity, uint64_t *count);
 S3R_API uint64_t s3r_kernel_launches(const S3RRenderer *r);   /* kernels launched by this renderer so far */
+/* CUDA-event time accumulated per stage since the last reset (needs option "timing" = 1): the
+ * geometry kernels (reset .. bin fill) and the tile rasteriser, measured on the launching stream;
+ * *chunks = number of (multi-view) submissions covered. */
+S3R_API int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raster_ms, uint64_t *chunks, int reset);
 S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
 /* options: "tma_store" (1 = cp.async.bulk tile write-out, default; 0 = plain stores),
- *          "fused_small" (1 = single-CTA geometry for small scenes, default), "views_per_chunk" */
+ *          "pin_host" (1 = cudaHostRegister the caller's frame buffers; default 0 — only for callers that
+ *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
+ *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
+ *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */
+
+/* Harness-only: resets the camera owned by updateAndRender (include/render.h) to the reference's
+ * initial state so that the same Input script can be replayed; scene and buffers stay loaded. */
+S3R_API void s3r_dropin_reset(void);
 
 #ifdef __cplusplus
 }

@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_co
     const uint32_t row = tid / SEGS_PER_ROW, seg = tid % SEGS_PER_ROW;
     const uint32_t y = ty0 + row, sx0 = tx0 + seg * SEG;
 
+    // A capacity overflow anywhere upstream makes the bin lists incomplete: the host regrows the
+    // buffers and renders the frame again, so this launch only has to stay in bounds.
+    if (f.counters[view * C_COUNT + C_OVERFLOW] != 0) { return; }
     const uint32_t *toff = f.tile_offset + view * f.tile_stride;
     const uint32_t begin = toff[tile], n = toff[tile + 1] - begin;
     unsigned long long *list = f.entries + (size_t)view * f.entry_cap + begin;

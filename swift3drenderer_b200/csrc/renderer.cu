@@ -75,14 +75,20 @@ struct S3RRenderer {
     DevBuf<unsigned long long> entries;
     DevBuf<float> cams;
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders
-    float *cams_pinned = nullptr;
-    size_t cams_pinned_floats = 0;
-    cudaEvent_t cams_event = nullptr;
-    bool cams_in_flight = false;
+    // submission ring: pinned camera staging + events, so the host can run RING chunks ahead
+    static constexpr int RING = 16;
+    float *cams_pinned = nullptr;     // RING x views_cap x 12
+    size_t cams_pinned_views = 0;
+    cudaEvent_t ev_cams[RING] = {}, ev_t0[RING] = {}, ev_t1[RING] = {}, ev_t2[RING] = {};
+    bool slot_used[RING] = {}, slot_timed[RING] = {};
+    uint64_t chunk_counter = 0;
+    int opt_timing = 0;
+    double geometry_ms = 0, raster_ms = 0;
+    uint64_t timed_chunks = 0;
     // last render (for finish / dumps)
     uint32_t last_views = 0, last_W = 0, last_H = 0;
     uint64_t launches = 0;
-    int opt_tma = 1, opt_pin_host = 1;
+    int opt_tma = 1, opt_pin_host = 0;   // pinning caller memory is opt-in: see pin_host()
     std::vector<HostPin> pins;
 };
 
@@ -105,7 +111,10 @@ extern "C" int s3r_create(S3RRenderer **out, int device) {
     S3RRenderer *r = new S3RRenderer();
     r->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&r->cams_event, cudaEventDisableTiming));
+    for (int i = 0; i < S3RRenderer::RING; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&r->ev_cams[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&r->ev_t0[i])); CUDA_TRY(cudaEventCreate(&r->ev_t1[i])); CUDA_TRY(cudaEventCreate(&r->ev_t2[i]));
+    }
     CUDA_TRY(configure_kernels());
     *out = r;
     return S3R_OK;
@@ -127,7 +136,9 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     r->counters.release(); r->tile_count.release(); r->tile_offset.release(); r->tile_cursor.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
-    if (r->cams_event) { cudaEventDestroy(r->cams_event); }
+    for (int i = 0; i < S3RRenderer::RING; i++) {
+        if (r->ev_cams[i]) { cudaEventDestroy(r->ev_cams[i]); cudaEventDestroy(r->ev_t0[i]); cudaEventDestroy(r->ev_t1[i]); cudaEventDestroy(r->ev_t2[i]); }
+    }
     if (r->stream) { cudaStreamDestroy(r->stream); }
     delete r;
 }
@@ -317,6 +328,10 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
         r->entry_cap = std::max<uint32_t>(16384, r->setup_cap * 4u);
         r->big_cap = std::max<uint32_t>(1024, r->setup_cap / 16u);
     }
+    {   // a small scene can put every triangle into every tile: make that case fit up front
+        const uint64_t worst = std::min<uint64_t>(2ull * T + 16, 256) * n_tiles;
+        if (worst > r->entry_cap) { r->entry_cap = (uint32_t)std::min<uint64_t>(worst, 0x7FFFFFFFull); }
+    }
     const uint32_t tile_stride = ((n_tiles + 1 + 63) / 64) * 64;
     if (views > r->views_cap || tile_stride > r->tile_stride) {
         r->views_cap = std::max(views, r->views_cap);
@@ -334,10 +349,11 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     CUDA_TRY(r->entries.ensure(vc * r->entry_cap));
     CUDA_TRY(r->big_list.ensure(vc * r->big_cap));
     CUDA_TRY(r->cams.ensure(vc * 12));
-    if (r->cams_pinned_floats < vc * 12) {
+    if (r->cams_pinned_views < vc) {
+        CUDA_TRY(cudaStreamSynchronize(r->stream));
         if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
-        CUDA_TRY(cudaMallocHost(&r->cams_pinned, vc * 12 * sizeof(float)));
-        r->cams_pinned_floats = vc * 12;
+        CUDA_TRY(cudaMallocHost(&r->cams_pinned, (size_t)S3RRenderer::RING * vc * 12 * sizeof(float)));
+        r->cams_pinned_views = vc;
     }
     return S3R_OK;
 }
@@ -352,11 +368,24 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.n_tiles = f.tiles_x * f.tiles_y;
     int rc = ensure_scratch(r, n_views, f.n_tiles);
     if (rc) { return rc; }
-    if (r->cams_in_flight) { CUDA_TRY(cudaEventSynchronize(r->cams_event)); }
-    memcpy(r->cams_pinned, cams, (size_t)n_views * 12 * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(r->cams.p, r->cams_pinned, (size_t)n_views * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaEventRecord(r->cams_event, s));
-    r->cams_in_flight = true;
+    const int slot = (int)(r->chunk_counter++ % S3RRenderer::RING);
+    if (r->slot_used[slot]) {  // the chunk that used this slot RING submissions ago
+        CUDA_TRY(cudaEventSynchronize(r->ev_cams[slot]));
+        if (r->slot_timed[slot]) {
+            CUDA_TRY(cudaEventSynchronize(r->ev_t2[slot]));
+            float g = 0, q = 0;
+            cudaEventElapsedTime(&g, r->ev_t0[slot], r->ev_t1[slot]);
+            cudaEventElapsedTime(&q, r->ev_t1[slot], r->ev_t2[slot]);
+            r->geometry_ms += g; r->raster_ms += q; r->timed_chunks++;
+            r->slot_timed[slot] = false;
+        }
+    }
+    float *staging = r->cams_pinned + (size_t)slot * r->cams_pinned_views * 12;
+    memcpy(staging, cams, (size_t)n_views * 12 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(r->cams.p, staging, (size_t)n_views * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));
+    r->slot_used[slot] = true;
+    const bool timed = r->opt_timing != 0;
 
     f.pos_x = r->pos_x.p; f.pos_y = r->pos_y.p; f.pos_z = r->pos_z.p;
     f.vi0 = r->vi[0].p; f.vi1 = r->vi[1].p; f.vi2 = r->vi[2].p;
@@ -377,8 +406,11 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out; f.out_view_stride = (unsigned long long)W * (y1 - y0);
     f.use_tma = r->opt_tma && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
+    if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
     r->launches += (uint64_t)launch_geometry(f, s);
+    if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
     r->launches += (uint64_t)launch_raster(f, s);
+    if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t2[slot], s)); r->slot_timed[slot] = true; }
     CUDA_TRY(cudaGetLastError());
     return S3R_OK;
 }
@@ -431,6 +463,11 @@ extern "C" int s3r_finish(S3RRenderer *r) {
     return finish_on(r, r->stream);
 }
 
+// OPT-IN ("pin_host" option / S3R_PIN_HOST=1): cudaHostRegister the caller's frame buffer so the D2H
+// copy runs at full PCIe rate.  Only safe when the caller keeps that allocation mapped for as long
+// as it passes it (the reference's main loop does: one double buffer, re-allocated on resize only,
+// main.swift:156-165).  A registration that outlives its memory poisons every later CUDA call that
+// touches a host pointer in the recycled range, so it is never done behind the caller's back.
 static bool pin_host(S3RRenderer *r, const void *ptr, size_t bytes) {
     if (!r->opt_pin_host) { return false; }
     for (auto &p : r->pins) {
@@ -455,6 +492,20 @@ static bool pin_host(S3RRenderer *r, const void *ptr, size_t bytes) {
     return true;
 }
 
+// A registration made for a caller's buffer goes stale if the caller unmaps that memory and later
+// gets the same virtual address back (free + malloc of a large block): the DMA would then land in
+// the old, still-pinned physical pages.  Pixels always have a zero top byte (0x00RRGGBB), so a
+// sentinel with a non-zero top byte written by the CPU before the copy and still present after it
+// proves that the copy did not reach the memory the CPU sees.
+static const uint32_t kSentinel = 0xA5C3A5C3u;
+
+static void plant_sentinels(uint32_t *dst, size_t n) {
+    dst[0] = kSentinel; dst[n / 2] = kSentinel; dst[n - 1] = kSentinel;
+}
+static bool sentinels_gone(const uint32_t *dst, size_t n) {
+    return dst[0] != kSentinel && dst[n / 2] != kSentinel && dst[n - 1] != kSentinel;
+}
+
 extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
                                uint32_t y0, uint32_t y1, uint32_t *host_out) {
     if (!r || !cams || !host_out) { return fail(S3R_E_ARG, "null argument"); }
@@ -462,18 +513,27 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
     if (W == 0 || H == 0 || y0 >= y1 || y1 > H) { return fail(S3R_E_ARG, "bad frame geometry"); }
     CUDA_TRY(cudaSetDevice(r->device));
     const size_t view_px = (size_t)W * (y1 - y0);
-    pin_host(r, host_out, view_px * n_views * 4);
+    const bool pinned = pin_host(r, host_out, view_px * n_views * 4);
     for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
         const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
+        uint32_t *dst = host_out + view_px * v0;
         CUDA_TRY(r->frame.ensure(view_px * nv));
         for (int attempt = 0; attempt < 8; attempt++) {
             int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream);
             if (rc) { return rc; }
             r->last_views = nv; r->last_W = W; r->last_H = H;
-            CUDA_TRY(cudaMemcpyAsync(host_out + view_px * v0, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost, r->stream));
+            if (pinned) { plant_sentinels(dst, view_px * nv); }
+            CUDA_TRY(cudaMemcpyAsync(dst, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost, r->stream));
             rc = finish_on(r, r->stream);
             if (rc < 0) { return rc; }
-            if (rc == 0) { break; }
+            if (rc == 0) {
+                if (pinned && !sentinels_gone(dst, view_px * nv)) {
+                    // stale registration: drop every pin and copy again through the pageable path
+                    unpin_all(r);
+                    CUDA_TRY(cudaMemcpy(dst, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost));
+                }
+                break;
+            }
         }
     }
     return S3R_OK;
@@ -542,9 +602,30 @@ extern "C" int s3r_dump_setups(S3RRenderer *r, uint32_t view, S3RSetupDump *out,
 
 extern "C" uint64_t s3r_kernel_launches(const S3RRenderer *r) { return r ? r->launches : 0; }
 
+extern "C" int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raster_ms, uint64_t *chunks, int reset) {
+    if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    for (int slot = 0; slot < S3RRenderer::RING; slot++) {  // drain the chunks still in the ring
+        if (r->slot_timed[slot]) {
+            CUDA_TRY(cudaEventSynchronize(r->ev_t2[slot]));
+            float g = 0, q = 0;
+            cudaEventElapsedTime(&g, r->ev_t0[slot], r->ev_t1[slot]);
+            cudaEventElapsedTime(&q, r->ev_t1[slot], r->ev_t2[slot]);
+            r->geometry_ms += g; r->raster_ms += q; r->timed_chunks++;
+            r->slot_timed[slot] = false;
+        }
+    }
+    if (geometry_ms) { *geometry_ms = r->geometry_ms; }
+    if (raster_ms) { *raster_ms = r->raster_ms; }
+    if (chunks) { *chunks = r->timed_chunks; }
+    if (reset) { r->geometry_ms = r->raster_ms = 0; r->timed_chunks = 0; }
+    return S3R_OK;
+}
+
 extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!r || !name) { return fail(S3R_E_ARG, "null argument"); }
     if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
+    if (!strcmp(name, "timing")) { r->opt_timing = value != 0; return S3R_OK; }
     if (!strcmp(name, "pin_host")) { r->opt_pin_host = value != 0; if (!value) { unpin_all(r); } return S3R_OK; }
     if (!strcmp(name, "views_per_chunk")) {
         if (value < 1) { return fail(S3R_E_ARG, "views_per_chunk < 1"); }
@@ -576,6 +657,7 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
         fprintf(stderr, "render.so: %s\n", s3r_last_error());
         exit(70);
     }
+    if (const char *env = getenv("S3R_PIN_HOST")) { g_renderer->opt_pin_host = atoi(env) != 0; }
     Dl_info info;
     char path[PATH_MAX + 64];
     path[0] = 0;
@@ -602,6 +684,12 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
     exit(666);  // render.cpp:173
 }
 }  // namespace
+
+// Harness-only: puts the drop-in's camera back to the reference's initial state (render.cpp:51-65) so a
+// benchmark can replay the same Input script; the loaded scene and device buffers are kept.
+extern "C" void s3r_dropin_reset(void) {
+    s3r_camera_reset(&g_camera);
+}
 
 extern "C" __attribute__((visibility("default"))) void updateAndRender(const PixelData *pixel_data, const Input *input) {
     if (!g_renderer) { drop_in_initialize(); }

@@ -69,7 +69,8 @@ EXPORTS = [
     "updateAndRender", "s3r_create", "s3r_destroy", "s3r_last_error", "s3r_load_scene_file",
     "s3r_load_scene_arrays", "s3r_scene_counts", "s3r_camera_reset", "s3r_camera_update", "s3r_factor",
     "s3r_render_device", "s3r_finish", "s3r_render_host", "s3r_get_stats", "s3r_dump_raster_vertices",
-    "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option",
+    "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
+    "s3r_dropin_reset",
 ]
 
 
@@ -130,6 +131,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_kernel_launches.argtypes = [vp]
     lib.s3r_kernel_launches.restype = u64
     lib.s3r_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    lib.s3r_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(u64), ctypes.c_int]
     if path is None:
         _lib = lib
     return lib
@@ -254,6 +257,11 @@ class Renderer:
             self._check(self._lib.s3r_dump_setups(self._h, view, out.ctypes.data, n.value, ctypes.byref(n)))
         return out
 
+    def timing(self, reset: bool = True) -> dict:
+        g, q, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+        self._check(self._lib.s3r_get_timing(self._h, ctypes.byref(g), ctypes.byref(q), ctypes.byref(n), int(reset)))
+        return {"geometry_ms": g.value, "raster_ms": q.value, "chunks": n.value}
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.s3r_kernel_launches(self._h))
@@ -287,6 +295,9 @@ class DropIn:
         inp = make_input(rec)
         self._fn(ctypes.byref(pd), ctypes.byref(inp))
         return out
+
+    def reset_camera(self) -> None:
+        self._lib.s3r_dropin_reset()
 
     def close(self) -> None:
         shutil.rmtree(self._dir, ignore_errors=True)

@@ -1,0 +1,265 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the committed golden
+frames of the unmodified reference, (b) the oracle on seeded inputs, (c) size-independent
+properties at the benchmark's full 3840x2160.  Integer/byte outputs: bit-exact.  The north-star
+tolerance (+-1 LSB on >= 99.9 % of pixels) is therefore met with zero differing pixels."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from swift3drenderer_b200 import scene as S
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def assert_same(a, b, what):
+    if not np.array_equal(a, b):
+        ys, xs = np.nonzero(a != b)
+        raise AssertionError(f"{what}: {len(ys)} px differ, first (x={xs[0]}, y={ys[0]}) "
+                             f"got {a[ys[0], xs[0]]:06x} want {b[ys[0], xs[0]]:06x}")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_reference_golden_frames(name, gpu_renderer, renderer_lib, golden):
+    (factory, script, n, keep, (W, H)), frames, pixels = golden(name)
+    gpu_renderer.load_scene(factory())
+    mats = renderer_lib.camera_path(S.input_script(script, n))
+    for k, f in enumerate(frames):
+        assert_same(gpu_renderer.render(mats[f], W, H)[0], pixels[k], f"{name} frame {f}")
+
+
+@pytest.mark.parametrize("size", [(640, 360), (1280, 720), (333, 187), (64, 32), (65, 33), (1, 1), (7, 500)])
+def test_cuda_matches_oracle_shipped_scene(size, gpu_renderer, renderer_lib, oracle_port):
+    W, H = size
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    osc = oracle_port.OracleScene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    for f in range(0, 600, 40):
+        assert_same(gpu_renderer.render(mats[f], W, H)[0], osc.render(mats[f], W, H)["pixels"], f"{W}x{H} frame {f}")
+
+
+@pytest.mark.parametrize("kind", ["ico_tex", "ico_col", "clip", "regfloor", "dense_small"])
+def test_cuda_matches_oracle_synthetic(kind, gpu_renderer, renderer_lib, oracle_port):
+    sc = {
+        "ico_tex": lambda: S.icosahedron_field(2000, seed=3, extent=60),
+        "ico_col": lambda: S.icosahedron_field(2000, seed=4, extent=60, textured=False),
+        "clip": lambda: S.clip_stress_scene(3000),
+        "regfloor": lambda: S.shipped_scene(2, regular_floor=True),
+        "dense_small": lambda: S.icosahedron_field(20000, seed=9, extent=40, r_range=(0.3, 1.0)),
+    }[kind]()
+    gpu_renderer.load_scene(sc)
+    osc = oracle_port.OracleScene(sc)
+    script = "flythrough" if kind == "regfloor" else "spin"
+    mats = renderer_lib.camera_path(S.input_script(script, 120))
+    for f in range(0, 120, 17):
+        o = osc.render(mats[f], 640, 360)
+        assert_same(gpu_renderer.render(mats[f], 640, 360)[0], o["pixels"], f"{kind} frame {f}")
+        st = gpu_renderer.stats()
+        assert st["near_rejected"] == o["stats"]["near_rejected"]
+        assert st["clipped"] == o["stats"]["clipped"] and st["spawned"] == o["stats"]["spawned"]
+        assert st["setups"] == o["stats"]["rasterized"]
+        assert st["culled"] == o["stats"]["offscreen"] + o["stats"]["small_or_backfacing"]
+
+
+def test_stage_dumps_are_bit_exact(gpu_renderer, renderer_lib, oracle_port):
+    """Stage-level KATs: vertex stage (render.cpp:285-289) and clip/cull/setup (render.cpp:297-359)."""
+    sc = S.clip_stress_scene(800)
+    gpu_renderer.load_scene(sc)
+    osc = oracle_port.OracleScene(sc)
+    m = renderer_lib.camera_path(S.input_script("spin", 12))[11]
+    W, H = 480, 270
+    gpu_renderer.render(m, W, H)
+    _, rv = osc.vertex_stage(m, W, H)
+    assert np.array_equal(gpu_renderer.raster_vertices().view(np.uint32), rv.view(np.uint32))
+    want = osc.render(m, W, H, want_setups=True)["setups"]
+    got = gpu_renderer.setups()
+    assert len(got) == len(want) > 50
+    assert (np.diff(want["order"].astype(np.int64)) > 0).all()  # the reference's order is strictly increasing in our key
+    for field in want.dtype.names:
+        assert np.array_equal(got[field].view(np.uint32), want[field].view(np.uint32)), field
+    assert (got["order"] >= sc.n_triangles).any()  # appended (clip-spawned) triangles present
+
+
+def test_full_4k_frames_match_oracle(gpu_renderer, renderer_lib, oracle_port):
+    """The benchmark configuration itself (C2: shipped scene, 3840x2160)."""
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    osc = oracle_port.OracleScene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    for f in (0, 100, 215, 330):
+        assert_same(gpu_renderer.render(mats[f], 3840, 2160)[0], osc.render(mats[f], 3840, 2160)["pixels"], f"4K frame {f}")
+
+
+def test_bands_reassemble_to_the_whole_frame(gpu_renderer, renderer_lib):
+    """Screen-band partition (multi-GPU config) must not change a single pixel: every band walks
+    the barycentrics from each triangle's own ymin exactly like the whole-frame render."""
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    W, H = 1920, 1080
+    for f in (100, 330, 470):
+        whole = gpu_renderer.render(mats[f], W, H)[0]
+        for n in (2, 3, 8):
+            edges = [H * k // n for k in range(n + 1)]
+            parts = [gpu_renderer.render(mats[f], W, H, y0=edges[k], y1=edges[k + 1])[0] for k in range(n)]
+            assert_same(np.concatenate(parts, 0), whole, f"{n} bands frame {f}")
+        # bands that are not tile-aligned
+        parts = [gpu_renderer.render(mats[f], W, H, y0=a, y1=b)[0] for a, b in ((0, 1), (1, 17), (17, 1000), (1000, 1080))]
+        assert_same(np.concatenate(parts, 0), whole, f"ragged bands frame {f}")
+
+
+def test_batched_views_equal_single_views(gpu_renderer, renderer_lib):
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))[::25]
+    W, H = 512, 512
+    batch = gpu_renderer.render(mats, W, H)
+    assert batch.shape == (len(mats), H, W)
+    for k in range(len(mats)):
+        assert_same(batch[k], gpu_renderer.render(mats[k], W, H)[0], f"view {k}")
+    gpu_renderer.set_option("views_per_chunk", 5)  # chunked submission gives the same frames
+    assert np.array_equal(gpu_renderer.render(mats, W, H), batch)
+    gpu_renderer.set_option("views_per_chunk", 256)
+
+
+def test_tma_and_plain_write_out_agree(gpu_renderer, renderer_lib):
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script("flythrough", 120))[110]
+    a = gpu_renderer.render(m, 1280, 720)[0]
+    gpu_renderer.set_option("tma_store", 0)
+    b = gpu_renderer.render(m, 1280, 720)[0]
+    gpu_renderer.set_option("tma_store", 1)
+    assert np.array_equal(a, b) and len(np.unique(a)) > 1000
+
+
+def test_capacity_regrowth_is_transparent(renderer_lib, oracle_port):
+    sc = S.icosahedron_field(2000, seed=3, extent=60)
+    r = renderer_lib.Renderer(0)
+    r.load_scene(sc)
+    r.set_option("setup_capacity", 8)  # far too small: forces the overflow -> regrow -> re-render path
+    m = renderer_lib.camera_path(S.input_script("spin", 5))[4]
+    got = r.render(m, 640, 360)[0]
+    assert r.stats()["overflow"] == 0 and r.stats()["setups"] > 8
+    assert_same(got, oracle_port.OracleScene(sc).render(m, 640, 360)["pixels"], "after regrow")
+    r.close()
+
+
+def test_empty_and_degenerate_scenes(renderer_lib, oracle_port):
+    r = renderer_lib.Renderer(0)
+    m = renderer_lib.camera_path(S.input_script("still", 1))[0]
+    empty = S.Scene(np.ones((0, 4), "<f4"), np.zeros(0, "<u8"), np.zeros(0, S.ATTR_DTYPE), np.zeros(0, "<u8"),
+                    S.procedural_textures(1))
+    r.load_scene(empty)
+    assert (r.render(m, 100, 50)[0] == 0x1E1E1E).all()
+    # everything behind the camera / off screen
+    sc = S.icosahedron_field(50, seed=2, extent=5, center=(0, 0, 500))
+    r.load_scene(sc)
+    got = r.render(m, 100, 50)[0]
+    assert_same(got, oracle_port.OracleScene(sc).render(m, 100, 50)["pixels"], "behind camera")
+    assert (got == 0x1E1E1E).all()
+    r.close()
+
+
+def test_invalid_scenes_are_rejected(renderer_lib):
+    r = renderer_lib.Renderer(0)
+    sc = S.shipped_scene(1)
+    sc.vertices[0, 3] = 2.0
+    with pytest.raises(renderer_lib.RendererError, match="w != 1"):
+        r.load_scene(sc)
+    sc = S.shipped_scene(1)
+    sc.attributes["kind"][3] = 9
+    with pytest.raises(renderer_lib.RendererError, match="kind"):
+        r.load_scene(sc)
+    with pytest.raises(renderer_lib.RendererError, match="no scene"):
+        r.render(np.zeros(12, np.float32), 8, 8)
+    r.close()
+
+
+def test_drop_in_update_and_render(renderer_lib, oracle_port, tmp_path):
+    """The reference's own calling pattern: private render.so beside data.bin, updateAndRender per frame
+    into alternating halves of one pageable allocation (main.swift:117-118), live resize (main.swift:156-165)."""
+    sc = S.shipped_scene(1)
+    path = str(tmp_path / "data.bin")
+    S.write_data_bin(path, sc)
+    osc = oracle_port.OracleScene(sc)
+    inp = S.input_script("flythrough", 600)[:140]
+    mats = oracle_port.camera_path(inp)
+    d = renderer_lib.DropIn(path)
+    W, H = 320, 180
+    double = np.zeros((2, H, W), np.uint32)
+    for f in range(len(inp)):
+        if f == 90:  # live resize
+            W, H = 400, 220
+            double = np.zeros((2, H, W), np.uint32)
+        out = d.update_and_render(W, H, inp[f], out=double[f & 1])
+        if f % 10 == 0 or f in (89, 90, 91):
+            assert_same(out, osc.render(mats[f], W, H)["pixels"], f"drop-in frame {f}")
+    d.close()
+
+
+def test_drop_in_exits_666_without_data_bin(renderer_lib, tmp_path):
+    """render-cpp/render.cpp:173 — exit(666) (status 666 & 0xFF = 154) when no data.bin is found."""
+    code = (
+        "import ctypes, shutil, sys\n"
+        f"shutil.copy({renderer_lib.LIB_PATH!r}, {str(tmp_path / 'render.so')!r})\n"
+        f"lib = ctypes.CDLL({str(tmp_path / 'render.so')!r})\n"
+        "class PD(ctypes.Structure):\n"
+        "    _fields_=[('b',ctypes.c_void_p),('w',ctypes.c_uint32),('h',ctypes.c_uint32),('p',ctypes.c_uint32),('s',ctypes.c_uint32)]\n"
+        "buf=(ctypes.c_uint32*64)(); pd=PD(ctypes.addressof(buf),8,8,4,256); inp=(ctypes.c_float*6)()\n"
+        "lib.updateAndRender(ctypes.byref(pd), ctypes.byref(inp))\n"
+    )
+    rc = subprocess.run([sys.executable, "-c", code]).returncode
+    assert rc == (666 & 0xFF)
+
+
+def test_device_resident_render_and_launch_count(gpu_renderer, renderer_lib):
+    import torch
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script("flythrough", 120))[110]
+    W, H = 1280, 720
+    host = gpu_renderer.render(m, W, H)[0]
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda:0")
+    before = gpu_renderer.kernel_launches
+    gpu_renderer.render_device(m, W, H, out.data_ptr())
+    assert gpu_renderer.finish() is False
+    assert gpu_renderer.kernel_launches - before >= 2
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), host)
+
+
+def test_stale_host_registration_is_detected(gpu_renderer, renderer_lib):
+    """Callers may free a frame buffer and get the same address back (large malloc = mmap); a cached
+    cudaHostRegister would then DMA into the old pages.  The library must still fill what the CPU sees."""
+    sc = S.shipped_scene(1)
+    r = renderer_lib.Renderer(0)
+    r.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script("flythrough", 120))[110]
+    W, H = 1280, 720
+    want = r.render(m, W, H)[0].copy()
+    r.set_option("pin_host", 1)  # opt-in fast path; the caller below then breaks its promise
+    for _ in range(6):
+        buf = np.zeros((1, H, W), np.uint32)  # fresh mmap each time, usually at a recycled address
+        got = r.render(m, W, H, out=buf)
+        assert np.array_equal(got[0], want)
+        del buf, got
+    r.set_option("pin_host", 0)  # drops every registration
+    r.close()
+
+
+def test_overflowing_bins_are_regrown(renderer_lib, oracle_port):
+    """Inside a solid every triangle covers every tile: far more (triangle, tile) pairs than survivors."""
+    sc = S.shipped_scene(1)
+    r = renderer_lib.Renderer(0)
+    r.load_scene(sc)
+    r.set_option("setup_capacity", 64)  # also shrinks the bin-entry capacity to 64
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    osc = oracle_port.OracleScene(sc)
+    for f in (110, 395, 520):
+        assert_same(r.render(mats[f], 1920, 1080)[0], osc.render(mats[f], 1920, 1080)["pixels"], f"frame {f}")
+    r.close()

@@ -1,0 +1,103 @@
+"""data.bin container, scene builders, rip-map atlases, Input scripts (host tools, no GPU)."""
+import os
+
+import numpy as np
+
+from swift3drenderer_b200 import scene as S
+
+
+def test_shipped_scene_counts_and_file_size(tmp_path):
+    sc = S.shipped_scene(1)
+    assert sc.counts() == {"V": 39, "I": 153, "A": 153, "T": 51, "textures": 2}  # SURVEY.md TL;DR 6
+    assert S.validate(sc) == []
+    n = S.write_data_bin(str(tmp_path / "data.bin"), sc)
+    assert n == 2107664 == os.path.getsize(tmp_path / "data.bin")
+
+
+def test_round_trip_and_odd_index_padding(tmp_path):
+    sc = S.shipped_scene(3)
+    assert sc.vertex_indices.shape[0] % 2 == 1  # 153 indices -> 8 bytes of padding after each index section
+    p = str(tmp_path / "d.bin")
+    S.write_data_bin(p, sc)
+    back = S.read_data_bin(p)
+    for f in ("vertices", "vertex_indices", "attributes", "attribute_indices", "textures"):
+        assert np.array_equal(getattr(sc, f), getattr(back, f)), f
+    raw = open(p, "rb").read()
+    assert np.frombuffer(raw, "<u8", 2, 0).tolist() == [39, 0]
+    off = 16 + 39 * 16
+    assert np.frombuffer(raw, "<u8", 2, off).tolist() == [153, 0]
+    off += 16 + 154 * 8
+    assert np.frombuffer(raw, "<u8", 2, off).tolist() == [153, 0]
+    rec = np.frombuffer(raw, np.uint8, 48, off + 16)
+    assert rec[32] == 1 and not rec[33:48].any()  # texture tag byte, zero tail
+
+
+def test_attribute_record_layout():
+    a = S.texture_attr((0, 1, 0), 1, (0.25, 0.5))
+    b = a.tobytes()
+    assert len(b) == 48
+    assert np.frombuffer(b, "<f4", 4, 0).tolist() == [0, 1, 0, 0]
+    assert np.frombuffer(b, "<u4", 2, 16).tolist() == [1, 0]
+    assert np.frombuffer(b, "<f4", 2, 24).tolist() == [0.25, 0.5]
+    assert np.frombuffer(b, "<u4", 1, 32)[0] == S.KIND_TEXTURE
+    c = S.color_attr((0, 0, 1), S.ORANGE).tobytes()
+    assert np.frombuffer(c, "<f4", 3, 16).tolist() == [255.0, 127.5, 0.0]
+    assert np.frombuffer(c, "<u4", 1, 32)[0] == S.KIND_COLOR
+
+
+def test_validator_flags_contract_violations():
+    sc = S.shipped_scene(1)
+    sc.vertices[3, 3] = 2.0
+    assert any("w != 1" in p for p in S.validate(sc))
+    sc = S.shipped_scene(1)
+    sc.attributes["payload"][0, 2] = np.float32(-0.5).view(np.uint32)
+    assert any("uv" in p for p in S.validate(sc))
+    sc = S.shipped_scene(1)
+    sc.vertex_indices[5] = 1000
+    assert any("out of range" in p for p in S.validate(sc))
+    sc = S.shipped_scene(1)
+    sc.attributes["kind"][7] = 2
+    assert any("kind" in p for p in S.validate(sc))
+
+
+def test_ripmap_atlas_levels_are_box_filters():
+    img = S.procedural_image(1)
+    atlas = S.build_ripmap_atlas(img)
+    assert atlas.shape == (512, 512) and atlas.dtype == np.uint32
+    rgb = np.stack([(atlas >> 16) & 255, (atlas >> 8) & 255, atlas & 255], -1)
+    assert np.array_equal(rgb[:256, :256], img)  # level (256, 256) is the image itself
+    # level (128, 256): x-halving lives at column offset 511 & ~255 = 256
+    expect = np.rint(0.5 * (img[:, 0::2].astype(float) + img[:, 1::2]))
+    assert np.abs(rgb[:256, 256:384].astype(float) - expect).max() <= 0.5
+    # level (1, 1) at (510, 510) is the mean colour; row/col 511 stay white
+    assert np.abs(rgb[510, 510] - img.reshape(-1, 3).mean(0)).max() <= 1.0
+    assert (rgb[511] == 255).all() and (rgb[:, 511] == 255).all()
+    for L in (256, 128, 64, 32, 16, 8, 4, 2, 1):  # offsets used by getTextureColor, render.cpp:128-129
+        assert (511 & ~(2 * L - 1)) + L <= 511
+
+
+def test_icosahedron_field_shapes():
+    sc = S.icosahedron_field(50, seed=1)
+    assert sc.counts()["V"] == 600 and sc.n_triangles == 1000 and sc.counts()["A"] == 3000
+    assert S.validate(sc) == []
+    un = S.icosahedron_field(50, seed=1, shared_vertices=False)
+    assert un.counts()["V"] == 3000
+    # same geometry either way
+    a = sc.vertices[sc.vertex_indices.astype(int)]
+    b = un.vertices[un.vertex_indices.astype(int)]
+    assert np.array_equal(a, b)
+    # outward-facing normals: normal . (face centre - solid centre) > 0
+    tri = a[:, :3].reshape(-1, 3, 3)
+    centre = tri.reshape(50, 60, 3).mean(1)
+    out = tri.mean(1) - np.repeat(centre, 20, 0)
+    n = sc.attributes["normal"][::3, :3]
+    assert ((n * out).sum(1) > 0).all()
+
+
+def test_input_scripts_are_deterministic_and_cover_ranges():
+    a, b = S.input_script("flythrough", 600), S.input_script("flythrough", 600)
+    assert a.tobytes() == b.tobytes() and a.dtype.itemsize == 24
+    assert set(np.unique(a["up"])) <= {0.0, 1.0, 2.0}  # input.swift:30-60 (Shift doubles)
+    assert np.abs(np.diff(a["mouse"], axis=0)).max() <= 12.01
+    c1 = S.input_script("c1_path", 300)
+    assert c1["down"][:60].all() and c1["right"][60:120].all() and (np.diff(c1["mouse"][120:, 0]) == 2).all()
