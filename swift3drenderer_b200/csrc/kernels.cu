@@ -704,7 +704,7 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
     frame_reset<<<dim3(ceil_div(max(f.n_tiles, (uint32_t)C_COUNT), 256), f.n_views), 256, 0, s>>>(f); launches++;
     vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
-    triangle_setup<<<dim3(ceil_div(f.T, 256), f.n_views), 256, 0, s>>>(f); launches++;
+    triangle_setup<<<dim3(max(1u, ceil_div(f.T, 256)), f.n_views), 256, 0, s>>>(f); launches++;
     const uint32_t bin_blocks = min(persistent, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
     bin_small<false><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;
     bin_big<false><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
