@@ -126,6 +126,11 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
  *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */
 
+/* Test hook: out[i] = the device build of walk_jump(start[i], delta[i], steps[i]) — the exact result of
+ * steps[i] sequential binary32 additions (render-cpp/render.cpp:374-379).  Host arrays. */
+S3R_API int s3r_debug_walk(S3RRenderer *r, const float *start, const float *delta, const uint32_t *steps,
+                           float *out, uint32_t count);
+
 /* Harness-only: resets the camera owned by updateAndRender (include/render.h) to the reference's
  * initial state so that the same Input script can be replayed; scene and buffers stay loaded. */
 S3R_API void s3r_dropin_reset(void);

@@ -471,8 +471,8 @@ struct RasterShared {
         uint4 state[TILE_W * TILE_H];                  // ... then per-pixel winners (w0, w1, w2, slot)
     } u;
     uint32_t colour[TILE_H][TILE_W];                   // 8 KB, source of the bulk write-out
-    SetupVis batch[BATCH];                             // 1 KB
-    float rowstart[BATCH][TILE_H][3];                  // 6 KB: weights at each row's first walked pixel
+    SetupVis batch[BATCH];                             // 0.5 KB
+    float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];    // 24 KB: exact weights at each 8-pixel segment's first walked pixel
 };
 
 // Ascending bitonic sort of a[0..n) (a may be shared or global); indices >= n act as +inf.
@@ -548,7 +548,7 @@ __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_
     return row * TILE_W + seg * SEG + (j ^ seg);  // spreads a thread's 8-pixel run over the 16-byte bank groups
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_constant__ Frame f) {
+__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y, tid = threadIdx.x;
@@ -591,19 +591,27 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_co
                     reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot)[q];
             }
             __syncthreads();
-            // ---- stage A: exact weights at the first walked pixel of every (triangle, row) ----
-            for (uint32_t item = tid; item < nb * TILE_H; item += RASTER_THREADS) {
-                const uint32_t b = item / TILE_H, r = item % TILE_H;
+            // ---- stage A: exact weights at the first walked pixel of every (triangle, row, segment).
+            // One work item per (triangle, row, barycentric component): jump down the rows from the
+            // triangle's own ymin, jump along the row from its own xmin to the tile, then take true
+            // steps through the tile, dropping the value at every 8-pixel segment boundary.
+            for (uint32_t item = tid; item < nb * (TILE_H * 3u); item += RASTER_THREADS) {
+                const uint32_t b = item / (TILE_H * 3u), rc = item % (TILE_H * 3u), r = rc / 3u, c = rc % 3u;
                 const SetupVis &v = sh.batch[b];
                 const uint32_t yy = ty0 + r;
-                if (yy >= v.ymin && yy <= v.ymax) {
-                    const uint32_t ny = yy - v.ymin;
-                    const uint32_t nx = max(tx0, (uint32_t)v.xmin) - v.xmin;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float wy = walk_jump(v.wstart[c], v.dy[c], ny);   // render.cpp:378-379
-                        sh.rowstart[b][r][c] = walk_jump(wy, v.dx[c], nx);      // render.cpp:374
-                    }
+                if (yy < v.ymin || yy > v.ymax) { continue; }
+                const uint32_t xs = max(tx0, (uint32_t)v.xmin), xe = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
+                if (xs > xe) { continue; }
+                const float d = v.dx[c];
+                const float wy = walk_jump(v.wstart[c], v.dy[c], yy - v.ymin);   // render.cpp:378-379
+                float w = walk_jump(wy, d, xs - v.xmin);                         // render.cpp:374
+                uint32_t x = xs, k = (xs - tx0) / SEG;
+                while (true) {
+                    sh.segstart[b][r][k][c] = w;
+                    const uint32_t next = tx0 + (k + 1u) * SEG;
+                    if (next > xe) { break; }
+                    for (; x < next; x++) { w = add_rn(w, d); }
+                    k++;
                 }
             }
             __syncthreads();
@@ -613,11 +621,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_co
                 if (y < v.ymin || y > v.ymax) { continue; }
                 const uint32_t xa = max(sx0, (uint32_t)v.xmin), xb = min(sx0 + SEG - 1u, (uint32_t)v.xmax);
                 if (xa > xb) { continue; }
-                const uint32_t skip = xa - max(tx0, (uint32_t)v.xmin);
                 const float d0 = v.dx[0], d1 = v.dx[1], d2 = v.dx[2];
-                float w0 = walk_jump(sh.rowstart[b][row][0], d0, skip);
-                float w1 = walk_jump(sh.rowstart[b][row][1], d1, skip);
-                float w2 = walk_jump(sh.rowstart[b][row][2], d2, skip);
+                float w0 = sh.segstart[b][row][seg][0], w1 = sh.segstart[b][row][seg][1], w2 = sh.segstart[b][row][seg][2];
                 const float rz0 = v.rvz[0], rz1 = v.rvz[1], rz2 = v.rvz[2];
                 const uint32_t slot = (uint32_t)sorted[base + b];
 #pragma unroll
@@ -634,7 +639,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) tile_raster(const __grid_co
                     }
                 }
             }
-            __syncthreads();  // batch / rowstart are rewritten by the next iteration
+            __syncthreads();  // batch / segstart are rewritten by the next iteration
         }
     }
 
@@ -694,7 +699,9 @@ cudaError_t configure_kernels() {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { return e; }
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    return cudaFuncSetAttribute(tile_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared));
+    e = cudaFuncSetAttribute(tile_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared));
+    if (e != cudaSuccess) { return e; }
+    return cudaFuncSetAttribute(tile_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -720,5 +727,15 @@ int launch_raster(const Frame &f, cudaStream_t s) {
 }
 
 int launch_geometry_small(const Frame &f, cudaStream_t s) { return launch_geometry(f, s); }
+
+// test hook: the device build of walk_jump on arrays (tests compare it with sequential adds)
+__global__ void walk_jump_kernel(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { out[i] = walk_jump(s[i], d[i], n[i]); }
+}
+
+void launch_walk_jump(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count, cudaStream_t st) {
+    walk_jump_kernel<<<(count + 255) / 256, 256, 0, st>>>(s, d, n, out, count);
+}
 
 }  // namespace s3r

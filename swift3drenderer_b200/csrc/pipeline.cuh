@@ -28,7 +28,7 @@ constexpr int TILE_H = 32;
 constexpr int RASTER_THREADS = 256;         // (TILE_W / SEG) * TILE_H
 constexpr int SEG = 8;                      // pixels per thread in the visibility pass
 constexpr int SEGS_PER_ROW = TILE_W / SEG;  // 8
-constexpr int BATCH = 16;                   // triangles staged per visibility batch
+constexpr int BATCH = 8;                    // triangles staged per visibility batch
 constexpr int SORT_CAP = 4096;              // bin entries sorted in shared memory (longer lists: in HBM)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
@@ -101,5 +101,6 @@ int launch_geometry(const Frame &f, cudaStream_t s);   // reset, vertex stage, c
 int launch_raster(const Frame &f, cudaStream_t s);     // per-tile visibility + shading + write-out
 int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry
 cudaError_t configure_kernels();
+void launch_walk_jump(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count, cudaStream_t st);
 
 }  // namespace s3r

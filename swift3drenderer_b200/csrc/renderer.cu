@@ -600,6 +600,24 @@ extern "C" int s3r_dump_setups(S3RRenderer *r, uint32_t view, S3RSetupDump *out,
     return S3R_OK;
 }
 
+extern "C" int s3r_debug_walk(S3RRenderer *r, const float *start, const float *delta, const uint32_t *steps,
+                              float *out, uint32_t count) {
+    if (!r || !start || !delta || !steps || !out) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    DevBuf<float> s, d, o;
+    DevBuf<uint32_t> n;
+    CUDA_TRY(s.ensure(count)); CUDA_TRY(d.ensure(count)); CUDA_TRY(o.ensure(count)); CUDA_TRY(n.ensure(count));
+    CUDA_TRY(cudaMemcpy(s.p, start, count * 4ull, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.p, delta, count * 4ull, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(n.p, steps, count * 4ull, cudaMemcpyHostToDevice));
+    launch_walk_jump(s.p, d.p, n.p, o.p, count, r->stream);
+    r->launches++;
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    CUDA_TRY(cudaMemcpy(out, o.p, count * 4ull, cudaMemcpyDeviceToHost));
+    s.release(); d.release(); o.release(); n.release();
+    return S3R_OK;
+}
+
 extern "C" uint64_t s3r_kernel_launches(const S3RRenderer *r) { return r ? r->launches : 0; }
 
 extern "C" int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raster_ms, uint64_t *chunks, int reset) {

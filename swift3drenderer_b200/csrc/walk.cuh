@@ -59,6 +59,19 @@ S3R_HD float add_rn(float a, float b) {
 #endif
 }
 
+// floor(a / b) for a < 2^23, 0 < b < 2^23 without an integer divide (both convert to binary32
+// exactly; the reciprocal estimate is off by at most one, fixed up with integer arithmetic).
+S3R_HD uint32_t div_small(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t k = (uint32_t)(__uint2float_rz(a) * __frcp_rn(__uint2float_rz(b)));
+    if (k * b > a) { --k; }
+    if ((k + 1u) * b <= a) { ++k; }
+    return k;
+#else
+    return a / b;
+#endif
+}
+
 // n sequential adds of d onto s, bit-exact.
 S3R_HD float walk_jump(float s, float d, uint32_t n) {
     if (n == 0) { return s; }
@@ -76,8 +89,8 @@ S3R_HD float walk_jump(float s, float d, uint32_t n) {
             // Stay inside the binade.  Downwards the landing mantissa must remain >= 1: an exact sum
             // just below 2^e is rounded on the finer grid of the binade underneath, so the bottom
             // value itself may only be reached by a true addition.
-            const uint32_t room = q > 0 ? (0x7FFFFFu - mant) / (uint32_t)q
-                                        : (mant ? (mant - 1u) / (uint32_t)(-q) : 0u);
+            const uint32_t room = q > 0 ? div_small(0x7FFFFFu - mant, (uint32_t)q)
+                                        : (mant ? div_small(mant - 1u, (uint32_t)(-q)) : 0u);
             const uint32_t k = room < n ? room : n;
             const uint32_t landed = bn + k * (uint32_t)q;
             n -= k;

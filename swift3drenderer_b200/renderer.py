@@ -70,7 +70,7 @@ EXPORTS = [
     "s3r_load_scene_arrays", "s3r_scene_counts", "s3r_camera_reset", "s3r_camera_update", "s3r_factor",
     "s3r_render_device", "s3r_finish", "s3r_render_host", "s3r_get_stats", "s3r_dump_raster_vertices",
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
-    "s3r_dropin_reset",
+    "s3r_dropin_reset", "s3r_debug_walk",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
     lib.s3r_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(u64), ctypes.c_int]
+    lib.s3r_debug_walk.argtypes = [vp, vp, vp, vp, vp, u32]
     if path is None:
         _lib = lib
     return lib
@@ -255,6 +256,12 @@ class Renderer:
         out = np.zeros(n.value, SETUP_DTYPE)
         if n.value:
             self._check(self._lib.s3r_dump_setups(self._h, view, out.ctypes.data, n.value, ctypes.byref(n)))
+        return out
+
+    def debug_walk(self, start, delta, steps) -> np.ndarray:
+        s = np.ascontiguousarray(start, "<f4"); d = np.ascontiguousarray(delta, "<f4"); n = np.ascontiguousarray(steps, "<u4")
+        out = np.empty_like(s)
+        self._check(self._lib.s3r_debug_walk(self._h, s.ctypes.data, d.ctypes.data, n.ctypes.data, out.ctypes.data, s.size))
         return out
 
     def timing(self, reset: bool = True) -> dict:

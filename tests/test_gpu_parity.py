@@ -264,3 +264,22 @@ def test_overflowing_bins_are_regrown(renderer_lib, oracle_port):
     for f in (110, 395, 520):
         assert_same(r.render(mats[f], 1920, 1080)[0], osc.render(mats[f], 1920, 1080)["pixels"], f"frame {f}")
     r.close()
+
+
+def test_device_walk_jump_equals_sequential_adds(gpu_renderer, oracle_port):
+    """The device build of walk_jump (division-free path) against true sequential binary32 adds."""
+    rs = np.random.RandomState(11)
+    n = 20000
+    s = rs.uniform(-2, 2, n).astype(np.float32)
+    d = (rs.uniform(-3, 3, n) / rs.randint(1, 4000, n)).astype(np.float32)
+    k = rs.randint(0, 3841, n).astype(np.uint32)
+    # adversarial: ties, binade floors, zero crossings, stuck walks
+    s[:8] = [2.0030441, 1.0, 1.0, 1.0, 0.0, -1.0, 16777216.0, 0.5]
+    d[:8] = [-3.4061623e-06, 2.0 ** -24, -(2.0 ** -25), 1.5 * 2.0 ** -23, 1e-3, 1e-3, 1.0, 0.0]
+    k[:8] = [1845, 3840, 3840, 3840, 3840, 3840, 100, 77]
+    got = gpu_renderer.debug_walk(s, d, k)
+    want = s.copy()
+    for step in range(int(k.max())):  # vectorised sequential adds in binary32
+        live = k > step
+        want[live] = (want[live] + d[live]).astype(np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).sum())
