@@ -124,6 +124,9 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *          "pin_host" (1 = cudaHostRegister the caller's frame buffers; default 0 — only for callers that
  *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
  *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
+ *          "fused_small" (1 = one fused geometry CTA per view for scenes of <= 4096 triangles, default),
+ *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/
+ *          copy pipeline depth of host renders, default 8), "copy_threads" (staging -> caller copy workers),
  *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */
 
 /* Test hook: out[i] = the device build of walk_jump(start[i], delta[i], steps[i]) — the exact result of

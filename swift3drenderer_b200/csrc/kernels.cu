@@ -57,21 +57,19 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // ------------------------------------------------------------------------------------------------
 // K0 — reset
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) frame_reset(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void reset_body(const Frame &f, uint32_t view, uint32_t i, uint32_t stride) {
     if (i < C_COUNT) { f.counters[view * C_COUNT + i] = 0; }
-    for (uint32_t t = i; t < f.n_tiles; t += gridDim.x * blockDim.x) { f.tile_count[view * f.tile_stride + t] = 0; }
+    for (uint32_t t = i; t < f.n_tiles; t += stride) { f.tile_count[view * f.tile_stride + t] = 0; }
+}
+
+__global__ void __launch_bounds__(256) frame_reset(const __grid_constant__ Frame f) {
+    reset_body(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1 — vertex stage: 4 vertices per thread, float4 loads of the planar streams, float4 stores.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y;
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (i4 >= f.Vpad) { return; }
-    const Cam cam = load_cam(f.cams + 12 * view);
+__device__ __forceinline__ void vertex_body(const Frame &f, const Cam &cam, uint32_t view, uint32_t i4) {
     const float4 x = __ldg(reinterpret_cast<const float4 *>(f.pos_x + i4));
     const float4 y = __ldg(reinterpret_cast<const float4 *>(f.pos_y + i4));
     const float4 z = __ldg(reinterpret_cast<const float4 *>(f.pos_z + i4));
@@ -83,6 +81,12 @@ __global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Fram
         const float3 rv = project(cv, f.factor, f.half_w, f.half_h);
         out[k] = make_float4(rv.x, rv.y, rv.z, 0.f);
     }
+}
+
+__global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Frame f) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= f.Vpad) { return; }
+    vertex_body(f, load_cam(f.cams + 12 * blockIdx.y), blockIdx.y, i4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,16 +288,15 @@ __device__ __forceinline__ bool clip_near(Corner &d0, Corner &d1, Corner &d2, Co
     return two_in_front;
 }
 
-__global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Frame f) {
-    __shared__ SetupShared sh;
-    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
-    const Cam cam = load_cam(f.cams + 12 * view);
+// One 256-triangle chunk, executed by one 256-thread CTA (all threads must call).
+__device__ __forceinline__ void setup_body(const Frame &f, const Cam &cam, uint32_t view, uint32_t chunk, SetupShared &sh) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
     if (tid == 0) { sh.count = 0; }
     if (tid < 4) { sh.stats[tid] = 0; }
     __syncthreads();
 
     // ---- phase 1: classify one triangle per thread from raster-space vertices only ----------
-    const uint32_t t = blockIdx.x * 256u + tid;
+    const uint32_t t = chunk * 256u + tid;
     uint32_t cls = 0;  // 0 rejected, 1 rasterisable as is, 2 straddles the near plane
     bool near_rej = false, culled = false;
     if (t < f.T) {
@@ -327,7 +330,6 @@ __global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Fr
 
     // ---- phase 2: dense full setup of the compacted work items (count <= 256: one pass) --------
     const uint32_t count = sh.count;
-    if (count == 0 && sh.stats[0] == 0 && sh.stats[3] == 0) { return; }
     const bool valid = tid < count;
     Corner d0, d1, d2, s0, s1, s2;
     bool spawn = false;
@@ -349,6 +351,12 @@ __global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Fr
     }
     __syncthreads();
     if (tid < 4 && sh.stats[tid]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR + tid, sh.stats[tid]); }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Frame f) {
+    __shared__ SetupShared sh;
+    setup_body(f, load_cam(f.cams + 12 * blockIdx.y), blockIdx.y, blockIdx.x, sh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,10 +387,9 @@ __device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t 
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(256) bin_small(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y;
+__device__ __forceinline__ void bin_small_body(const Frame &f, uint32_t view, uint32_t first, uint32_t stride) {
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+    for (uint32_t slot = first; slot < n; slot += stride) {
         const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
@@ -403,10 +410,14 @@ __global__ void __launch_bounds__(256) bin_small(const __grid_constant__ Frame f
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y;
+__global__ void __launch_bounds__(256) bin_small(const __grid_constant__ Frame f) {
+    bin_small_body<FILL>(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+template <bool FILL>
+__device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view, uint32_t first, uint32_t stride) {
     const uint32_t n = min(f.counters[view * C_COUNT + C_BIG], f.big_cap);
-    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
+    for (uint32_t b = first; b < n; b += stride) {
         const uint32_t slot = f.big_list[(size_t)view * f.big_cap + b];
         const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
@@ -419,16 +430,23 @@ __global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) 
     }
 }
 
-// exclusive scan of the tile histogram (one CTA per view); also seeds the fill cursors
-__global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame f) {
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    const uint32_t view = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
+    bin_big_body<FILL>(f, blockIdx.y, blockIdx.x, gridDim.x);
+}
+
+struct ScanShared { uint32_t warp_tot[32]; uint32_t carry; };
+
+// exclusive scan of the tile histogram by one CTA of any size (multiple of 32); also seeds the fill cursors
+__device__ __forceinline__ void scan_body(const Frame &f, uint32_t view, ScanShared &ss) {
+    uint32_t *warp_tot = ss.warp_tot;
+    uint32_t &carry = ss.carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     const uint32_t *cnt = f.tile_count + view * f.tile_stride;
     uint32_t *off = f.tile_offset + view * f.tile_stride, *cur = f.tile_cursor + view * f.tile_stride;
     if (tid == 0) { carry = 0; }
     __syncthreads();
-    for (uint32_t base = 0; base < f.n_tiles; base += 1024) {
+    for (uint32_t base = 0; base < f.n_tiles; base += nthreads) {
         const uint32_t i = base + tid;
         const uint32_t c = i < f.n_tiles ? cnt[i] : 0u;
         uint32_t incl = c;
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame 
         if (lane == 31) { warp_tot[warp] = incl; }
         __syncthreads();
         if (warp == 0) {
-            uint32_t w = warp_tot[lane], wi = w;
+            uint32_t w = lane < nwarps ? warp_tot[lane] : 0u, wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) { wi += o; } }
             warp_tot[lane] = wi - w;  // exclusive
@@ -446,7 +464,7 @@ __global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame 
         const uint32_t excl = carry + warp_tot[warp] + incl - c;
         if (i < f.n_tiles) { off[i] = excl; cur[i] = excl; }
         __syncthreads();
-        if (tid == 1023) { carry = excl + c; }
+        if (tid == nthreads - 1u) { carry = excl + c; }
         __syncthreads();
     }
     if (tid == 0) {
@@ -459,6 +477,34 @@ __global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame 
         atomicMax(f.sticky + 1, c[C_SETUPS]);
         atomicMax(f.sticky + 2, carry);
         atomicMax(f.sticky + 3, c[C_BIG]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame f) {
+    __shared__ ScanShared ss;
+    scan_body(f, blockIdx.x, ss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused geometry for small scenes: one 256-thread CTA per view runs reset, vertex stage and setup back
+// to back (block barriers instead of kernel boundaries).  No binning at all: with at most SORT_CAP
+// surviving triangles every raster CTA scans the setup list itself (Frame::direct_bin).  The per-frame
+// work of a 51-triangle scene is launch latency, not arithmetic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Frame f) {
+    __shared__ SetupShared sh;
+    const uint32_t view = blockIdx.x, tid = threadIdx.x;
+    const Cam cam = load_cam(f.cams + 12 * view);
+    if (tid < C_COUNT) { f.counters[view * C_COUNT + tid] = 0; }
+    for (uint32_t i4 = tid * 4u; i4 < f.Vpad; i4 += 1024u) { vertex_body(f, cam, view, i4); }
+    __syncthreads();
+    for (uint32_t chunk = 0; chunk * 256u < f.T; chunk++) { setup_body(f, cam, view, chunk, sh); }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t *c = f.counters + view * C_COUNT;
+        if (c[C_OVERFLOW]) { atomicOr(f.sticky + 0, c[C_OVERFLOW]); }
+        atomicMax(f.sticky + 1, c[C_SETUPS]);
     }
 }
 
@@ -551,7 +597,7 @@ __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_
 __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
-    const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y, tid = threadIdx.x;
+    const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y + f.raster_row0, tid = threadIdx.x;
     const uint32_t tile = tile_y * f.tiles_x + tile_x;
     const uint32_t tx0 = tile_x * TILE_W, ty0 = (tile_y + f.tile_row0) * TILE_H;
     const uint32_t row = tid / SEGS_PER_ROW, seg = tid % SEGS_PER_ROW;
@@ -560,9 +606,30 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     // A capacity overflow anywhere upstream makes the bin lists incomplete: the host regrows the
     // buffers and renders the frame again, so this launch only has to stay in bounds.
     if (f.counters[view * C_COUNT + C_OVERFLOW] != 0) { return; }
-    const uint32_t *toff = f.tile_offset + view * f.tile_stride;
-    const uint32_t begin = toff[tile], n = toff[tile + 1] - begin;
-    unsigned long long *list = f.entries + (size_t)view * f.entry_cap + begin;
+    uint32_t n;
+    unsigned long long *list = nullptr;
+    if (f.direct_bin) {
+        // small scene: collect this tile's triangles straight from the setup list (bbox overlap,
+        // clamped to the band); at most SORT_CAP survivors by construction of the small path
+        __shared__ uint32_t s_n;
+        if (tid == 0) { s_n = 0; }
+        __syncthreads();
+        const uint32_t n_setups = min(f.counters[view * C_COUNT + C_SETUPS], min(f.setup_cap, (uint32_t)SORT_CAP));
+        const uint32_t ylo_t = max(ty0, f.y0), yhi_t = min(ty0 + TILE_H, f.y1);   // [ylo_t, yhi_t)
+        for (uint32_t slot = tid; slot < n_setups; slot += RASTER_THREADS) {
+            const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+            if (xmax >= tx0 && xmin < tx0 + TILE_W && ymax >= ylo_t && ymin < yhi_t) {
+                sh.u.entries[atomicAdd(&s_n, 1u)] = ((unsigned long long)head.z << 32) | slot;
+            }
+        }
+        __syncthreads();
+        n = s_n;
+    } else {
+        const uint32_t begin = f.tile_offset[view * f.tile_stride + tile];
+        n = f.tile_offset[view * f.tile_stride + tile + 1] - begin;
+        list = f.entries + (size_t)view * f.entry_cap + begin;
+    }
 
     float depth[SEG], bw0[SEG], bw1[SEG], bw2[SEG];
     uint32_t win[SEG];
@@ -573,8 +640,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         // ---- restore the reference's triangle order ------------------------------------------
         const bool in_smem = n <= SORT_CAP;
         if (in_smem) {
-            for (uint32_t i = tid; i < n; i += RASTER_THREADS) { sh.u.entries[i] = list[i]; }
-            __syncthreads();
+            if (!f.direct_bin) {
+                for (uint32_t i = tid; i < n; i += RASTER_THREADS) { sh.u.entries[i] = list[i]; }
+                __syncthreads();
+            }
             block_sort(sh.u.entries, n);
         } else {
             block_sort(list, n);  // rare: longer than the shared buffer, sort in place in HBM/L2
@@ -663,8 +732,48 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     }
 
     // ---- write-out -------------------------------------------------------------------------
-    uint32_t *out = f.out + (size_t)view * f.out_view_stride;
     const uint32_t cols = min((uint32_t)TILE_W, f.W - tx0);
+    if (f.out_packed24) {
+        // host transport format: 3 bytes per pixel.  Pack each row of 64 pixels into 48 words
+        // (reusing the dead per-pixel state), then bulk-copy 192-byte rows.
+        __syncthreads();
+        uint32_t *packed = reinterpret_cast<uint32_t *>(sh.u.state);   // [TILE_H][48]
+        for (uint32_t g = tid; g < TILE_H * (TILE_W / 4); g += RASTER_THREADS) {
+            const uint32_t pr = g / (TILE_W / 4), q = g % (TILE_W / 4);
+            const uint4 p = *reinterpret_cast<const uint4 *>(&sh.colour[pr][q * 4]);
+            uint32_t *o = packed + pr * 48u + q * 3u;
+            o[0] = p.x | (p.y << 24);
+            o[1] = (p.y >> 8) | (p.z << 16);
+            o[2] = (p.z >> 16) | (p.w << 8);
+        }
+        uint8_t *out8 = reinterpret_cast<uint8_t *>(f.out) + (size_t)view * f.out_view_stride * 3u;
+        if (f.use_tma) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid < TILE_H) {
+                const uint32_t yy = ty0 + tid;
+                if (yy >= f.y0 && yy < f.y1) {
+                    uint8_t *dst = out8 + ((size_t)(yy - f.y0) * f.W + tx0) * 3u;
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + tid * 48u);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "r"(cols * 3u) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
+            __syncthreads();
+            const uint8_t *pb = reinterpret_cast<const uint8_t *>(packed);
+            for (uint32_t i = tid; i < TILE_H * TILE_W * 3u; i += RASTER_THREADS) {
+                const uint32_t pr = i / (TILE_W * 3u), off = i % (TILE_W * 3u), yy = ty0 + pr;
+                if (off < cols * 3u && yy >= f.y0 && yy < f.y1) {
+                    out8[((size_t)(yy - f.y0) * f.W + tx0) * 3u + off] = pb[pr * 192u + off];
+                }
+            }
+        }
+        return;
+    }
+    uint32_t *out = f.out + (size_t)view * f.out_view_stride;
     if (f.use_tma) {
         // make the generic-proxy writes to the colour tile visible to the async (TMA) proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -722,11 +831,14 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
 }
 
 int launch_raster(const Frame &f, cudaStream_t s) {
-    tile_raster<<<dim3(f.tiles_x, f.tiles_y, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+    tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
     return 1;
 }
 
-int launch_geometry_small(const Frame &f, cudaStream_t s) { return launch_geometry(f, s); }
+int launch_geometry_small(const Frame &f, cudaStream_t s) {
+    geometry_small<<<f.n_views, 256, 0, s>>>(f);
+    return 1;
+}
 
 // test hook: the device build of walk_jump on arrays (tests compare it with sequential adds)
 __global__ void walk_jump_kernel(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count) {

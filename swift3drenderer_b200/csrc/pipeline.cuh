@@ -77,6 +77,7 @@ struct Frame {
     uint32_t W, H, y0, y1;
     float fw, fh, half_w, half_h, factor;
     uint32_t tiles_x, tile_row0, tiles_y, n_tiles;
+    uint32_t raster_row0, raster_rows;   // tile rows [raster_row0, raster_row0 + raster_rows) of the band go in one raster launch
     // per-view scratch
     float4 *rv;
     SetupVis *vis;
@@ -94,6 +95,8 @@ struct Frame {
     uint32_t *out;
     unsigned long long out_view_stride;  // pixels
     int use_tma;
+    int direct_bin;     // 1: no bin arrays — every raster CTA collects its triangles from the setup list itself
+    int out_packed24;   // 1: `out` is a byte buffer with 3 bytes per pixel (B, G, R), used for host transport
 };
 
 // Launchers (kernels.cu).  Each returns the number of kernels it enqueued.

@@ -14,10 +14,12 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/render.h"
 #include "../../include/s3r_b200.h"
+#include "hostcopy.hpp"
 #include "pipeline.cuh"
 
 using namespace s3r;
@@ -70,11 +72,12 @@ struct S3RRenderer {
     DevBuf<SetupVis> vis;
     DevBuf<SetupShade> shade;
     DevBuf<uint32_t> sticky;
+    uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
     float factor_override = 0.f;   // drop-in path: the reference's stale-factor rule (render.cpp:276-279)
     DevBuf<uint32_t> counters, tile_count, tile_offset, tile_cursor, big_list;
     DevBuf<unsigned long long> entries;
     DevBuf<float> cams;
-    DevBuf<uint32_t> frame;   // internal device framebuffer for host renders
+    DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
     // submission ring: pinned camera staging + events, so the host can run RING chunks ahead
     static constexpr int RING = 16;
     float *cams_pinned = nullptr;     // RING x views_cap x 12
@@ -87,8 +90,17 @@ struct S3RRenderer {
     uint64_t timed_chunks = 0;
     // last render (for finish / dumps)
     uint32_t last_views = 0, last_W = 0, last_H = 0;
+    cudaStream_t last_stream = nullptr;   // stream of the last s3r_render_device submission
     uint64_t launches = 0;
     int opt_tma = 1, opt_pin_host = 0;   // pinning caller memory is opt-in: see pin_host()
+    // staged host output (default path of s3r_render_host)
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_SLICES = 64;
+    cudaEvent_t ev_raster[MAX_SLICES] = {}, ev_copy[MAX_SLICES] = {};
+    uint8_t *staging = nullptr;
+    size_t staging_bytes = 0;
+    HostCopier *copier = nullptr;
+    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1;
     std::vector<HostPin> pins;
 };
 
@@ -115,6 +127,14 @@ extern "C" int s3r_create(S3RRenderer **out, int device) {
         CUDA_TRY(cudaEventCreateWithFlags(&r->ev_cams[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&r->ev_t0[i])); CUDA_TRY(cudaEventCreate(&r->ev_t1[i])); CUDA_TRY(cudaEventCreate(&r->ev_t2[i]));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < S3RRenderer::MAX_SLICES; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&r->ev_raster[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&r->ev_copy[i], cudaEventDisableTiming));
+    }
+    if (const char *env = getenv("S3R_COPY_THREADS")) { r->opt_copy_threads = atoi(env); }
+    if (const char *env = getenv("S3R_HOST_BANDS")) { r->opt_host_bands = std::max(1, atoi(env)); }
+    if (const char *env = getenv("S3R_PACK24")) { r->opt_pack24 = atoi(env) != 0; }
     CUDA_TRY(configure_kernels());
     *out = r;
     return S3R_OK;
@@ -136,6 +156,13 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     r->counters.release(); r->tile_count.release(); r->tile_offset.release(); r->tile_cursor.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
+    delete r->copier;
+    if (r->sticky_host) { cudaFreeHost(r->sticky_host); }
+    if (r->staging) { cudaFreeHost(r->staging); }
+    for (int i = 0; i < S3RRenderer::MAX_SLICES; i++) {
+        if (r->ev_raster[i]) { cudaEventDestroy(r->ev_raster[i]); cudaEventDestroy(r->ev_copy[i]); }
+    }
+    if (r->copy_stream) { cudaStreamDestroy(r->copy_stream); }
     for (int i = 0; i < S3RRenderer::RING; i++) {
         if (r->ev_cams[i]) { cudaEventDestroy(r->ev_cams[i]); cudaEventDestroy(r->ev_t0[i]); cudaEventDestroy(r->ev_t1[i]); cudaEventDestroy(r->ev_t2[i]); }
     }
@@ -342,7 +369,11 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     CUDA_TRY(r->vis.ensure(vc * r->setup_cap));
     CUDA_TRY(r->shade.ensure(vc * r->setup_cap));
     CUDA_TRY(r->counters.ensure(vc * C_COUNT));
-    if (!r->sticky.p) { CUDA_TRY(r->sticky.ensure(4)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 16)); }
+    if (!r->sticky.p) {
+        CUDA_TRY(r->sticky.ensure(4)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 16));
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&r->sticky_host), 16));
+        memset(r->sticky_host, 0, 16);
+    }
     CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
     CUDA_TRY(r->tile_offset.ensure(vc * r->tile_stride));
     CUDA_TRY(r->tile_cursor.ensure(vc * r->tile_stride));
@@ -358,8 +389,12 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     return S3R_OK;
 }
 
+// raster_bands > 1: the tile rows are rasterised in that many launches, with r->ev_raster[b] recorded
+// after band b (used by the staged host path to start the D2H of a band while the next one renders);
+// band_rows[b] receives the first pixel row (relative to y0) after band b.
 static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H, uint32_t y0,
-                        uint32_t y1, uint32_t *dev_out, cudaStream_t s) {
+                        uint32_t y1, uint32_t *dev_out, cudaStream_t s, int raster_bands = 1,
+                        uint32_t *band_rows = nullptr, bool packed24 = false) {
     Frame f;
     memset(&f, 0, sizeof(f));
     f.tiles_x = (W + TILE_W - 1) / TILE_W;
@@ -405,11 +440,30 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.entries = r->entries.p; f.entry_cap = r->entry_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out; f.out_view_stride = (unsigned long long)W * (y1 - y0);
-    f.use_tma = r->opt_tma && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
+    f.out_packed24 = packed24 ? 1 : 0;
+    f.use_tma = r->opt_tma && (W % (packed24 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
-    r->launches += (uint64_t)launch_geometry(f, s);
+    // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
+    // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
+    f.direct_bin = (r->opt_fused_small && 2u * f.T <= (uint32_t)SORT_CAP && f.setup_cap >= 2u * f.T) ? 1 : 0;
+    r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
+    if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
+        CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
+    }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
-    r->launches += (uint64_t)launch_raster(f, s);
+    const int nb = std::max(1, std::min<int>(raster_bands, (int)f.tiles_y));
+    for (int b = 0; b < nb; b++) {
+        f.raster_row0 = (uint32_t)((uint64_t)f.tiles_y * b / nb);
+        f.raster_rows = (uint32_t)((uint64_t)f.tiles_y * (b + 1) / nb) - f.raster_row0;
+        r->launches += (uint64_t)launch_raster(f, s);
+        if (raster_bands > 1 || band_rows) {
+            CUDA_TRY(cudaEventRecord(r->ev_raster[b], s));
+            if (band_rows) {
+                const uint32_t end_row = (f.tile_row0 + f.raster_row0 + f.raster_rows) * TILE_H;
+                band_rows[b] = std::min(y1, std::max(y0, end_row)) - y0;
+            }
+        }
+    }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t2[slot], s)); r->slot_timed[slot] = true; }
     CUDA_TRY(cudaGetLastError());
     return S3R_OK;
@@ -424,6 +478,7 @@ extern "C" int s3r_render_device(S3RRenderer *r, const float *cams, uint32_t n_v
     }
     CUDA_TRY(cudaSetDevice(r->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
+    r->last_stream = s;
     const size_t view_px = (size_t)W * (y1 - y0);
     for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
         const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
@@ -442,10 +497,11 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
     CUDA_TRY(cudaStreamSynchronize(s));
     if (r->last_views == 0 || !r->sticky.p) { return S3R_OK; }
     uint32_t sticky[4];
-    CUDA_TRY(cudaMemcpy(sticky, r->sticky.p, sizeof(sticky), cudaMemcpyDeviceToHost));
+    memcpy(sticky, r->sticky_host, sizeof(sticky));   // copied after the geometry of the last submission; the sync above covers it
     const uint32_t overflow = sticky[0], need_setups = sticky[1], need_entries = sticky[2], need_big = sticky[3];
     if (!overflow) { return S3R_OK; }
     CUDA_TRY(cudaMemset(r->sticky.p, 0, sizeof(sticky)));
+    memset(r->sticky_host, 0, sizeof(sticky));
     if (overflow & 1u) {
         r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * r->T + 16, (uint64_t)need_setups + need_setups / 2 + 1024);
         r->entry_cap = std::max(r->entry_cap, r->setup_cap * 4u);
@@ -460,7 +516,7 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
 
 extern "C" int s3r_finish(S3RRenderer *r) {
     if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
-    return finish_on(r, r->stream);
+    return finish_on(r, r->last_stream ? r->last_stream : r->stream);
 }
 
 // OPT-IN ("pin_host" option / S3R_PIN_HOST=1): cudaHostRegister the caller's frame buffer so the D2H
@@ -506,6 +562,23 @@ static bool sentinels_gone(const uint32_t *dst, size_t n) {
     return dst[0] != kSentinel && dst[n / 2] != kSentinel && dst[n - 1] != kSentinel;
 }
 
+static int ensure_staging(S3RRenderer *r, size_t bytes) {
+    if (r->staging_bytes < bytes) {
+        if (r->staging) { cudaFreeHost(r->staging); r->staging = nullptr; r->staging_bytes = 0; }
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&r->staging), bytes));
+        r->staging_bytes = bytes;
+    }
+    if (!r->copier) {
+        int n = r->opt_copy_threads;
+        if (n <= 0) {  // measured on the 16-core B200 host: 14 workers keep up with 24-bit PCIe transport
+            const unsigned hc = std::thread::hardware_concurrency();
+            n = (int)std::min<unsigned>(14, hc > 3 ? hc - 2 : 1);
+        }
+        r->copier = new HostCopier(n);
+    }
+    return S3R_OK;
+}
+
 extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
                                uint32_t y0, uint32_t y1, uint32_t *host_out) {
     if (!r || !cams || !host_out) { return fail(S3R_E_ARG, "null argument"); }
@@ -517,13 +590,65 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
     for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
         const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
         uint32_t *dst = host_out + view_px * v0;
+        // 24-bit transport: the top byte of every pixel is zero, so only 3 bytes per pixel cross PCIe and
+        // the copy threads expand them while moving staging -> caller buffer
+        const bool packed = !pinned && r->opt_pack24;
+        const size_t bpp = packed ? 3 : 4;
+        const size_t chunk_bytes = view_px * nv * bpp;
         CUDA_TRY(r->frame.ensure(view_px * nv));
+        if (!pinned) { int rc = ensure_staging(r, chunk_bytes + 64); if (rc) { return rc; } }
         for (int attempt = 0; attempt < 8; attempt++) {
-            int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream);
+            // ---- enqueue: geometry, banded raster, one D2H per band/slice on the copy stream -----
+            uint32_t band_rows[S3RRenderer::MAX_SLICES];
+            const int bands = nv == 1 ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
+            int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream, bands, band_rows, packed);
             if (rc) { return rc; }
             r->last_views = nv; r->last_W = W; r->last_H = H;
+            std::vector<CopySlice> slices;
+            uint8_t *target = pinned ? reinterpret_cast<uint8_t *>(dst) : r->staging;
             if (pinned) { plant_sentinels(dst, view_px * nv); }
-            CUDA_TRY(cudaMemcpyAsync(dst, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost, r->stream));
+            int n_ev = 0;
+            if (nv == 1) {
+                const int nb = std::max(1, std::min<int>(bands, (int)((y1 - 1) / TILE_H - y0 / TILE_H + 1)));
+                uint32_t row = 0;
+                for (int b = 0; b < nb; b++) {
+                    const size_t pa = (size_t)row * W, pe = (size_t)band_rows[b] * W;
+                    const size_t a = pa * bpp, e = pe * bpp;
+                    row = band_rows[b];
+                    CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[b], 0));
+                    if (e > a) {
+                        CUDA_TRY(cudaMemcpyAsync(target + a, reinterpret_cast<uint8_t *>(r->frame.p) + a, e - a,
+                                                 cudaMemcpyDeviceToHost, r->copy_stream));
+                        CUDA_TRY(cudaEventRecord(r->ev_copy[n_ev], r->copy_stream));
+                        slices.push_back(CopySlice{r->staging + a, reinterpret_cast<uint8_t *>(dst) + pa * 4, pe - pa});
+                        n_ev++;
+                    }
+                }
+            } else {
+                CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[0], 0));
+                const size_t total_px = view_px * nv;
+                const size_t n_sl = std::min<size_t>(S3RRenderer::MAX_SLICES, std::max<size_t>(1, chunk_bytes >> 22));
+                for (size_t i = 0; i < n_sl; i++) {
+                    const size_t pa = (total_px * i / n_sl) & ~(size_t)63;
+                    const size_t pe = i + 1 == n_sl ? total_px : (total_px * (i + 1) / n_sl) & ~(size_t)63;
+                    if (pe <= pa) { continue; }
+                    CUDA_TRY(cudaMemcpyAsync(target + pa * bpp, reinterpret_cast<uint8_t *>(r->frame.p) + pa * bpp, (pe - pa) * bpp,
+                                             cudaMemcpyDeviceToHost, r->copy_stream));
+                    CUDA_TRY(cudaEventRecord(r->ev_copy[n_ev], r->copy_stream));
+                    slices.push_back(CopySlice{r->staging + pa * bpp, reinterpret_cast<uint8_t *>(dst) + pa * 4, pe - pa});
+                    n_ev++;
+                }
+            }
+            // ---- drain: as each slice lands in staging the worker threads move it to the caller ----
+            if (!pinned) { r->copier->begin(&slices, packed); }
+            cudaError_t ce = cudaSuccess;
+            for (int i = 0; i < n_ev; i++) {
+                const cudaError_t e1 = cudaEventSynchronize(r->ev_copy[i]);
+                if (e1 != cudaSuccess) { ce = e1; }
+                if (!pinned) { r->copier->publish(i + 1); }
+            }
+            if (!pinned) { r->copier->wait(); }
+            if (ce != cudaSuccess) { return fail(S3R_E_CUDA, std::string("device-to-host copy: ") + cudaGetErrorString(ce)); }
             rc = finish_on(r, r->stream);
             if (rc < 0) { return rc; }
             if (rc == 0) {
@@ -643,6 +768,15 @@ extern "C" int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raste
 extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!r || !name) { return fail(S3R_E_ARG, "null argument"); }
     if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
+    if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
+    if (!strcmp(name, "pack24")) { r->opt_pack24 = value != 0; return S3R_OK; }
+    if (!strcmp(name, "host_bands")) { r->opt_host_bands = (int)std::max<int64_t>(1, value); return S3R_OK; }
+    if (!strcmp(name, "copy_threads")) {
+        cudaStreamSynchronize(r->stream);
+        delete r->copier; r->copier = nullptr;
+        r->opt_copy_threads = (int)value;
+        return S3R_OK;
+    }
     if (!strcmp(name, "timing")) { r->opt_timing = value != 0; return S3R_OK; }
     if (!strcmp(name, "pin_host")) { r->opt_pin_host = value != 0; if (!value) { unpin_all(r); } return S3R_OK; }
     if (!strcmp(name, "views_per_chunk")) {

@@ -283,3 +283,45 @@ def test_device_walk_jump_equals_sequential_adds(gpu_renderer, oracle_port):
         live = k > step
         want[live] = (want[live] + d[live]).astype(np.float32)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).sum())
+
+
+def test_fused_and_multi_kernel_geometry_agree(renderer_lib, oracle_port):
+    """Small scenes take the single-CTA fused geometry kernel; it must produce the same frame and the same
+    setup records as the general eight-launch path (and as the oracle)."""
+    sc = S.shipped_scene(2, regular_floor=True)  # 1849 triangles: several 256-triangle chunks
+    r = renderer_lib.Renderer(0)
+    r.load_scene(sc)
+    osc = oracle_port.OracleScene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    for f in (40, 150, 275):
+        r.set_option("fused_small", 1)
+        a = r.render(mats[f], 1280, 720)[0]
+        sa, la = r.setups(), r.stats()
+        r.set_option("fused_small", 0)
+        b = r.render(mats[f], 1280, 720)[0]
+        sb, lb = r.setups(), r.stats()
+        assert_same(a, b, f"fused vs general frame {f}")
+        assert sa.tobytes() == sb.tobytes()
+        geo = ('triangles_in', 'near_rejected', 'clipped', 'spawned', 'culled', 'setups', 'overflow')
+        assert {k: la[k] for k in geo} == {k: lb[k] for k in geo}  # the fused path keeps no bin statistics
+        assert_same(a, osc.render(mats[f], 1280, 720)["pixels"], f"fused vs oracle frame {f}")
+    r.close()
+
+
+def test_host_transport_variants_agree(renderer_lib):
+    """24-bit vs 32-bit PCIe transport, 1 vs 8 raster/copy bands, pinned vs staged: same bytes."""
+    sc = S.shipped_scene(1)
+    r = renderer_lib.Renderer(0)
+    r.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script("flythrough", 600))[330]
+    for (W, H) in ((1920, 1080), (1000, 563), (48, 40)):
+        ref = None
+        for pack, bands, pin in ((1, 8, 0), (0, 8, 0), (1, 1, 0), (0, 3, 0), (1, 8, 1)):
+            r.set_option("pack24", pack); r.set_option("host_bands", bands); r.set_option("pin_host", pin)
+            out = np.full((1, H, W), 0x55555555, np.uint32)
+            got = r.render(m, W, H, out=out)[0]
+            ref = got.copy() if ref is None else ref
+            assert_same(got, ref, f"{W}x{H} pack={pack} bands={bands} pin={pin}")
+            assert (got >> 24 == 0).all()
+        r.set_option("pin_host", 0)
+    r.close()
