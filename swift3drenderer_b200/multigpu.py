@@ -1,0 +1,54 @@
+"""Multi-GPU host logic: one process per GPU over ``torch.distributed``.
+
+Two partitions (BASELINE.json north_star):
+
+* frame-parallel — ``frame_shard`` deals camera poses to ranks; no collective on the data path.
+* screen bands   — ``band_edges`` splits the rows ``[0, H)`` into one contiguous band per rank; every rank
+  runs the geometry stages on the whole scene and rasterises only its band (each triangle's barycentric
+  walk starts at the triangle's own ymin, so a band boundary changes no pixel); ``assemble_bands``
+  concatenates the bands on every rank with one all-gather (NCCL over NVLink on GPUs; gloo in the CPU test).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def band_edges(height: int, world: int) -> List[Tuple[int, int]]:
+    """Rows [y0, y1) of each rank's band: as equal as possible, every band non-empty while world <= height."""
+    assert world >= 1 and height >= world
+    return [(height * k // world, height * (k + 1) // world) for k in range(world)]
+
+
+def frame_shard(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous block of frame indices for `rank` (camera poses are precomputed on the host)."""
+    return range(n_frames * rank // world, n_frames * (rank + 1) // world)
+
+
+def assemble_bands(band: torch.Tensor, height: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """All-gathers per-rank bands ``(rows_k, W)`` into the full ``(H, W)`` frame on every rank.
+
+    Bands may differ by one row, so each rank contributes a buffer padded to the tallest band and the
+    padding is dropped after the collective."""
+    edges = band_edges(height, world)
+    assert band.shape[0] == edges[rank][1] - edges[rank][0]
+    width = band.shape[1]
+    tallest = max(b - a for a, b in edges)
+    send = torch.zeros((tallest, width), dtype=band.dtype, device=band.device)
+    send[: band.shape[0]] = band
+    recv = torch.empty((world, tallest, width), dtype=band.dtype, device=band.device)
+    if world == 1:
+        recv[0] = send
+    else:
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    return torch.cat([recv[k, : b - a] for k, (a, b) in enumerate(edges)], 0)
+
+
+def render_banded(render_band: Callable[[int, int], torch.Tensor], height: int, rank: int, world: int,
+                  group=None) -> torch.Tensor:
+    """`render_band(y0, y1)` must return this rank's rows as an ``(y1 - y0, W)`` int32 tensor (on the GPU it
+    wraps ``Renderer.render_device(..., y0=y0, y1=y1)``); returns the assembled frame."""
+    y0, y1 = band_edges(height, world)[rank]
+    return assemble_bands(render_band(y0, y1), height, rank, world, group)
