@@ -46,7 +46,8 @@ __device__ __forceinline__ float3 add3(float3 a, float3 b) { return make_float3(
 __device__ __forceinline__ float3 scale3(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 // simd_fast_normalize as pinned by the oracle shim: v * (1 / sqrt(dot(v, v)))
-__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, 1.0f / sqrtf(dot3(a, a))); }
+// (1.0f / x is the correctly rounded reciprocal, and so is __frcp_rn(x): same bits, fewer instructions)
+__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, __frcp_rn(__fsqrt_rn(dot3(a, a)))); }
 // EDGE_FUNCTION(a, b, c), render.cpp:9
 __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by, float cx, float cy) {
     return (cx - ax) * (ay - by) + (cy - ay) * (bx - ax);
@@ -137,7 +138,7 @@ __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, c
     if (min_x >= f.fw || min_y >= f.fh) { return false; }
     const float area = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, d2.rv.x, d2.rv.y);
     if (area < 10) { return false; }
-    const float inv_area = 1 / area;
+    const float inv_area = __frcp_rn(area);  // 1 / area
     const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
     const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
     const float px = (float)xmin + 0.5f, py = (float)ymin + 0.5f;
@@ -149,7 +150,7 @@ __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, c
     v.wstart[2] = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, px, py) * inv_area;
     v.dx[0] = (d1.rv.y - d2.rv.y) * inv_area; v.dx[1] = (d2.rv.y - d0.rv.y) * inv_area; v.dx[2] = (d0.rv.y - d1.rv.y) * inv_area;
     v.dy[0] = (d2.rv.x - d1.rv.x) * inv_area; v.dy[1] = (d0.rv.x - d2.rv.x) * inv_area; v.dy[2] = (d1.rv.x - d0.rv.x) * inv_area;
-    v.rvz[0] = 1 / d0.rv.z; v.rvz[1] = 1 / d1.rv.z; v.rvz[2] = 1 / d2.rv.z;
+    v.rvz[0] = __frcp_rn(d0.rv.z); v.rvz[1] = __frcp_rn(d1.rv.z); v.rvz[2] = __frcp_rn(d2.rv.z);  // 1 / z
     const Corner *d[3] = {&d0, &d1, &d2};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -363,6 +364,29 @@ __global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Fr
 // K3 — sort-middle binning (count -> scan -> fill).  Entries are (order << 32 | slot) so that each
 // tile can restore the reference's processing order with one sort.
 // ------------------------------------------------------------------------------------------------
+// Conservative trivial reject of a (triangle, tile) pair: true only if one barycentric weight is
+// provably negative at every pixel of the tile (clipped to the bbox), i.e. no pixel there can pass the
+// inside test (render.cpp:362), so skipping the pair cannot change the frame.
+// The walked weight differs from the real-valued linear function L(x, y) = wstart + (x - xmin) dx +
+// (y - ymin) dy only by accumulated rounding: each of the at most (bw + bh) additions is off by at most
+// half an ulp, i.e. 2^-24 of the largest magnitude on the way (<= max |L| over the bbox corners).  The
+// margin used is more than twice that bound plus the error of evaluating L in binary32 here.
+__device__ __forceinline__ bool tile_outside_triangle(const SetupVis &v, uint32_t tx0, uint32_t ylo_t, uint32_t yhi_t) {
+    const uint32_t x0 = max(tx0, (uint32_t)v.xmin), x1 = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
+    const uint32_t y0 = max(ylo_t, (uint32_t)v.ymin), y1 = min(yhi_t - 1u, (uint32_t)v.ymax);
+    const float bw = (float)(v.xmax - v.xmin), bh = (float)(v.ymax - v.ymin);
+    const float fx0 = (float)(x0 - v.xmin), fx1 = (float)(x1 - v.xmin), fy0 = (float)(y0 - v.ymin), fy1 = (float)(y1 - v.ymin);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float ws = v.wstart[c], dx = v.dx[c], dy = v.dy[c];
+        const float wmax = fabsf(ws) + fabsf(dx) * bw + fabsf(dy) * bh;          // >= max |L| over the bbox
+        const float margin = (bw + bh + 16.f) * 2.4e-7f * (wmax + 1.f);
+        const float best = ws + (dx > 0.f ? fx1 : fx0) * dx + (dy > 0.f ? fy1 : fy0) * dy;   // max of L over the rectangle
+        if (best < -margin) { return true; }
+    }
+    return false;
+}
+
 struct TileRange { uint32_t tx0, tx1, ty0, ty1; bool empty; };
 
 __device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
@@ -403,8 +427,13 @@ __device__ __forceinline__ void bin_small_body(const Frame &f, uint32_t view, ui
             }
             continue;
         }
+        const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
         for (uint32_t ty = r.ty0; ty <= r.ty1; ty++) {
-            for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) { bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z); }
+            const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
+            for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) {
+                if (ntiles > 1u && tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }
+                bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z);
+            }
         }
     }
 }
@@ -423,8 +452,11 @@ __device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view, uint
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
         const uint32_t nx = r.tx1 - r.tx0 + 1u, ntiles = nx * (r.ty1 - r.ty0 + 1u);
+        const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
         for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) {
             const uint32_t ty = r.ty0 + i / nx, tx = r.tx0 + i % nx;
+            const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
+            if (tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }   // same decision in count and fill
             bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z);
         }
     }
@@ -591,7 +623,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const Frame &f, uint32_t view, u
 }
 
 __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_t j) {
-    return row * TILE_W + seg * SEG + (j ^ seg);  // spreads a thread's 8-pixel run over the 16-byte bank groups
+    return row * TILE_W + seg * SEG + (j ^ (seg & 7u));  // spreads a thread's 8-pixel run over the 16-byte bank groups
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
@@ -620,7 +652,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             if (xmax >= tx0 && xmin < tx0 + TILE_W && ymax >= ylo_t && ymin < yhi_t) {
-                sh.u.entries[atomicAdd(&s_n, 1u)] = ((unsigned long long)head.z << 32) | slot;
+                const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
+                if (!tile_outside_triangle(*vp, tx0, ylo_t, yhi_t)) {
+                    sh.u.entries[atomicAdd(&s_n, 1u)] = ((unsigned long long)head.z << 32) | slot;
+                }
             }
         }
         __syncthreads();
@@ -737,11 +772,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         // host transport format: 3 bytes per pixel.  Pack each row of 64 pixels into 48 words
         // (reusing the dead per-pixel state), then bulk-copy 192-byte rows.
         __syncthreads();
-        uint32_t *packed = reinterpret_cast<uint32_t *>(sh.u.state);   // [TILE_H][48]
+        constexpr uint32_t PW = TILE_W * 3u / 4u;                       // packed words per tile row
+        uint32_t *packed = reinterpret_cast<uint32_t *>(sh.u.state);   // [TILE_H][PW]
         for (uint32_t g = tid; g < TILE_H * (TILE_W / 4); g += RASTER_THREADS) {
             const uint32_t pr = g / (TILE_W / 4), q = g % (TILE_W / 4);
             const uint4 p = *reinterpret_cast<const uint4 *>(&sh.colour[pr][q * 4]);
-            uint32_t *o = packed + pr * 48u + q * 3u;
+            uint32_t *o = packed + pr * PW + q * 3u;
             o[0] = p.x | (p.y << 24);
             o[1] = (p.y >> 8) | (p.z << 16);
             o[2] = (p.z >> 16) | (p.w << 8);
@@ -754,7 +790,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
                 const uint32_t yy = ty0 + tid;
                 if (yy >= f.y0 && yy < f.y1) {
                     uint8_t *dst = out8 + ((size_t)(yy - f.y0) * f.W + tx0) * 3u;
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + tid * 48u);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + tid * PW);
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(dst), "r"(src), "r"(cols * 3u) : "memory");
                 }
@@ -767,7 +803,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             for (uint32_t i = tid; i < TILE_H * TILE_W * 3u; i += RASTER_THREADS) {
                 const uint32_t pr = i / (TILE_W * 3u), off = i % (TILE_W * 3u), yy = ty0 + pr;
                 if (off < cols * 3u && yy >= f.y0 && yy < f.y1) {
-                    out8[((size_t)(yy - f.y0) * f.W + tx0) * 3u + off] = pb[pr * 192u + off];
+                    out8[((size_t)(yy - f.y0) * f.W + tx0) * 3u + off] = pb[pr * (PW * 4u) + off];
                 }
             }
         }

@@ -23,11 +23,16 @@
 
 namespace s3r {
 
-constexpr int TILE_W = 64;
-constexpr int TILE_H = 32;
+#ifndef S3R_TILE_W
+#define S3R_TILE_W 64
+#define S3R_TILE_H 32
+#endif
+constexpr int TILE_W = S3R_TILE_W;
+constexpr int TILE_H = S3R_TILE_H;
 constexpr int RASTER_THREADS = 256;         // (TILE_W / SEG) * TILE_H
 constexpr int SEG = 8;                      // pixels per thread in the visibility pass
-constexpr int SEGS_PER_ROW = TILE_W / SEG;  // 8
+constexpr int SEGS_PER_ROW = TILE_W / SEG;
+static_assert(SEGS_PER_ROW * TILE_H == RASTER_THREADS, "one thread per 8-pixel segment");
 constexpr int BATCH = 8;                    // triangles staged per visibility batch
 constexpr int SORT_CAP = 4096;              // bin entries sorted in shared memory (longer lists: in HBM)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively

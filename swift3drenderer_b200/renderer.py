@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "render.so")
+LIB_PATH = os.environ.get("S3R_LIB") or os.path.join(HERE, "lib", "render.so")  # S3R_LIB: experiment builds
 CSRC = os.path.join(HERE, "csrc")
 
 
