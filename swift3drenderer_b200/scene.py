@@ -472,7 +472,7 @@ def _batched_axes(rng: np.random.RandomState, n: int):
 def icosahedron_field(
     n: int,
     seed: int = 7,
-    extent: float = 100.0,
+    extent=100.0,
     r_range: Tuple[float, float] = (1.0, 10.0),
     textured: bool = True,
     shared_vertices: bool = True,
@@ -495,7 +495,8 @@ def icosahedron_field(
     cz = np.array([0, 0, 0, 0, k, k, -k, -k, l, -l, l, -l], np.float32)[None, :, None]
     unit = cx * X + cy * Y + cz * Z  # (n, 12, 3)
     r = rng.uniform(r_range[0], r_range[1], n).astype(np.float32)[:, None, None]
-    p = (rng.uniform(-extent, extent, (n, 3)).astype(np.float32) + np.asarray(center, np.float32))[:, None, :]
+    ext = np.broadcast_to(np.asarray(extent, np.float32), (3,))
+    p = ((rng.uniform(-1, 1, (n, 3)) * ext).astype(np.float32) + np.asarray(center, np.float32))[:, None, :]
     pos = (r * unit + p).astype(np.float32)  # (n, 12, 3)
 
     faces = np.asarray(ICOSA_FACES, np.int64)  # (20, 3)
@@ -529,12 +530,38 @@ def icosahedron_field(
     return Scene(verts, vi, at.reshape(-1), ai, tx)
 
 
-def clip_stress_scene(n: int = 50000, seed: int = 11, textures: Optional[np.ndarray] = None) -> Scene:
-    """Camera (at the origin, looking down -z) sits inside a dense field so that a large share of
-    triangles straddle z = near.  Unshared vertices keep the reference inside its scratch (H13)."""
-    return icosahedron_field(
-        n, seed=seed, extent=3.0, r_range=(0.3, 3.0), textured=True, shared_vertices=False, textures=textures
+def concat_scenes(a: Scene, b: Scene) -> Scene:
+    """Appends scene ``b`` to ``a`` (indices re-based; both must use the same texture set)."""
+    assert a.textures.shape == b.textures.shape and np.array_equal(a.textures, b.textures)
+    return Scene(
+        np.concatenate([a.vertices, b.vertices]),
+        np.concatenate([a.vertex_indices, b.vertex_indices + np.uint64(a.vertices.shape[0])]),
+        np.concatenate([a.attributes, b.attributes]),
+        np.concatenate([a.attribute_indices, b.attribute_indices + np.uint64(a.attributes.shape[0])]),
+        a.textures,
     )
+
+
+def clip_stress_scene(n: int = 50000, seed: int = 11, textures: Optional[np.ndarray] = None) -> Scene:
+    """C4: the camera (origin, looking down -z) sits inside a dense field.  70 % of the solids lie in a
+    thin slab around the near plane z = -0.1 (about half of their triangles straddle it), 30 % in front of
+    the camera so that clipped and unclipped geometry is actually visible.  Unshared vertices keep the
+    reference inside its 2x scratch arrays (hazard H13).  Measured straddle fraction: ~36 %."""
+    tx = procedural_textures(2) if textures is None else textures
+    n_slab = int(n * 0.7)
+    slab = icosahedron_field(n_slab, seed=seed, extent=(40.0, 25.0, 1.5), r_range=(2.0, 3.0), textured=True,
+                             shared_vertices=False, textures=tx)
+    front = icosahedron_field(n - n_slab, seed=seed + 1, extent=(30.0, 17.0, 25.0), r_range=(0.3, 1.5), textured=True,
+                              shared_vertices=False, textures=tx, center=(0.0, 0.0, -28.0))
+    return concat_scenes(slab, front)
+
+
+def c3_scene(n: int = 1_000_000, seed: int = 7, textures: Optional[np.ndarray] = None) -> Scene:
+    """C3: n textured icosahedrons (20 n triangles, shared vertices, per-corner attributes) filling the
+    view frustum around z = -4000 so that ~21 % of the triangles survive the area >= 10 cull at 4K from
+    the origin (10-30 %) with a depth complexity of ~7."""
+    return icosahedron_field(n, seed=seed, extent=(1500.0, 850.0, 800.0), r_range=(1.0, 10.0), textured=True,
+                             shared_vertices=True, textures=textures, center=(0.0, 0.0, -4000.0))
 
 
 # ----------------------------------------------------------------------------------------
@@ -558,6 +585,11 @@ def input_script(name: str, frames: int) -> np.ndarray:
                 inp[f]["up"] = float(f % 2)
         elif name == "flythrough":  # C2 path, planned below (needs camera feedback)
             return _flythrough(frames)
+        elif name == "strafe":  # C4: translate only, so the near plane keeps cutting the slab of solids
+            if (f // 8) % 2 == 0:
+                inp[f]["right"] = 1
+            else:
+                inp[f]["left"] = 1
         elif name == "spin":
             mouse += (11.0, 3.0 * np.sin(f * 0.1))
             inp[f]["up"] = 1 if (f // 20) % 2 == 0 else 0
