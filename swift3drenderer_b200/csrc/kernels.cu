@@ -185,6 +185,52 @@ __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, c
     return true;
 }
 
+// Conservative trivial reject of a (triangle, tile) pair: true only if one barycentric weight is
+// provably negative at every pixel of the tile (clipped to the bbox), i.e. no pixel there can pass the
+// inside test (render.cpp:362), so skipping the pair cannot change the frame.
+// The walked weight differs from the real-valued linear function L(x, y) = wstart + (x - xmin) dx +
+// (y - ymin) dy only by accumulated rounding: each of the at most (bw + bh) additions is off by at most
+// half an ulp, i.e. 2^-24 of the largest magnitude on the way (<= max |L| over the bbox corners).  The
+// margin used is more than twice that bound plus the error of evaluating L in binary32 here.
+__device__ __forceinline__ bool tile_outside_triangle(const SetupVis &v, uint32_t tx0, uint32_t ylo_t, uint32_t yhi_t) {
+    const uint32_t x0 = max(tx0, (uint32_t)v.xmin), x1 = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
+    const uint32_t y0 = max(ylo_t, (uint32_t)v.ymin), y1 = min(yhi_t - 1u, (uint32_t)v.ymax);
+    const float bw = (float)(v.xmax - v.xmin), bh = (float)(v.ymax - v.ymin);
+    const float fx0 = (float)(x0 - v.xmin), fx1 = (float)(x1 - v.xmin), fy0 = (float)(y0 - v.ymin), fy1 = (float)(y1 - v.ymin);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float ws = v.wstart[c], dx = v.dx[c], dy = v.dy[c];
+        const float wmax = fabsf(ws) + fabsf(dx) * bw + fabsf(dy) * bh;          // >= max |L| over the bbox
+        const float margin = (bw + bh + 16.f) * 2.4e-7f * (wmax + 1.f);
+        const float best = ws + (dx > 0.f ? fx1 : fx0) * dx + (dy > 0.f ? fy1 : fy0) * dy;   // max of L over the rectangle
+        if (best < -margin) { return true; }
+    }
+    return false;
+}
+
+struct TileRange { uint32_t tx0, tx1, ty0, ty1; bool empty; };
+
+__device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
+    TileRange r;
+    const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
+    r.empty = ylo > yhi;
+    r.tx0 = xmin / TILE_W; r.tx1 = xmax / TILE_W;
+    r.ty0 = ylo / TILE_H - f.tile_row0; r.ty1 = yhi / TILE_H - f.tile_row0;
+    return r;
+}
+
+template <bool FILL>
+__device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot, uint32_t order) {
+    if (!FILL) {
+        atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
+    } else {
+        const uint32_t pos = atomicAdd(f.tile_cursor + view * f.tile_stride + tile, 1u);
+        if (pos < f.entry_cap) {
+            f.entries[(size_t)view * f.entry_cap + pos] = ((unsigned long long)order << 32) | slot;
+        }
+    }
+}
+
 struct SetupShared {
     uint32_t list[256];
     uint32_t count;
@@ -222,6 +268,28 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
     const uint4 *ss = reinterpret_cast<const uint4 *>(&s);
 #pragma unroll
     for (int i = 0; i < 8; i++) { ds[i] = ss[i]; }
+    f.head[(size_t)view * f.setup_cap + slot] = sv[0];   // bbox + order key + kind: all binning needs
+}
+
+// K3 count pass for one survivor: tile histogram for triangles over few tiles (with the conservative
+// outside test), everything larger goes to the cooperative big list.
+__device__ __forceinline__ void count_tiles(const Frame &f, uint32_t view, uint32_t slot, const SetupVis &v) {
+    const TileRange r = tile_range(f, v.xmin, v.xmax, v.ymin, v.ymax);
+    if (r.empty) { return; }
+    const uint32_t ntiles = (r.tx1 - r.tx0 + 1u) * (r.ty1 - r.ty0 + 1u);
+    if (ntiles > BIG_TILES) {
+        const uint32_t pos = atomicAdd(f.counters + view * C_COUNT + C_BIG, 1u);
+        if (pos < f.big_cap) { f.big_list[(size_t)view * f.big_cap + pos] = slot; }
+        else { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 4u); }
+        return;
+    }
+    for (uint32_t ty = r.ty0; ty <= r.ty1; ty++) {
+        const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
+        for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) {
+            if (ntiles > 1u && tile_outside_triangle(v, tx * TILE_W, ylo_t, yhi_t)) { continue; }
+            atomicAdd(f.tile_count + view * f.tile_stride + ty * f.tiles_x + tx, 1u);
+        }
+    }
 }
 
 __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const Corner &d1, const Corner &d2,
@@ -238,6 +306,7 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
     if (keep) {
         if (slot < f.setup_cap) {
             store_setup(f, view, slot, v, s);
+            if (!f.direct_bin) { count_tiles(f, view, slot, v); }   // K3 count pass, fused
         } else {
             atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 1u);
         }
@@ -289,8 +358,9 @@ __device__ __forceinline__ bool clip_near(Corner &d0, Corner &d1, Corner &d2, Co
     return two_in_front;
 }
 
-// One 256-triangle chunk, executed by one 256-thread CTA (all threads must call).
-__device__ __forceinline__ void setup_body(const Frame &f, const Cam &cam, uint32_t view, uint32_t chunk, SetupShared &sh) {
+// Phase 1 of K2 for one 256-triangle chunk (one 256-thread CTA, all threads call): classify from the
+// raster-space vertices only and compact the work items into sh.list[0 .. sh.count).
+__device__ __forceinline__ void classify_body(const Frame &f, uint32_t view, uint32_t chunk, SetupShared &sh) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
     if (tid == 0) { sh.count = 0; }
     if (tid < 4) { sh.stats[tid] = 0; }
@@ -311,7 +381,10 @@ __device__ __forceinline__ void setup_body(const Frame &f, const Cam &cam, uint3
             const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
             const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
             const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
-            if (off || edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) { culled = true; } else { cls = 1; }
+            // screen-band partition: a triangle whose rows cannot meet [y0, y1) contributes nothing to this band
+            // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
+            const bool off_band = max_y < f.band_lo || min_y >= f.band_hi;
+            if (off || off_band || edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) { culled = true; } else { cls = 1; }
         }
     }
     {   // warp-ballot compaction of the work items into shared memory
@@ -328,8 +401,11 @@ __device__ __forceinline__ void setup_body(const Frame &f, const Cam &cam, uint3
         if (cls != 0) { sh.list[base + __popc(m_work & ((1u << lane) - 1u))] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
     }
     __syncthreads();
+}
 
-    // ---- phase 2: dense full setup of the compacted work items (count <= 256: one pass) --------
+// Phase 2 of K2: dense full setup of up to 256 work items held in sh.list (all 256 threads call).
+__device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, uint32_t view, SetupShared &sh) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
     const uint32_t count = sh.count;
     const bool valid = tid < count;
     Corner d0, d1, d2, s0, s1, s2;
@@ -355,66 +431,44 @@ __device__ __forceinline__ void setup_body(const Frame &f, const Cam &cam, uint3
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) triangle_setup(const __grid_constant__ Frame f) {
+// K2a: classify every input triangle (light: ~32 registers, full occupancy) and append the work items of
+// each CTA to the global work list with one atomic per CTA.
+__global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
-    setup_body(f, load_cam(f.cams + 12 * blockIdx.y), blockIdx.y, blockIdx.x, sh);
+    const uint32_t view = blockIdx.y, tid = threadIdx.x;
+    classify_body(f, view, blockIdx.x, sh);
+    const uint32_t count = sh.count;
+    if (tid == 0 && count) { sh.base = atomicAdd(f.counters + view * C_COUNT + C_WORK, count); }
+    __syncthreads();
+    if (tid < count) { f.worklist[(size_t)view * f.T + sh.base + tid] = sh.list[tid]; }
+    if (tid < 4 && sh.stats[tid]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR + tid, sh.stats[tid]); }
+}
+
+// K2b: dense setup over the compacted work list (persistent grid-stride; every lane has a survivor
+// candidate, so the register-heavy gather/clip/setup code runs at full lane efficiency).
+__global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__ Frame f) {
+    __shared__ SetupShared sh;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x;
+    const Cam cam = load_cam(f.cams + 12 * view);
+    const uint32_t n_work = f.counters[view * C_COUNT + C_WORK];
+    for (uint32_t base = blockIdx.x * 256u; base < n_work; base += gridDim.x * 256u) {
+        if (tid == 0) { sh.count = min(256u, n_work - base); }
+        if (tid < 4) { sh.stats[tid] = 0; }
+        if (base + tid < n_work) { sh.list[tid] = f.worklist[(size_t)view * f.T + base + tid]; }
+        __syncthreads();
+        process_items(f, cam, view, sh);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K3 — sort-middle binning (count -> scan -> fill).  Entries are (order << 32 | slot) so that each
 // tile can restore the reference's processing order with one sort.
 // ------------------------------------------------------------------------------------------------
-// Conservative trivial reject of a (triangle, tile) pair: true only if one barycentric weight is
-// provably negative at every pixel of the tile (clipped to the bbox), i.e. no pixel there can pass the
-// inside test (render.cpp:362), so skipping the pair cannot change the frame.
-// The walked weight differs from the real-valued linear function L(x, y) = wstart + (x - xmin) dx +
-// (y - ymin) dy only by accumulated rounding: each of the at most (bw + bh) additions is off by at most
-// half an ulp, i.e. 2^-24 of the largest magnitude on the way (<= max |L| over the bbox corners).  The
-// margin used is more than twice that bound plus the error of evaluating L in binary32 here.
-__device__ __forceinline__ bool tile_outside_triangle(const SetupVis &v, uint32_t tx0, uint32_t ylo_t, uint32_t yhi_t) {
-    const uint32_t x0 = max(tx0, (uint32_t)v.xmin), x1 = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
-    const uint32_t y0 = max(ylo_t, (uint32_t)v.ymin), y1 = min(yhi_t - 1u, (uint32_t)v.ymax);
-    const float bw = (float)(v.xmax - v.xmin), bh = (float)(v.ymax - v.ymin);
-    const float fx0 = (float)(x0 - v.xmin), fx1 = (float)(x1 - v.xmin), fy0 = (float)(y0 - v.ymin), fy1 = (float)(y1 - v.ymin);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const float ws = v.wstart[c], dx = v.dx[c], dy = v.dy[c];
-        const float wmax = fabsf(ws) + fabsf(dx) * bw + fabsf(dy) * bh;          // >= max |L| over the bbox
-        const float margin = (bw + bh + 16.f) * 2.4e-7f * (wmax + 1.f);
-        const float best = ws + (dx > 0.f ? fx1 : fx0) * dx + (dy > 0.f ? fy1 : fy0) * dy;   // max of L over the rectangle
-        if (best < -margin) { return true; }
-    }
-    return false;
-}
-
-struct TileRange { uint32_t tx0, tx1, ty0, ty1; bool empty; };
-
-__device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
-    TileRange r;
-    const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
-    r.empty = ylo > yhi;
-    r.tx0 = xmin / TILE_W; r.tx1 = xmax / TILE_W;
-    r.ty0 = ylo / TILE_H - f.tile_row0; r.ty1 = yhi / TILE_H - f.tile_row0;
-    return r;
-}
-
-template <bool FILL>
-__device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot, uint32_t order) {
-    if (!FILL) {
-        atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
-    } else {
-        const uint32_t pos = atomicAdd(f.tile_cursor + view * f.tile_stride + tile, 1u);
-        if (pos < f.entry_cap) {
-            f.entries[(size_t)view * f.entry_cap + pos] = ((unsigned long long)order << 32) | slot;
-        }
-    }
-}
-
 template <bool FILL>
 __device__ __forceinline__ void bin_small_body(const Frame &f, uint32_t view, uint32_t first, uint32_t stride) {
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     for (uint32_t slot = first; slot < n; slot += stride) {
-        const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+        const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
         if (r.empty) { continue; }
@@ -448,7 +502,7 @@ __device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view, uint
     const uint32_t n = min(f.counters[view * C_COUNT + C_BIG], f.big_cap);
     for (uint32_t b = first; b < n; b += stride) {
         const uint32_t slot = f.big_list[(size_t)view * f.big_cap + b];
-        const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+        const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
         const uint32_t nx = r.tx1 - r.tx0 + 1u, ntiles = nx * (r.ty1 - r.ty0 + 1u);
@@ -531,7 +585,10 @@ __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Fr
     if (tid < C_COUNT) { f.counters[view * C_COUNT + tid] = 0; }
     for (uint32_t i4 = tid * 4u; i4 < f.Vpad; i4 += 1024u) { vertex_body(f, cam, view, i4); }
     __syncthreads();
-    for (uint32_t chunk = 0; chunk * 256u < f.T; chunk++) { setup_body(f, cam, view, chunk, sh); }
+    for (uint32_t chunk = 0; chunk * 256u < f.T; chunk++) {
+        classify_body(f, view, chunk, sh);
+        process_items(f, cam, view, sh);
+    }
     __syncthreads();
     if (tid == 0) {
         const uint32_t *c = f.counters + view * C_COUNT;
@@ -649,7 +706,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         const uint32_t n_setups = min(f.counters[view * C_COUNT + C_SETUPS], min(f.setup_cap, (uint32_t)SORT_CAP));
         const uint32_t ylo_t = max(ty0, f.y0), yhi_t = min(ty0 + TILE_H, f.y1);   // [ylo_t, yhi_t)
         for (uint32_t slot = tid; slot < n_setups; slot += RASTER_THREADS) {
-            const uint4 head = *reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             if (xmax >= tx0 && xmin < tx0 + TILE_W && ymax >= ylo_t && ymin < yhi_t) {
                 const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
@@ -856,9 +913,9 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
     frame_reset<<<dim3(ceil_div(max(f.n_tiles, (uint32_t)C_COUNT), 256), f.n_views), 256, 0, s>>>(f); launches++;
     vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
-    triangle_setup<<<dim3(max(1u, ceil_div(f.T, 256)), f.n_views), 256, 0, s>>>(f); launches++;
+    triangle_classify<<<dim3(max(1u, ceil_div(f.T, 256)), f.n_views), 256, 0, s>>>(f); launches++;
+    triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
     const uint32_t bin_blocks = min(persistent, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
-    bin_small<false><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;
     bin_big<false><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
     tile_scan<<<f.n_views, 1024, 0, s>>>(f); launches++;
     bin_small<true><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;

@@ -43,7 +43,7 @@ constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.
 constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:96
 
 enum Counter : uint32_t {
-    C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7,
+    C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7, C_WORK = 8,
     C_COUNT = 16
 };
 
@@ -81,12 +81,15 @@ struct Frame {
     uint32_t n_views;
     uint32_t W, H, y0, y1;
     float fw, fh, half_w, half_h, factor;
+    float band_lo, band_hi;   // (float)y0, (float)y1: early band reject in the classify pass
     uint32_t tiles_x, tile_row0, tiles_y, n_tiles;
     uint32_t raster_row0, raster_rows;   // tile rows [raster_row0, raster_row0 + raster_rows) of the band go in one raster launch
     // per-view scratch
     float4 *rv;
     SetupVis *vis;
     SetupShade *shade;
+    uint4 *head;          // per survivor: {xmin | xmax << 16, ymin | ymax << 16, order, kind}
+    uint32_t *worklist;   // [views][T] classify -> setup work items
     uint32_t setup_cap;
     uint32_t *counters;
     uint32_t *sticky;   // [4] across chunks: overflow bits (OR), max setups, max entries, max big
