@@ -226,7 +226,7 @@ __device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t 
     } else {
         const uint32_t pos = atomicAdd(f.tile_cursor + view * f.tile_stride + tile, 1u);
         if (pos < f.entry_cap) {
-            f.entries[(size_t)view * f.entry_cap + pos] = ((unsigned long long)order << 32) | slot;
+            f.entries[(size_t)view * f.entry_cap + pos] = slot;
         }
     }
 }
@@ -600,35 +600,24 @@ __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Fr
 // ------------------------------------------------------------------------------------------------
 // K4 — per-tile rasteriser
 // ------------------------------------------------------------------------------------------------
-struct RasterShared {
-    union {
-        unsigned long long entries[SORT_CAP];          // sorted bin list (32 KB) while walking ...
-        uint4 state[TILE_W * TILE_H];                  // ... then per-pixel winners (w0, w1, w2, slot)
-    } u;
-    uint32_t colour[TILE_H][TILE_W];                   // 8 KB, source of the bulk write-out
-    SetupVis batch[BATCH];                             // 0.5 KB
-    float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];    // 24 KB: exact weights at each 8-pixel segment's first walked pixel
-};
+constexpr uint32_t SMALL_MAX = 16;   // triangles whose whole bbox is at most this wide and high take the per-triangle path
 
-// Ascending bitonic sort of a[0..n) (a may be shared or global); indices >= n act as +inf.
-__device__ __forceinline__ void block_sort(unsigned long long *a, uint32_t n) {
-    uint32_t N = 1;
-    while (N < n) { N <<= 1; }
-    for (uint32_t k = 2; k <= N; k <<= 1) {
-        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {  // flip stage
-            const uint32_t p = i ^ (k - 1u);
-            if (p > i && p < n) { const unsigned long long x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
-        }
-        __syncthreads();
-        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-                const uint32_t p = i ^ j;
-                if (p > i && p < n) { const unsigned long long x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
-            }
-            __syncthreads();
-        }
-    }
-}
+struct RasterShared {
+    union {                                               // 32 KB
+        struct {
+            float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];   // big triangles: exact weights at each 8-pixel segment start
+            SetupVis batch[BATCH];
+        } big;
+        uint4 state[TILE_W * TILE_H];                     // later: per-pixel winners (w0, w1, w2, slot) for shading
+    } u;
+    union {                                               // 16 KB
+        unsigned long long keys[TILE_W * TILE_H];         // small triangles: depth << 32 | ~order, atomicMax
+        uint32_t colour[TILE_H][TILE_W];                  // later: the colour tile, source of the bulk write-out
+    } k;
+    uint32_t slots[SORT_CAP];                             // 16 KB: this tile's triangles when collected in-kernel (direct_bin)
+    uint32_t bigq[RASTER_THREADS];                        // big triangles found in the current 256-entry chunk
+    uint32_t n_list, n_big, any_small;
+};
 
 __device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115-122
     i--; i |= i >> 1; i |= i >> 2; i |= i >> 4;
@@ -683,6 +672,48 @@ __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_
     return row * TILE_W + seg * SEG + (j ^ (seg & 7u));  // spreads a thread's 8-pixel run over the 16-byte bank groups
 }
 
+// Per-triangle walk of a small triangle inside one tile, exactly as the reference walks it
+// (render.cpp:360-382): rows from the triangle's own ymin, pixels from its own xmin, true additions only.
+// PASS 1 publishes depth keys with atomicMax; PASS 2 (after every key is final) lets the winner of each
+// pixel drop its weights for shading.  Keys are depth << 32 | ~order: larger 1/z wins, on equal depth the
+// earlier triangle in the reference's processing order wins (strict '>' at render.cpp:364).
+template <int PASS>
+__device__ __forceinline__ void walk_small(const Frame &f, uint32_t view, uint32_t slot, uint4 head, uint32_t tx0,
+                                           uint32_t ty0, uint32_t ylo_t, uint32_t yhi_t, RasterShared &sh) {
+    const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+    const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+    const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
+    const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
+    const float rz0 = __uint_as_float(q3.y), rz1 = __uint_as_float(q3.z), rz2 = __uint_as_float(q3.w);
+    float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y), wy2 = __uint_as_float(q1.z);
+    const unsigned long long key_lo = (unsigned long long)(~head.z);
+    const uint32_t y_end = min(ymax, yhi_t - 1u), x_end = min(xmax, tx0 + TILE_W - 1u);
+    for (uint32_t y = ymin; y <= y_end; y++) {
+        if (y >= ylo_t) {
+            float w0 = wy0, w1 = wy1, w2 = wy2;
+            for (uint32_t x = xmin; x <= x_end; x++) {
+                if (x >= tx0 && w0 >= 0 && w1 >= 0 && w2 >= 0) {                      // render.cpp:362
+                    const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
+                    if (ooz > 0.f) {                                                 // depth buffer starts at 0, strict '>'
+                        const uint32_t idx = (y - ty0) * TILE_W + (x - tx0);
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo;
+                        if (PASS == 1) {
+                            if (key > sh.k.keys[idx]) { atomicMax(&sh.k.keys[idx], key); }
+                        } else if (sh.k.keys[idx] == key) {
+                            const uint32_t pc = x - tx0;
+                            sh.u.state[(y - ty0) * TILE_W + (pc & ~7u) + ((pc & 7u) ^ ((pc >> 3) & 7u))] =
+                                make_uint4(__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), slot);
+                        }
+                    }
+                }
+                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+            }
+        }
+        wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
@@ -691,32 +722,35 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     const uint32_t tx0 = tile_x * TILE_W, ty0 = (tile_y + f.tile_row0) * TILE_H;
     const uint32_t row = tid / SEGS_PER_ROW, seg = tid % SEGS_PER_ROW;
     const uint32_t y = ty0 + row, sx0 = tx0 + seg * SEG;
+    const uint32_t ylo_t = max(ty0, f.y0), yhi_t = min(ty0 + TILE_H, f.y1);   // rows [ylo_t, yhi_t) of this tile are in the band
 
-    // A capacity overflow anywhere upstream makes the bin lists incomplete: the host regrows the
+    // A capacity overflow anywhere upstream makes the lists incomplete: the host regrows the
     // buffers and renders the frame again, so this launch only has to stay in bounds.
     if (f.counters[view * C_COUNT + C_OVERFLOW] != 0) { return; }
+
+    // ---- this tile's triangle list (unordered: depth keys carry the order) ---------------------
+    if (tid == 0) { sh.n_list = 0; sh.n_big = 0; sh.any_small = 0; }
+#pragma unroll
+    for (int i = 0; i < (TILE_W * TILE_H) / RASTER_THREADS; i++) { sh.k.keys[i * RASTER_THREADS + tid] = 0ull; }
+    __syncthreads();
     uint32_t n;
-    unsigned long long *list = nullptr;
+    const uint32_t *list;
     if (f.direct_bin) {
-        // small scene: collect this tile's triangles straight from the setup list (bbox overlap,
-        // clamped to the band); at most SORT_CAP survivors by construction of the small path
-        __shared__ uint32_t s_n;
-        if (tid == 0) { s_n = 0; }
-        __syncthreads();
+        // small scene: collect straight from the survivors' heads (bbox overlap clamped to the band, plus the
+        // conservative outside test); at most SORT_CAP survivors exist by construction of this mode
         const uint32_t n_setups = min(f.counters[view * C_COUNT + C_SETUPS], min(f.setup_cap, (uint32_t)SORT_CAP));
-        const uint32_t ylo_t = max(ty0, f.y0), yhi_t = min(ty0 + TILE_H, f.y1);   // [ylo_t, yhi_t)
         for (uint32_t slot = tid; slot < n_setups; slot += RASTER_THREADS) {
             const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             if (xmax >= tx0 && xmin < tx0 + TILE_W && ymax >= ylo_t && ymin < yhi_t) {
-                const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
-                if (!tile_outside_triangle(*vp, tx0, ylo_t, yhi_t)) {
-                    sh.u.entries[atomicAdd(&s_n, 1u)] = ((unsigned long long)head.z << 32) | slot;
+                if (!tile_outside_triangle(f.vis[(size_t)view * f.setup_cap + slot], tx0, ylo_t, yhi_t)) {
+                    sh.slots[atomicAdd(&sh.n_list, 1u)] = slot;
                 }
             }
         }
         __syncthreads();
-        n = s_n;
+        n = sh.n_list;
+        list = sh.slots;
     } else {
         const uint32_t begin = f.tile_offset[view * f.tile_stride + tile];
         n = f.tile_offset[view * f.tile_stride + tile + 1] - begin;
@@ -728,37 +762,39 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 #pragma unroll
     for (int j = 0; j < SEG; j++) { depth[j] = 0.f; bw0[j] = bw1[j] = bw2[j] = 0.f; win[j] = NO_TRI; }
 
-    if (n > 0) {
-        // ---- restore the reference's triangle order ------------------------------------------
-        const bool in_smem = n <= SORT_CAP;
-        if (in_smem) {
-            if (!f.direct_bin) {
-                for (uint32_t i = tid; i < n; i += RASTER_THREADS) { sh.u.entries[i] = list[i]; }
-                __syncthreads();
+    // ---- phase 1: visibility.  256 list entries at a time: small triangles are walked by one thread each
+    // (depth keys in shared memory), big ones are queued and then walked by the whole CTA, eight at a time,
+    // every thread owning 8 pixels whose depth/winner/weights stay in registers.
+    for (uint32_t cbase = 0; cbase < n; cbase += RASTER_THREADS) {
+        const uint32_t i = cbase + tid;
+        if (i < n) {
+            const uint32_t slot = list[i];
+            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+            const uint32_t bwid = (head.x >> 16) - (head.x & 0xFFFFu), bhgt = (head.y >> 16) - (head.y & 0xFFFFu);
+            if (bwid < SMALL_MAX && bhgt < SMALL_MAX) {
+                sh.any_small = 1u;
+                walk_small<1>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh);
+            } else {
+                sh.bigq[atomicAdd(&sh.n_big, 1u)] = slot;
             }
-            block_sort(sh.u.entries, n);
-        } else {
-            block_sort(list, n);  // rare: longer than the shared buffer, sort in place in HBM/L2
         }
-        const unsigned long long *sorted = in_smem ? sh.u.entries : list;
-
-        for (uint32_t base = 0; base < n; base += BATCH) {
-            const uint32_t nb = min((uint32_t)BATCH, n - base);
-            // ---- stage the batch's coverage records ---------------------------------------
-            if (tid < nb * 4u) {
+        __syncthreads();
+        const uint32_t nbig = sh.n_big;
+        for (uint32_t base = 0; base < nbig; base += BATCH) {
+            const uint32_t nb = min((uint32_t)BATCH, nbig - base);
+            if (tid < nb * 4u) {   // stage the batch's coverage records
                 const uint32_t b = tid >> 2, q = tid & 3u;
-                const uint32_t slot = (uint32_t)sorted[base + b];
-                reinterpret_cast<uint4 *>(&sh.batch[b])[q] =
-                    reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot)[q];
+                reinterpret_cast<uint4 *>(&sh.u.big.batch[b])[q] =
+                    reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.bigq[base + b])[q];
             }
             __syncthreads();
-            // ---- stage A: exact weights at the first walked pixel of every (triangle, row, segment).
-            // One work item per (triangle, row, barycentric component): jump down the rows from the
-            // triangle's own ymin, jump along the row from its own xmin to the tile, then take true
-            // steps through the tile, dropping the value at every 8-pixel segment boundary.
+            // stage A: exact weights at the first walked pixel of every (triangle, row, segment).  One work
+            // item per (triangle, row, barycentric component): jump down the rows from the triangle's own
+            // ymin, jump along the row from its own xmin to the tile, then take true steps through the
+            // tile, dropping the value at every 8-pixel segment boundary.
             for (uint32_t item = tid; item < nb * (TILE_H * 3u); item += RASTER_THREADS) {
                 const uint32_t b = item / (TILE_H * 3u), rc = item % (TILE_H * 3u), r = rc / 3u, c = rc % 3u;
-                const SetupVis &v = sh.batch[b];
+                const SetupVis &v = sh.u.big.batch[b];
                 const uint32_t yy = ty0 + r;
                 if (yy < v.ymin || yy > v.ymax) { continue; }
                 const uint32_t xs = max(tx0, (uint32_t)v.xmin), xe = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
@@ -768,7 +804,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
                 float w = walk_jump(wy, d, xs - v.xmin);                         // render.cpp:374
                 uint32_t x = xs, k = (xs - tx0) / SEG;
                 while (true) {
-                    sh.segstart[b][r][k][c] = w;
+                    sh.u.big.segstart[b][r][k][c] = w;
                     const uint32_t next = tx0 + (k + 1u) * SEG;
                     if (next > xe) { break; }
                     for (; x < next; x++) { w = add_rn(w, d); }
@@ -776,25 +812,29 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
                 }
             }
             __syncthreads();
-            // ---- stage B: every thread walks its 8 pixels through the batch, in order ---------
+            // stage B: every thread walks its 8 pixels through the batch
             for (uint32_t b = 0; b < nb; b++) {
-                const SetupVis &v = sh.batch[b];
+                const SetupVis &v = sh.u.big.batch[b];
                 if (y < v.ymin || y > v.ymax) { continue; }
                 const uint32_t xa = max(sx0, (uint32_t)v.xmin), xb = min(sx0 + SEG - 1u, (uint32_t)v.xmax);
                 if (xa > xb) { continue; }
                 const float d0 = v.dx[0], d1 = v.dx[1], d2 = v.dx[2];
-                float w0 = sh.segstart[b][row][seg][0], w1 = sh.segstart[b][row][seg][1], w2 = sh.segstart[b][row][seg][2];
+                float w0 = sh.u.big.segstart[b][row][seg][0], w1 = sh.u.big.segstart[b][row][seg][1],
+                      w2 = sh.u.big.segstart[b][row][seg][2];
                 const float rz0 = v.rvz[0], rz1 = v.rvz[1], rz2 = v.rvz[2];
-                const uint32_t slot = (uint32_t)sorted[base + b];
+                const uint32_t slot = sh.bigq[base + b], order = v.order;
 #pragma unroll
                 for (int j = 0; j < SEG; j++) {
                     const uint32_t x = sx0 + j;
                     if (x >= xa && x <= xb) {
                         if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                         // render.cpp:362
                             const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;      // render.cpp:363
-                            if (ooz > depth[j]) {                                    // render.cpp:364
-                                depth[j] = ooz; bw0[j] = w0; bw1[j] = w1; bw2[j] = w2; win[j] = slot;
+                            bool better = ooz > depth[j];                            // render.cpp:364
+                            if (ooz == depth[j] && ooz > 0.f) {
+                                // exact depth tie between two triangles: the reference keeps the earlier one
+                                better = order < f.head[(size_t)view * f.setup_cap + win[j]].z;
                             }
+                            if (better) { depth[j] = ooz; bw0[j] = w0; bw1[j] = w1; bw2[j] = w2; win[j] = slot; }
                         }
                         w0 = add_rn(w0, d0); w1 = add_rn(w1, d1); w2 = add_rn(w2, d2);   // render.cpp:374
                     }
@@ -802,16 +842,47 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             }
             __syncthreads();  // batch / segstart are rewritten by the next iteration
         }
+        if (tid == 0) { sh.n_big = 0; }
+        __syncthreads();
     }
 
-    // ---- hand the winners to a pixel-per-lane layout for coherent shading ------------------
-    __syncthreads();  // the sorted list (aliased with state) is dead from here on
+    // ---- phase 2: per-pixel winners into shared memory (pixel-per-lane layout for coherent shading) ----
+    const bool any_small = sh.any_small != 0;
+    if (any_small) {
 #pragma unroll
-    for (int j = 0; j < SEG; j++) {
-        sh.u.state[swizzled(row, seg, j)] =
-            make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+        for (int j = 0; j < SEG; j++) { sh.u.state[swizzled(row, seg, j)] = make_uint4(0u, 0u, 0u, NO_TRI); }
+        __syncthreads();
+        for (uint32_t cbase = 0; cbase < n; cbase += RASTER_THREADS) {   // small winners drop their weights
+            const uint32_t i = cbase + tid;
+            if (i < n) {
+                const uint32_t slot = list[i];
+                const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+                const uint32_t bwid = (head.x >> 16) - (head.x & 0xFFFFu), bhgt = (head.y >> 16) - (head.y & 0xFFFFu);
+                if (bwid < SMALL_MAX && bhgt < SMALL_MAX) { walk_small<2>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh); }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SEG; j++) {   // a big-triangle candidate wins where its key beats the small ones'
+            if (win[j] != NO_TRI) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(depth[j]) << 32) |
+                                               (unsigned long long)(~f.head[(size_t)view * f.setup_cap + win[j]].z);
+                if (key > sh.k.keys[row * TILE_W + seg * SEG + j]) {
+                    sh.u.state[swizzled(row, seg, j)] =
+                        make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+                }
+            }
+        }
+    } else {
+        __syncthreads();  // big-triangle staging (aliased with state) is dead from here on
+#pragma unroll
+        for (int j = 0; j < SEG; j++) {
+            sh.u.state[swizzled(row, seg, j)] =
+                make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+        }
     }
     __syncthreads();
+    // ---- phase 3: deferred shading, one pixel per lane -------------------------------------------
 #pragma unroll 1
     for (uint32_t it = 0; it < (TILE_W * TILE_H) / RASTER_THREADS; it++) {
         const uint32_t p = it * RASTER_THREADS + tid, pr = p / TILE_W, pc = p % TILE_W;
@@ -820,7 +891,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         if (st.w != NO_TRI) {
             rgb = shade_pixel(f, view, st.w, __uint_as_float(st.x), __uint_as_float(st.y), __uint_as_float(st.z));
         }
-        sh.colour[pr][pc] = rgb;
+        sh.k.colour[pr][pc] = rgb;
     }
 
     // ---- write-out -------------------------------------------------------------------------
@@ -833,7 +904,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         uint32_t *packed = reinterpret_cast<uint32_t *>(sh.u.state);   // [TILE_H][PW]
         for (uint32_t g = tid; g < TILE_H * (TILE_W / 4); g += RASTER_THREADS) {
             const uint32_t pr = g / (TILE_W / 4), q = g % (TILE_W / 4);
-            const uint4 p = *reinterpret_cast<const uint4 *>(&sh.colour[pr][q * 4]);
+            const uint4 p = *reinterpret_cast<const uint4 *>(&sh.k.colour[pr][q * 4]);
             uint32_t *o = packed + pr * PW + q * 3u;
             o[0] = p.x | (p.y << 24);
             o[1] = (p.y >> 8) | (p.z << 16);
@@ -875,7 +946,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             const uint32_t yy = ty0 + tid;
             if (yy >= f.y0 && yy < f.y1) {
                 uint32_t *dst = out + (size_t)(yy - f.y0) * f.W + tx0;
-                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.colour[tid][0]);
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.k.colour[tid][0]);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"(cols * 4u) : "memory");
             }
@@ -886,7 +957,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         __syncthreads();
         for (uint32_t p = tid; p < TILE_W * TILE_H; p += RASTER_THREADS) {
             const uint32_t pr = p / TILE_W, pc = p % TILE_W, yy = ty0 + pr;
-            if (pc < cols && yy >= f.y0 && yy < f.y1) { out[(size_t)(yy - f.y0) * f.W + tx0 + pc] = sh.colour[pr][pc]; }
+            if (pc < cols && yy >= f.y0 && yy < f.y1) { out[(size_t)(yy - f.y0) * f.W + tx0 + pc] = sh.k.colour[pr][pc]; }
         }
     }
 }

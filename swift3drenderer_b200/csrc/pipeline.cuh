@@ -34,7 +34,7 @@ constexpr int SEG = 8;                      // pixels per thread in the visibili
 constexpr int SEGS_PER_ROW = TILE_W / SEG;
 static_assert(SEGS_PER_ROW * TILE_H == RASTER_THREADS, "one thread per 8-pixel segment");
 constexpr int BATCH = 8;                    // triangles staged per visibility batch
-constexpr int SORT_CAP = 4096;              // bin entries sorted in shared memory (longer lists: in HBM)
+constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
 
@@ -95,7 +95,7 @@ struct Frame {
     uint32_t *sticky;   // [4] across chunks: overflow bits (OR), max setups, max entries, max big
     uint32_t *tile_count, *tile_offset, *tile_cursor;
     uint32_t tile_stride;
-    unsigned long long *entries;
+    uint32_t *entries;          // per-tile lists of survivor slots (unordered)
     uint32_t entry_cap;
     uint32_t *big_list;
     uint32_t big_cap;

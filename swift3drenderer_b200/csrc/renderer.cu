@@ -77,7 +77,7 @@ struct S3RRenderer {
     uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
     float factor_override = 0.f;   // drop-in path: the reference's stale-factor rule (render.cpp:276-279)
     DevBuf<uint32_t> counters, tile_count, tile_offset, tile_cursor, big_list;
-    DevBuf<unsigned long long> entries;
+    DevBuf<uint32_t> entries;
     DevBuf<float> cams;
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
     // submission ring: pinned camera staging + events, so the host can run RING chunks ahead
