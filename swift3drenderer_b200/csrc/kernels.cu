@@ -4,7 +4,7 @@
 //   vertex_stage       K1  model/view/projection over planar float4 position streams   (render.cpp:285-289)
 //   triangle_setup     K2  gather, near reject, near-plane clip (0/1/2 out), cull, setup,
 //                          warp-ballot + block-scan compaction                          (render.cpp:297-359, 212-262)
-//   bin_small/bin_big  K3  sort-middle binning: count -> tile_scan -> fill              (no reference counterpart)
+//   (setup) + bin_big  K3  sort-middle binning, single pass into fixed-capacity tile lists (no reference counterpart)
 //   tile_raster        K4  per-tile exact barycentric walk + depth test in registers, deferred
 //                          perspective-correct shading + rip-map fetch, colour tile in shared
 //                          memory, cp.async.bulk (TMA) write-out                        (render.cpp:360-382, 124-132)
@@ -219,16 +219,12 @@ __device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, u
     return r;
 }
 
-template <bool FILL>
-__device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot, uint32_t order) {
-    if (!FILL) {
-        atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
-    } else {
-        const uint32_t pos = atomicAdd(f.tile_cursor + view * f.tile_stride + tile, 1u);
-        if (pos < f.entry_cap) {
-            f.entries[(size_t)view * f.entry_cap + pos] = slot;
-        }
-    }
+// Single-pass binning: every tile owns a fixed-capacity list (tile_cap slots); one atomic reserves the
+// position.  Lists are unordered (the depth keys carry the order).  Overflowing tiles are detected by
+// frame_finalize; the host regrows tile_cap and renders the frame again.
+__device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot) {
+    const uint32_t pos = atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
+    if (pos < f.tile_cap) { f.entries[((size_t)view * f.tile_stride + tile) * f.tile_cap + pos] = slot; }
 }
 
 struct SetupShared {
@@ -271,8 +267,8 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
     f.head[(size_t)view * f.setup_cap + slot] = sv[0];   // bbox + order key + kind: all binning needs
 }
 
-// K3 count pass for one survivor: tile histogram for triangles over few tiles (with the conservative
-// outside test), everything larger goes to the cooperative big list.
+// K3 for one survivor, fused into setup: triangles over few tiles are binned right here (with the
+// conservative outside test), everything larger goes to the cooperative big list.
 __device__ __forceinline__ void count_tiles(const Frame &f, uint32_t view, uint32_t slot, const SetupVis &v) {
     const TileRange r = tile_range(f, v.xmin, v.xmax, v.ymin, v.ymax);
     if (r.empty) { return; }
@@ -287,7 +283,7 @@ __device__ __forceinline__ void count_tiles(const Frame &f, uint32_t view, uint3
         const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
         for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) {
             if (ntiles > 1u && tile_outside_triangle(v, tx * TILE_W, ylo_t, yhi_t)) { continue; }
-            atomicAdd(f.tile_count + view * f.tile_stride + ty * f.tiles_x + tx, 1u);
+            bin_one(f, view, ty * f.tiles_x + tx, slot);
         }
     }
 }
@@ -306,7 +302,7 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
     if (keep) {
         if (slot < f.setup_cap) {
             store_setup(f, view, slot, v, s);
-            if (!f.direct_bin) { count_tiles(f, view, slot, v); }   // K3 count pass, fused
+            if (!f.direct_bin) { count_tiles(f, view, slot, v); }   // K3 (binning), fused
         } else {
             atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 1u);
         }
@@ -464,43 +460,11 @@ __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__
 // K3 — sort-middle binning (count -> scan -> fill).  Entries are (order << 32 | slot) so that each
 // tile can restore the reference's processing order with one sort.
 // ------------------------------------------------------------------------------------------------
-template <bool FILL>
-__device__ __forceinline__ void bin_small_body(const Frame &f, uint32_t view, uint32_t first, uint32_t stride) {
-    const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
-    for (uint32_t slot = first; slot < n; slot += stride) {
-        const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
-        const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
-        const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
-        if (r.empty) { continue; }
-        const uint32_t ntiles = (r.tx1 - r.tx0 + 1u) * (r.ty1 - r.ty0 + 1u);
-        if (ntiles > BIG_TILES) {
-            if (!FILL) {
-                const uint32_t pos = atomicAdd(f.counters + view * C_COUNT + C_BIG, 1u);
-                if (pos < f.big_cap) { f.big_list[(size_t)view * f.big_cap + pos] = slot; }
-                else { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 4u); }
-            }
-            continue;
-        }
-        const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
-        for (uint32_t ty = r.ty0; ty <= r.ty1; ty++) {
-            const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
-            for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) {
-                if (ntiles > 1u && tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }
-                bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z);
-            }
-        }
-    }
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(256) bin_small(const __grid_constant__ Frame f) {
-    bin_small_body<FILL>(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-}
-
-template <bool FILL>
-__device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view, uint32_t first, uint32_t stride) {
+// Triangles over more than BIG_TILES tiles: one CTA per triangle, threads over its tiles.
+__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
     const uint32_t n = min(f.counters[view * C_COUNT + C_BIG], f.big_cap);
-    for (uint32_t b = first; b < n; b += stride) {
+    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
         const uint32_t slot = f.big_list[(size_t)view * f.big_cap + b];
         const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
@@ -510,66 +474,36 @@ __device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view, uint
         for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) {
             const uint32_t ty = r.ty0 + i / nx, tx = r.tx0 + i % nx;
             const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
-            if (tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }   // same decision in count and fill
-            bin_one<FILL>(f, view, ty * f.tiles_x + tx, slot, head.z);
+            if (tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }
+            bin_one(f, view, ty * f.tiles_x + tx, slot);
         }
     }
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
-    bin_big_body<FILL>(f, blockIdx.y, blockIdx.x, gridDim.x);
-}
-
-struct ScanShared { uint32_t warp_tot[32]; uint32_t carry; };
-
-// exclusive scan of the tile histogram by one CTA of any size (multiple of 32); also seeds the fill cursors
-__device__ __forceinline__ void scan_body(const Frame &f, uint32_t view, ScanShared &ss) {
-    uint32_t *warp_tot = ss.warp_tot;
-    uint32_t &carry = ss.carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const uint32_t *cnt = f.tile_count + view * f.tile_stride;
-    uint32_t *off = f.tile_offset + view * f.tile_stride, *cur = f.tile_cursor + view * f.tile_stride;
-    if (tid == 0) { carry = 0; }
+// After all binning: total and longest tile list, overflow bits, and the cross-submission record the host
+// reads back (one CTA per view).
+__global__ void __launch_bounds__(256) frame_finalize(const __grid_constant__ Frame f) {
+    __shared__ uint32_t s_sum, s_max;
+    const uint32_t view = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) { s_sum = 0; s_max = 0; }
     __syncthreads();
-    for (uint32_t base = 0; base < f.n_tiles; base += nthreads) {
-        const uint32_t i = base + tid;
-        const uint32_t c = i < f.n_tiles ? cnt[i] : 0u;
-        uint32_t incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) { incl += o; } }
-        if (lane == 31) { warp_tot[warp] = incl; }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = lane < nwarps ? warp_tot[lane] : 0u, wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) { wi += o; } }
-            warp_tot[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_tot[warp] + incl - c;
-        if (i < f.n_tiles) { off[i] = excl; cur[i] = excl; }
-        __syncthreads();
-        if (tid == nthreads - 1u) { carry = excl + c; }
-        __syncthreads();
+    uint32_t sum = 0, mx = 0;
+    for (uint32_t t = tid; t < f.n_tiles; t += 256u) {
+        const uint32_t c = f.tile_count[view * f.tile_stride + t];
+        sum += c; mx = max(mx, c);
     }
+    atomicAdd(&s_sum, sum);
+    atomicMax(&s_max, mx);
+    __syncthreads();
     if (tid == 0) {
-        off[f.n_tiles] = carry;
-        f.counters[view * C_COUNT + C_ENTRIES] = carry;
-        if (carry > f.entry_cap) { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 2u); }
-        // all overflow sources have been decided by now: fold them into the cross-chunk record
-        const uint32_t *c = f.counters + view * C_COUNT;
+        uint32_t *c = f.counters + view * C_COUNT;
+        c[C_ENTRIES] = s_sum;
+        if (s_max > f.tile_cap) { c[C_OVERFLOW] |= 2u; }
         if (c[C_OVERFLOW]) { atomicOr(f.sticky + 0, c[C_OVERFLOW]); }
         atomicMax(f.sticky + 1, c[C_SETUPS]);
-        atomicMax(f.sticky + 2, carry);
+        atomicMax(f.sticky + 2, s_max);
         atomicMax(f.sticky + 3, c[C_BIG]);
     }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(1024) tile_scan(const __grid_constant__ Frame f) {
-    __shared__ ScanShared ss;
-    scan_body(f, blockIdx.x, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -752,9 +686,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         n = sh.n_list;
         list = sh.slots;
     } else {
-        const uint32_t begin = f.tile_offset[view * f.tile_stride + tile];
-        n = f.tile_offset[view * f.tile_stride + tile + 1] - begin;
-        list = f.entries + (size_t)view * f.entry_cap + begin;
+        n = min(f.tile_count[view * f.tile_stride + tile], f.tile_cap);
+        list = f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap;
     }
 
     float depth[SEG], bw0[SEG], bw1[SEG], bw2[SEG];
@@ -986,11 +919,8 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
     triangle_classify<<<dim3(max(1u, ceil_div(f.T, 256)), f.n_views), 256, 0, s>>>(f); launches++;
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
-    const uint32_t bin_blocks = min(persistent, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
-    bin_big<false><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
-    tile_scan<<<f.n_views, 1024, 0, s>>>(f); launches++;
-    bin_small<true><<<dim3(bin_blocks, f.n_views), 256, 0, s>>>(f); launches++;
-    bin_big<true><<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
+    bin_big<<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
+    frame_finalize<<<f.n_views, 256, 0, s>>>(f); launches++;
     return launches;
 }
 

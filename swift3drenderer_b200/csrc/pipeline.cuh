@@ -13,7 +13,7 @@
 //   per view (frame scratch, strided by view)
 //     rv                  float4[Vpad]       raster-space vertices (x, y, z, -) from the vertex stage
 //     vis / shade         64 B + 128 B per surviving triangle (compacted)
-//     tile_count/offset/cursor, entries (u64 = order<<32 | slot), big_list, counters
+//     tile_count, entries (u32 survivor slots, tile_cap per tile, unordered), big_list, counters
 //
 // Screen tiles are TILE_W x TILE_H pixels, aligned to the full frame's origin (so a band-partitioned
 // render bins and rasterises exactly the tiles the whole-frame render would).
@@ -93,10 +93,10 @@ struct Frame {
     uint32_t setup_cap;
     uint32_t *counters;
     uint32_t *sticky;   // [4] across chunks: overflow bits (OR), max setups, max entries, max big
-    uint32_t *tile_count, *tile_offset, *tile_cursor;
+    uint32_t *tile_count;       // [views][tile_stride] entries binned per tile this frame
     uint32_t tile_stride;
     uint32_t *entries;          // per-tile lists of survivor slots (unordered)
-    uint32_t entry_cap;
+    uint32_t tile_cap;          // capacity of every tile's list
     uint32_t *big_list;
     uint32_t big_cap;
     // output

@@ -66,7 +66,7 @@ struct S3RRenderer {
     DevBuf<uint32_t> texels;
     // per-view scratch
     uint32_t views_cap = 0, tile_stride = 0;
-    uint32_t setup_cap = 0, entry_cap = 0, big_cap = 0;
+    uint32_t setup_cap = 0, tile_cap = 0, big_cap = 0;
     uint32_t views_per_chunk = 256;
     DevBuf<float4> rv;
     DevBuf<SetupVis> vis;
@@ -76,7 +76,7 @@ struct S3RRenderer {
     DevBuf<uint32_t> sticky;
     uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
     float factor_override = 0.f;   // drop-in path: the reference's stale-factor rule (render.cpp:276-279)
-    DevBuf<uint32_t> counters, tile_count, tile_offset, tile_cursor, big_list;
+    DevBuf<uint32_t> counters, tile_count, big_list;
     DevBuf<uint32_t> entries;
     DevBuf<float> cams;
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
@@ -155,7 +155,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->worklist.release();
-    r->counters.release(); r->tile_count.release(); r->tile_offset.release(); r->tile_cursor.release();
+    r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
     delete r->copier;
@@ -231,7 +231,7 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
     r->V = V; r->Vpad = px.size(); r->I = I; r->T = T; r->A = A; r->n_texels = n_texels;
     r->has_scene = true;
     r->views_cap = 0;  // scratch is re-sized on the next render
-    r->worklist.release(); r->setup_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->entries.release(); r->big_list.release();
+    r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->entries.release(); r->big_list.release();
     return S3R_OK;
 }
 
@@ -350,17 +350,25 @@ extern "C" float s3r_factor(uint32_t height) { return kNear * (float)height / (2
 // --------------------------------------------------------------------------------------------------
 // frame scratch
 // --------------------------------------------------------------------------------------------------
+// Small scenes (2T <= SORT_CAP survivors at most) skip the bin arrays: one fused geometry CTA per view and
+// in-kernel per-tile collection in the rasteriser.
+static bool uses_direct_bin(const S3RRenderer *r) {
+    return r->opt_fused_small && 2ull * r->T <= (uint64_t)SORT_CAP && r->setup_cap >= 2ull * r->T;
+}
+
 static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     const uint32_t T = (uint32_t)r->T;
     if (r->setup_cap == 0) {
         // survivors are usually a small share of 2T; start at T/4 (min 4096) and regrow on demand
         r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * T + 16, std::max<uint64_t>(4096, T / 4));
-        r->entry_cap = std::max<uint32_t>(16384, r->setup_cap * 4u);
         r->big_cap = std::max<uint32_t>(1024, r->setup_cap / 16u);
+        r->tile_cap = 0;
     }
-    {   // a small scene can put every triangle into every tile: make that case fit up front
-        const uint64_t worst = std::min<uint64_t>(2ull * T + 16, 256) * n_tiles;
-        if (worst > r->entry_cap) { r->entry_cap = (uint32_t)std::min<uint64_t>(worst, 0x7FFFFFFFull); }
+    if (r->tile_cap == 0) {
+        // per-tile list capacity: 4x the average load, a power of two in [256, setup_cap]; regrown on overflow
+        uint64_t want = 4ull * r->setup_cap / std::max<uint32_t>(n_tiles, 1u), cap = 256;
+        while (cap < want) { cap <<= 1; }
+        r->tile_cap = (uint32_t)std::min<uint64_t>(cap, std::max<uint32_t>(r->setup_cap, 256u));
     }
     const uint32_t tile_stride = ((n_tiles + 1 + 63) / 64) * 64;
     if (views > r->views_cap || tile_stride > r->tile_stride) {
@@ -380,9 +388,8 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
         memset(r->sticky_host, 0, 16);
     }
     CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
-    CUDA_TRY(r->tile_offset.ensure(vc * r->tile_stride));
-    CUDA_TRY(r->tile_cursor.ensure(vc * r->tile_stride));
-    CUDA_TRY(r->entries.ensure(vc * r->entry_cap));
+    // bin lists exist only for scenes that do not take the in-kernel collection path
+    if (!uses_direct_bin(r)) { CUDA_TRY(r->entries.ensure(vc * (size_t)r->tile_stride * r->tile_cap)); }
     CUDA_TRY(r->big_list.ensure(vc * r->big_cap));
     CUDA_TRY(r->cams.ensure(vc * 12));
     if (r->cams_pinned_views < vc) {
@@ -441,9 +448,9 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.band_lo = (float)y0; f.band_hi = (float)y1;
     f.counters = r->counters.p;
     f.sticky = r->sticky.p;
-    f.tile_count = r->tile_count.p; f.tile_offset = r->tile_offset.p; f.tile_cursor = r->tile_cursor.p;
+    f.tile_count = r->tile_count.p;
     f.tile_stride = r->tile_stride;
-    f.entries = r->entries.p; f.entry_cap = r->entry_cap;
+    f.entries = r->entries.p; f.tile_cap = r->tile_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out; f.out_view_stride = (unsigned long long)W * (y1 - y0);
     f.out_packed24 = packed24 ? 1 : 0;
@@ -451,7 +458,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
     // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
-    f.direct_bin = (r->opt_fused_small && 2u * f.T <= (uint32_t)SORT_CAP && f.setup_cap >= 2u * f.T) ? 1 : 0;
+    f.direct_bin = uses_direct_bin(r) ? 1 : 0;
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
@@ -510,12 +517,11 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
     memset(r->sticky_host, 0, sizeof(sticky));
     if (overflow & 1u) {
         r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * r->T + 16, (uint64_t)need_setups + need_setups / 2 + 1024);
-        r->entry_cap = std::max(r->entry_cap, r->setup_cap * 4u);
         r->big_cap = std::max(r->big_cap, r->setup_cap / 16u);
         // vis/shade are view-strided by setup_cap: force reallocation
         r->vis.release(); r->shade.release(); r->head.release(); r->entries.release(); r->big_list.release();
     }
-    if (overflow & 2u) { r->entry_cap = std::max(r->entry_cap, need_entries + need_entries / 2 + 1024); r->entries.release(); }
+    if (overflow & 2u) { r->tile_cap = std::max(r->tile_cap, need_entries + need_entries / 2 + 64); r->entries.release(); }
     if (overflow & 4u) { r->big_cap = std::max(r->big_cap, need_big + need_big / 2 + 64); r->big_list.release(); }
     return 1;
 }
@@ -793,7 +799,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "setup_capacity")) {  // test hook: force the regrow path
         if (value < 1) { return fail(S3R_E_ARG, "setup_capacity < 1"); }
         cudaStreamSynchronize(r->stream);
-        r->setup_cap = (uint32_t)value; r->entry_cap = std::max<uint32_t>(64, (uint32_t)value); r->big_cap = 4;
+        r->setup_cap = (uint32_t)value; r->tile_cap = 4; r->big_cap = 4;
         r->vis.release(); r->shade.release(); r->head.release(); r->entries.release(); r->big_list.release();
         return S3R_OK;
     }

@@ -46,6 +46,22 @@ def assemble_bands(band: torch.Tensor, height: int, rank: int, world: int, group
     return torch.cat([recv[k, : b - a] for k, (a, b) in enumerate(edges)], 0)
 
 
+def equal_bands(height: int, world: int) -> bool:
+    return height % world == 0
+
+
+def gather_bands_inplace(frame: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """Fast path when ``height % world == 0``: every rank has rendered its band straight into rows
+    ``band_edges(H, world)[rank]`` of its own full-size ``frame``; one in-place all-gather (NCCL: send buffer =
+    receive buffer + rank * count, no staging copy) completes the frame on every rank."""
+    height = frame.shape[0]
+    assert height % world == 0 and frame.is_contiguous()
+    if world > 1:
+        y0, y1 = band_edges(height, world)[rank]
+        dist.all_gather_into_tensor(frame.view(-1), frame[y0:y1].view(-1), group=group)
+    return frame
+
+
 def render_banded(render_band: Callable[[int, int], torch.Tensor], height: int, rank: int, world: int,
                   group=None) -> torch.Tensor:
     """`render_band(y0, y1)` must return this rank's rows as an ``(y1 - y0, W)`` int32 tensor (on the GPU it

@@ -39,6 +39,11 @@ def _worker(rank, world, port, height, width, out_dir):
 
     frame = multigpu.render_banded(render_band, height, rank, world)
     ok = np.array_equal(frame.numpy().view(np.uint32), whole)
+    if multigpu.equal_bands(height, world):  # in-place fast path: each rank fills only its own rows
+        y0, y1 = multigpu.band_edges(height, world)[rank]
+        mine = torch.zeros((height, width), dtype=torch.int32)
+        mine[y0:y1] = render_band(y0, y1)
+        ok = ok and np.array_equal(multigpu.gather_bands_inplace(mine, rank, world).numpy().view(np.uint32), whole)
     shard = list(multigpu.frame_shard(600, rank, world))
     gathered = [None] * world
     dist.all_gather_object(gathered, shard)

@@ -1,0 +1,27 @@
+"""tools/c3_band_probe.py — development aid: renders one 1/8 screen band of the C3 scene on a single GPU
+(what each rank does in the 8-GPU configuration) so that ncu can list its kernels."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+from swift3drenderer_b200 import renderer as R, scene as S
+
+n_solids = int(os.environ.get("C3_SOLIDS", "1000000"))
+path = f"/dev/shm/s3r_c3_{n_solids}.data.bin"
+if not os.path.exists(path):
+    S.write_data_bin(path, S.c3_scene(n_solids))
+r = R.Renderer(0)
+r.load_scene_file(path)
+inp = np.zeros(4, S.INPUT_DTYPE)
+mats = R.camera_path(inp)
+W, H = 3840, 2160
+out = torch.zeros((270, W), dtype=torch.int32, device="cuda:0")
+for rep in range(3):
+    for f in range(4):
+        r.render_device(mats[f], W, H, out.data_ptr(), y0=270 * 3, y1=270 * 4)
+    while r.finish():
+        pass
+r.set_option("timing", 1); r.timing()
+for f in range(4):
+    r.render_device(mats[f], W, H, out.data_ptr(), y0=270 * 3, y1=270 * 4)
+r.finish()
+print(r.timing(), r.stats())

@@ -109,13 +109,22 @@ def main():
             frames_done = n
         else:  # screen bands + all-gather of the assembled frame on every rank
             y0, y1 = multigpu.band_edges(H, world)[rank]
-            band = torch.empty((y1 - y0, W), dtype=torch.int32, device=dev)
             full = [None]
+            if multigpu.equal_bands(H, world):  # render into the frame's own rows, gather in place
+                frames = torch.zeros((4, H, W), dtype=torch.int32, device=dev)
 
-            def step():
-                for f in range(n):
-                    r.render_device(mats[f], W, H, band.data_ptr(), y0=y0, y1=y1, stream=stream.cuda_stream)
-                    full[0] = multigpu.assemble_bands(band, H, rank, world)
+                def step():
+                    for f in range(n):
+                        fr = frames[f % 4]
+                        r.render_device(mats[f], W, H, fr[y0:y1].data_ptr(), y0=y0, y1=y1, stream=stream.cuda_stream)
+                        full[0] = multigpu.gather_bands_inplace(fr, rank, world)
+            else:
+                band = torch.empty((y1 - y0, W), dtype=torch.int32, device=dev)
+
+                def step():
+                    for f in range(n):
+                        r.render_device(mats[f], W, H, band.data_ptr(), y0=y0, y1=y1, stream=stream.cuda_stream)
+                        full[0] = multigpu.assemble_bands(band, H, rank, world)
             frames_done = n
 
         for _ in range(2):  # warm-up incl. capacity regrowth
