@@ -208,14 +208,31 @@ __device__ __forceinline__ bool tile_outside_triangle(const SetupVis &v, uint32_
     return false;
 }
 
-struct TileRange { uint32_t tx0, tx1, ty0, ty1; bool empty; };
+// Tile-row ownership.  Absolute tile row `a` (counted from the top of the full frame) belongs to this
+// submission iff it meets the band [y0, y1) and a % row_stride == row_phase.  row_stride == 1 is the
+// contiguous band; row_stride == n GPUs interleaves the tile rows for load balance.  The local row index
+// (grid row, tile arrays, compacted output) is a - tile_row0 resp. a / row_stride.
+__device__ __forceinline__ bool owns_row(const Frame &f, uint32_t a) { return f.row_stride == 1u || a % f.row_stride == f.row_phase; }
+__device__ __forceinline__ uint32_t local_row(const Frame &f, uint32_t a) { return f.row_stride == 1u ? a - f.tile_row0 : a / f.row_stride; }
+__device__ __forceinline__ uint32_t abs_row(const Frame &f, uint32_t l) { return f.row_stride == 1u ? l + f.tile_row0 : l * f.row_stride + f.row_phase; }
+// output row of pixel row yy (inside absolute tile row a)
+__device__ __forceinline__ size_t out_row(const Frame &f, uint32_t yy, uint32_t a) {
+    return f.row_stride == 1u ? (size_t)(yy - f.y0) : (size_t)(a / f.row_stride) * TILE_H + (yy - a * TILE_H);
+}
+__device__ __forceinline__ uint32_t owned_rows_in(const Frame &f, uint32_t a0, uint32_t a1) {   // #owned rows in [a0, a1]
+    if (f.row_stride == 1u) { return a1 - a0 + 1u; }
+    const uint32_t first = a0 + (f.row_phase + f.row_stride - a0 % f.row_stride) % f.row_stride;
+    return first > a1 ? 0u : (a1 - first) / f.row_stride + 1u;
+}
+
+struct TileRange { uint32_t tx0, tx1, a0, a1; bool empty; };   // tile columns and ABSOLUTE tile rows, clamped to the band
 
 __device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
     TileRange r;
     const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
     r.empty = ylo > yhi;
     r.tx0 = xmin / TILE_W; r.tx1 = xmax / TILE_W;
-    r.ty0 = ylo / TILE_H - f.tile_row0; r.ty1 = yhi / TILE_H - f.tile_row0;
+    r.a0 = ylo / TILE_H; r.a1 = yhi / TILE_H;
     return r;
 }
 
@@ -272,18 +289,20 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
 __device__ __forceinline__ void count_tiles(const Frame &f, uint32_t view, uint32_t slot, const SetupVis &v) {
     const TileRange r = tile_range(f, v.xmin, v.xmax, v.ymin, v.ymax);
     if (r.empty) { return; }
-    const uint32_t ntiles = (r.tx1 - r.tx0 + 1u) * (r.ty1 - r.ty0 + 1u);
+    const uint32_t ntiles = (r.tx1 - r.tx0 + 1u) * owned_rows_in(f, r.a0, r.a1);
+    if (ntiles == 0u) { return; }
     if (ntiles > BIG_TILES) {
         const uint32_t pos = atomicAdd(f.counters + view * C_COUNT + C_BIG, 1u);
         if (pos < f.big_cap) { f.big_list[(size_t)view * f.big_cap + pos] = slot; }
         else { atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 4u); }
         return;
     }
-    for (uint32_t ty = r.ty0; ty <= r.ty1; ty++) {
-        const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
+    for (uint32_t a = r.a0; a <= r.a1; a++) {
+        if (!owns_row(f, a)) { continue; }
+        const uint32_t ya = a * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
         for (uint32_t tx = r.tx0; tx <= r.tx1; tx++) {
             if (ntiles > 1u && tile_outside_triangle(v, tx * TILE_W, ylo_t, yhi_t)) { continue; }
-            bin_one(f, view, ty * f.tiles_x + tx, slot);
+            bin_one(f, view, local_row(f, a) * f.tiles_x + tx, slot);
         }
     }
 }
@@ -379,7 +398,11 @@ __device__ __forceinline__ void classify_body(const Frame &f, uint32_t view, uin
             const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
             // screen-band partition: a triangle whose rows cannot meet [y0, y1) contributes nothing to this band
             // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
-            const bool off_band = max_y < f.band_lo || min_y >= f.band_hi;
+            bool off_band = max_y < f.band_lo || min_y >= f.band_hi;
+            if (!off_band && !off && f.row_stride != 1u) {   // interleaved tile rows: does it touch a row this submission owns?
+                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                off_band = ymin > ymax || owned_rows_in(f, ymin / TILE_H, ymax / TILE_H) == 0u;
+            }
             if (off || off_band || edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) { culled = true; } else { cls = 1; }
         }
     }
@@ -469,13 +492,14 @@ __global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) 
         const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         const TileRange r = tile_range(f, xmin, xmax, ymin, ymax);
-        const uint32_t nx = r.tx1 - r.tx0 + 1u, ntiles = nx * (r.ty1 - r.ty0 + 1u);
+        const uint32_t nx = r.tx1 - r.tx0 + 1u, ntiles = nx * (r.a1 - r.a0 + 1u);
         const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
         for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) {
-            const uint32_t ty = r.ty0 + i / nx, tx = r.tx0 + i % nx;
-            const uint32_t ya = (ty + f.tile_row0) * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
+            const uint32_t a = r.a0 + i / nx, tx = r.tx0 + i % nx;
+            if (!owns_row(f, a)) { continue; }
+            const uint32_t ya = a * TILE_H, ylo_t = max(ya, f.y0), yhi_t = min(ya + TILE_H, f.y1);
             if (tile_outside_triangle(*vp, tx * TILE_W, ylo_t, yhi_t)) { continue; }
-            bin_one(f, view, ty * f.tiles_x + tx, slot);
+            bin_one(f, view, local_row(f, a) * f.tiles_x + tx, slot);
         }
     }
 }
@@ -652,8 +676,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y + f.raster_row0, tid = threadIdx.x;
-    const uint32_t tile = tile_y * f.tiles_x + tile_x;
-    const uint32_t tx0 = tile_x * TILE_W, ty0 = (tile_y + f.tile_row0) * TILE_H;
+    const uint32_t tile = tile_y * f.tiles_x + tile_x;               // tile_y: local row index
+    const uint32_t tile_a = abs_row(f, tile_y);                      // absolute tile row
+    const uint32_t tx0 = tile_x * TILE_W, ty0 = tile_a * TILE_H;
     const uint32_t row = tid / SEGS_PER_ROW, seg = tid % SEGS_PER_ROW;
     const uint32_t y = ty0 + row, sx0 = tx0 + seg * SEG;
     const uint32_t ylo_t = max(ty0, f.y0), yhi_t = min(ty0 + TILE_H, f.y1);   // rows [ylo_t, yhi_t) of this tile are in the band
@@ -850,7 +875,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             if (tid < TILE_H) {
                 const uint32_t yy = ty0 + tid;
                 if (yy >= f.y0 && yy < f.y1) {
-                    uint8_t *dst = out8 + ((size_t)(yy - f.y0) * f.W + tx0) * 3u;
+                    uint8_t *dst = out8 + (out_row(f, yy, tile_a) * f.W + tx0) * 3u;
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + tid * PW);
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(dst), "r"(src), "r"(cols * 3u) : "memory");
@@ -864,7 +889,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             for (uint32_t i = tid; i < TILE_H * TILE_W * 3u; i += RASTER_THREADS) {
                 const uint32_t pr = i / (TILE_W * 3u), off = i % (TILE_W * 3u), yy = ty0 + pr;
                 if (off < cols * 3u && yy >= f.y0 && yy < f.y1) {
-                    out8[((size_t)(yy - f.y0) * f.W + tx0) * 3u + off] = pb[pr * (PW * 4u) + off];
+                    out8[(out_row(f, yy, tile_a) * f.W + tx0) * 3u + off] = pb[pr * (PW * 4u) + off];
                 }
             }
         }
@@ -878,7 +903,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         if (tid < TILE_H) {
             const uint32_t yy = ty0 + tid;
             if (yy >= f.y0 && yy < f.y1) {
-                uint32_t *dst = out + (size_t)(yy - f.y0) * f.W + tx0;
+                uint32_t *dst = out + out_row(f, yy, tile_a) * f.W + tx0;
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.k.colour[tid][0]);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"(cols * 4u) : "memory");
@@ -890,7 +915,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         __syncthreads();
         for (uint32_t p = tid; p < TILE_W * TILE_H; p += RASTER_THREADS) {
             const uint32_t pr = p / TILE_W, pc = p % TILE_W, yy = ty0 + pr;
-            if (pc < cols && yy >= f.y0 && yy < f.y1) { out[(size_t)(yy - f.y0) * f.W + tx0 + pc] = sh.k.colour[pr][pc]; }
+            if (pc < cols && yy >= f.y0 && yy < f.y1) { out[out_row(f, yy, tile_a) * f.W + tx0 + pc] = sh.k.colour[pr][pc]; }
         }
     }
 }

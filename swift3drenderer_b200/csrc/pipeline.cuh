@@ -82,7 +82,8 @@ struct Frame {
     uint32_t W, H, y0, y1;
     float fw, fh, half_w, half_h, factor;
     float band_lo, band_hi;   // (float)y0, (float)y1: early band reject in the classify pass
-    uint32_t tiles_x, tile_row0, tiles_y, n_tiles;
+    uint32_t tiles_x, tile_row0, tiles_y, n_tiles;   // tiles_y: tile rows this submission owns
+    uint32_t row_stride, row_phase;                  // tile-row ownership: a % row_stride == row_phase (1, 0 = contiguous band)
     uint32_t raster_row0, raster_rows;   // tile rows [raster_row0, raster_row0 + raster_rows) of the band go in one raster launch
     // per-view scratch
     float4 *rv;

@@ -406,12 +406,20 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
 // band_rows[b] receives the first pixel row (relative to y0) after band b.
 static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H, uint32_t y0,
                         uint32_t y1, uint32_t *dev_out, cudaStream_t s, int raster_bands = 1,
-                        uint32_t *band_rows = nullptr, bool packed24 = false) {
+                        uint32_t *band_rows = nullptr, bool packed24 = false, uint32_t row_stride = 1,
+                        uint32_t row_phase = 0) {
     Frame f;
     memset(&f, 0, sizeof(f));
     f.tiles_x = (W + TILE_W - 1) / TILE_W;
-    f.tile_row0 = y0 / TILE_H;
-    f.tiles_y = (y1 - 1) / TILE_H - f.tile_row0 + 1;
+    f.row_stride = row_stride; f.row_phase = row_phase;
+    if (row_stride == 1) {
+        f.tile_row0 = y0 / TILE_H;
+        f.tiles_y = (y1 - 1) / TILE_H - f.tile_row0 + 1;
+    } else {   // interleaved tile rows of the whole frame
+        const uint32_t rows = (H + TILE_H - 1) / TILE_H;
+        f.tile_row0 = 0;
+        f.tiles_y = rows > row_phase ? (rows - row_phase + row_stride - 1) / row_stride : 0;
+    }
     f.n_tiles = f.tiles_x * f.tiles_y;
     int rc = ensure_scratch(r, n_views, f.n_tiles);
     if (rc) { return rc; }
@@ -452,7 +460,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.tile_stride = r->tile_stride;
     f.entries = r->entries.p; f.tile_cap = r->tile_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
-    f.out = dev_out; f.out_view_stride = (unsigned long long)W * (y1 - y0);
+    f.out = dev_out;
+    f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
     f.out_packed24 = packed24 ? 1 : 0;
     f.use_tma = r->opt_tma && (W % (packed24 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
@@ -496,6 +505,32 @@ extern "C" int s3r_render_device(S3RRenderer *r, const float *cams, uint32_t n_v
     for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
         const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
         int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, dev_out + view_px * v0, s);
+        if (rc) { return rc; }
+        r->last_views = nv;
+    }
+    r->last_W = W; r->last_H = H;
+    return S3R_OK;
+}
+
+extern "C" uint32_t s3r_tile_height(void) { return (uint32_t)TILE_H; }
+
+extern "C" int s3r_render_device_rows(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
+                                      uint32_t row_stride, uint32_t row_phase, uint32_t *dev_out, void *stream) {
+    if (!r || !cams || !dev_out) { return fail(S3R_E_ARG, "null argument"); }
+    if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
+    if (W == 0 || H == 0 || W > 65535 || H > 65535 || n_views == 0 || row_stride == 0 || row_phase >= row_stride) {
+        return fail(S3R_E_ARG, "bad frame geometry");
+    }
+    if ((H + TILE_H - 1) / TILE_H <= row_phase) { return S3R_OK; }   // this phase owns no tile row
+    CUDA_TRY(cudaSetDevice(r->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
+    r->last_stream = s;
+    const uint32_t rows = (H + TILE_H - 1) / TILE_H, owned = (rows - row_phase + row_stride - 1) / row_stride;
+    const size_t view_px = (size_t)W * owned * TILE_H;
+    for (uint32_t v0 = 0; v0 < n_views; v0 += r->views_per_chunk) {
+        const uint32_t nv = std::min(r->views_per_chunk, n_views - v0);
+        int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, 0, H, dev_out + view_px * v0, s, 1, nullptr, false,
+                              row_stride, row_phase);
         if (rc) { return rc; }
         r->last_views = nv;
     }

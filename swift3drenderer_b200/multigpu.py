@@ -62,6 +62,33 @@ def gather_bands_inplace(frame: torch.Tensor, rank: int, world: int, group=None)
     return frame
 
 
+class InterleavedAssembler:
+    """Tile rows dealt round-robin to the ranks (``a % world == rank``): every rank gets an even share of the
+    screen whatever the scene looks like.  Each rank renders its rows compacted (``Renderer.render_device_rows``);
+    ``gather`` all-gathers the padded per-rank buffers and de-interleaves them into the frame with one
+    index_select."""
+
+    def __init__(self, height: int, width: int, rank: int, world: int, device, tile_h: int):
+        from .renderer import rows_layout
+        self.rank, self.world = rank, world
+        tile_rows = (height + tile_h - 1) // tile_h
+        self.buf_rows = ((tile_rows + world - 1) // world) * tile_h          # tallest compacted buffer, same on all ranks
+        self.mine = torch.zeros((self.buf_rows, width), dtype=torch.int32, device=device)
+        self.staging = torch.empty((world, self.buf_rows, width), dtype=torch.int32, device=device)
+        src = torch.empty(height, dtype=torch.int64)
+        for k in range(world):
+            _, frame_rows, buf_rows = rows_layout(height, world, k, tile_h)
+            src[torch.from_numpy(frame_rows)] = torch.from_numpy(buf_rows) + k * self.buf_rows
+        self.src = src.to(device)
+
+    def gather(self, group=None) -> torch.Tensor:
+        if self.world == 1:
+            self.staging[0] = self.mine
+        else:
+            dist.all_gather_into_tensor(self.staging.view(-1), self.mine.view(-1), group=group)
+        return self.staging.view(self.world * self.buf_rows, -1).index_select(0, self.src)
+
+
 def render_banded(render_band: Callable[[int, int], torch.Tensor], height: int, rank: int, world: int,
                   group=None) -> torch.Tensor:
     """`render_band(y0, y1)` must return this rank's rows as an ``(y1 - y0, W)`` int32 tensor (on the GPU it

@@ -70,7 +70,7 @@ EXPORTS = [
     "s3r_load_scene_arrays", "s3r_scene_counts", "s3r_camera_reset", "s3r_camera_update", "s3r_factor",
     "s3r_render_device", "s3r_finish", "s3r_render_host", "s3r_get_stats", "s3r_dump_raster_vertices",
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
-    "s3r_dropin_reset", "s3r_debug_walk",
+    "s3r_dropin_reset", "s3r_debug_walk", "s3r_render_device_rows", "s3r_tile_height",
 ]
 
 
@@ -134,6 +134,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(u64), ctypes.c_int]
     lib.s3r_debug_walk.argtypes = [vp, vp, vp, vp, vp, u32]
+    lib.s3r_render_device_rows.argtypes = [vp, vp, u32, u32, u32, u32, u32, vp, vp]
+    lib.s3r_tile_height.restype = u32
     if path is None:
         _lib = lib
     return lib
@@ -168,6 +170,25 @@ def camera_path(inputs) -> np.ndarray:
     """(n, 12) camera matrices: pose k is the state after k + 1 Input records."""
     cam = Camera()
     return np.stack([cam.update(r) for r in inputs]) if len(inputs) else np.zeros((0, 12), np.float32)
+
+
+def tile_height() -> int:
+    return int(load_library().s3r_tile_height())
+
+
+def rows_layout(height: int, row_stride: int, row_phase: int, th: Optional[int] = None):
+    """(compacted buffer rows, frame row -> buffer row map for the rows this phase owns) of
+    ``s3r_render_device_rows``."""
+    th = th or tile_height()
+    tile_rows = (height + th - 1) // th
+    owned = [a for a in range(tile_rows) if a % row_stride == row_phase]
+    frame_rows, buf_rows = [], []
+    for l, a in enumerate(owned):
+        for i in range(th):
+            if a * th + i < height:
+                frame_rows.append(a * th + i)
+                buf_rows.append(l * th + i)
+    return len(owned) * th, np.asarray(frame_rows, np.int64), np.asarray(buf_rows, np.int64)
 
 
 class Renderer:
@@ -232,6 +253,13 @@ class Renderer:
         y1 = height if y1 is None else y1
         self._check(self._lib.s3r_render_device(self._h, cams.ctypes.data, cams.shape[0], width, height, y0, y1,
                                                  ctypes.c_void_p(dev_ptr), ctypes.c_void_p(stream)))
+
+    def render_device_rows(self, cameras, width: int, height: int, row_stride: int, row_phase: int, dev_ptr: int,
+                           stream: int = 0) -> None:
+        """Interleaved tile rows (``a % row_stride == row_phase``), compacted output; see ``rows_layout``."""
+        cams = np.ascontiguousarray(cameras, "<f4").reshape(-1, 12)
+        self._check(self._lib.s3r_render_device_rows(self._h, cams.ctypes.data, cams.shape[0], width, height, row_stride,
+                                                      row_phase, ctypes.c_void_p(dev_ptr), ctypes.c_void_p(stream)))
 
     def finish(self) -> bool:
         """Waits for enqueued work; True means a capacity overflowed and the last call must be repeated."""

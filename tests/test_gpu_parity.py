@@ -325,3 +325,25 @@ def test_host_transport_variants_agree(renderer_lib):
             assert (got >> 24 == 0).all()
         r.set_option("pin_host", 0)
     r.close()
+
+
+def test_interleaved_tile_rows_reassemble_to_the_whole_frame(gpu_renderer, renderer_lib):
+    """Multi-GPU load-balanced partition: tile rows dealt round-robin; the union must be the whole frame."""
+    import torch
+    th = renderer_lib.tile_height()
+    for sc, script, fidx in ((S.shipped_scene(1), "flythrough", 330), (S.icosahedron_field(3000, seed=5, extent=50), "spin", 9)):
+        gpu_renderer.load_scene(sc)
+        m = renderer_lib.camera_path(S.input_script(script, 600 if script == "flythrough" else 10))[fidx]
+        for (W, H) in ((1920, 1080), (640, 361)):
+            whole = gpu_renderer.render(m, W, H)[0]
+            for world in (2, 3, 8):
+                frame = np.zeros((H, W), np.uint32)
+                for phase in range(world):
+                    rows, frame_rows, buf_rows = renderer_lib.rows_layout(H, world, phase, th)
+                    if rows == 0:
+                        continue
+                    buf = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
+                    gpu_renderer.render_device_rows(m, W, H, world, phase, buf.data_ptr())
+                    assert gpu_renderer.finish() is False
+                    frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
+                assert_same(frame, whole, f"{W}x{H} interleaved over {world}")

@@ -44,6 +44,13 @@ def _worker(rank, world, port, height, width, out_dir):
         mine = torch.zeros((height, width), dtype=torch.int32)
         mine[y0:y1] = render_band(y0, y1)
         ok = ok and np.array_equal(multigpu.gather_bands_inplace(mine, rank, world).numpy().view(np.uint32), whole)
+    # interleaved tile rows: every rank fills its compacted buffer, one all-gather + de-interleave
+    th = 32
+    asm = multigpu.InterleavedAssembler(height, width, rank, world, torch.device("cpu"), th)
+    from swift3drenderer_b200.renderer import rows_layout
+    _, frame_rows, buf_rows = rows_layout(height, world, rank, th)
+    asm.mine[torch.from_numpy(buf_rows)] = torch.from_numpy(whole[frame_rows].astype(np.int32))
+    ok = ok and np.array_equal(asm.gather().numpy().view(np.uint32), whole)
     shard = list(multigpu.frame_shard(600, rank, world))
     gathered = [None] * world
     dist.all_gather_object(gathered, shard)

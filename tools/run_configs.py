@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--c3-solids", type=int, default=1_000_000)
     ap.add_argument("--c4-solids", type=int, default=50_000)
     ap.add_argument("--c5-views", type=int, default=4096)
+    ap.add_argument("--partition", default="rows", choices=["rows", "bands"],
+                    help="multi-GPU split of a frame: interleaved tile rows (load balanced) or contiguous bands")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -93,7 +95,7 @@ def main():
         mats = R.camera_path(inputs)
         n = len(mats)
         b_alg = 12 * counts["V"] + 28 * counts["A"] + 8 * counts["I"] + 4 * W * H
-        line = {"config": name, "gpus": world, "mode": mode, "W": W, "H": H, "frames": n, **counts, "note": note}
+        line = {"config": name, "gpus": world, "mode": mode if mode == "frames" else args.partition, "W": W, "H": H, "frames": n, **counts, "note": note}
 
         if mode == "frames":  # frame-parallel: this rank renders its share of the poses, several per launch
             mine = list(multigpu.frame_shard(n, rank, world))
@@ -110,7 +112,14 @@ def main():
         else:  # screen bands + all-gather of the assembled frame on every rank
             y0, y1 = multigpu.band_edges(H, world)[rank]
             full = [None]
-            if multigpu.equal_bands(H, world):  # render into the frame's own rows, gather in place
+            if args.partition == "rows" and world > 1:  # interleaved tile rows: compacted buffer, gather, de-interleave
+                asm = multigpu.InterleavedAssembler(H, W, rank, world, dev, R.tile_height())
+
+                def step():
+                    for f in range(n):
+                        r.render_device_rows(mats[f], W, H, world, rank, asm.mine.data_ptr(), stream=stream.cuda_stream)
+                        full[0] = asm.gather()
+            elif multigpu.equal_bands(H, world):  # render into the frame's own rows, gather in place
                 frames = torch.zeros((4, H, W), dtype=torch.int32, device=dev)
 
                 def step():
