@@ -393,17 +393,23 @@ __device__ __forceinline__ void classify_body(const Frame &f, uint32_t view, uin
         } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
             cls = 2;
         } else {
-            const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
-            const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
-            const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
-            // screen-band partition: a triangle whose rows cannot meet [y0, y1) contributes nothing to this band
-            // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
-            bool off_band = max_y < f.band_lo || min_y >= f.band_hi;
-            if (!off_band && !off && f.row_stride != 1u) {   // interleaved tile rows: does it touch a row this submission owns?
-                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
-                off_band = ymin > ymax || owned_rows_in(f, ymin / TILE_H, ymax / TILE_H) == 0u;
+            // the order of the three culls does not matter for the result (all are 'continue's before any side
+            // effect, render.cpp:311-317); the area test removes ~80 % of a dense field, so it goes first
+            if (edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) {
+                culled = true;
+            } else {
+                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+                const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
+                // screen partition: a triangle whose rows cannot meet this submission's rows contributes nothing
+                // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
+                bool off_band = max_y < f.band_lo || min_y >= f.band_hi;
+                if (!off_band && !off && f.row_stride != 1u) {   // interleaved tile rows: does it touch a row we own?
+                    const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                    off_band = ymin > ymax || owned_rows_in(f, ymin / TILE_H, ymax / TILE_H) == 0u;
+                }
+                if (off || off_band) { culled = true; } else { cls = 1; }
             }
-            if (off || off_band || edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10) { culled = true; } else { cls = 1; }
         }
     }
     {   // warp-ballot compaction of the work items into shared memory

@@ -14,14 +14,15 @@ r.load_scene_file(path)
 inp = np.zeros(4, S.INPUT_DTYPE)
 mats = R.camera_path(inp)
 W, H = 3840, 2160
-out = torch.zeros((270, W), dtype=torch.int32, device="cuda:0")
+rows, _, _ = R.rows_layout(H, 8, 3)
+out = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
 for rep in range(3):
     for f in range(4):
-        r.render_device(mats[f], W, H, out.data_ptr(), y0=270 * 3, y1=270 * 4)
+        r.render_device_rows(mats[f], W, H, 8, 3, out.data_ptr())
     while r.finish():
         pass
 r.set_option("timing", 1); r.timing()
 for f in range(4):
-    r.render_device(mats[f], W, H, out.data_ptr(), y0=270 * 3, y1=270 * 4)
+    r.render_device_rows(mats[f], W, H, 8, 3, out.data_ptr())
 r.finish()
 print(r.timing(), r.stats())
