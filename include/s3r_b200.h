@@ -107,7 +107,7 @@ S3R_API int s3r_render_device(S3RRenderer *r, const float *cameras, uint32_t n_v
 /* Interleaved partition for multi-GPU load balance: renders the tile rows a (s3r_tile_height() pixel rows
  * each, counted from the top of the frame) with a % row_stride == row_phase.  Output: those tile rows
  * compacted in order — ceil((ceil(H / th) - row_phase) / row_stride) * th rows of `width` uint32 per view
- * (rows beyond `height` in the last tile row are left untouched). */
+ * (rows beyond `height` in the last tile row are padding: untouched or background). */
 S3R_API int s3r_render_device_rows(S3RRenderer *r, const float *cameras, uint32_t n_views, uint32_t width,
                                    uint32_t height, uint32_t row_stride, uint32_t row_phase, uint32_t *dev_out,
                                    void *stream);

@@ -55,6 +55,9 @@ __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by,
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+constexpr uint32_t WON = 0x80000000u;   // mark: this small triangle passed a depth pre-check in pass 1
+constexpr uint32_t SMALL_MAX = 16;      // triangles whose whole bbox is narrower and lower than this take the per-triangle path
+
 // ------------------------------------------------------------------------------------------------
 // K0 — reset
 // ------------------------------------------------------------------------------------------------
@@ -284,6 +287,10 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
     f.head[(size_t)view * f.setup_cap + slot] = sv[0];   // bbox + order key + kind: all binning needs
 }
 
+__device__ __forceinline__ bool is_small_bbox(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
+    return xmax - xmin < SMALL_MAX && ymax - ymin < SMALL_MAX;
+}
+
 // K3 for one survivor, fused into setup: triangles over few tiles are binned right here (with the
 // conservative outside test), everything larger goes to the cooperative big list.
 __device__ __forceinline__ void count_tiles(const Frame &f, uint32_t view, uint32_t slot, const SetupVis &v) {
@@ -321,7 +328,8 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
     if (keep) {
         if (slot < f.setup_cap) {
             store_setup(f, view, slot, v, s);
-            if (!f.direct_bin) { count_tiles(f, view, slot, v); }   // K3 (binning), fused
+            // general path: only triangles too large for the flat per-triangle walk are binned into tiles
+            if (!f.direct_bin && !is_small_bbox(v.xmin, v.xmax, v.ymin, v.ymax)) { count_tiles(f, view, slot, v); }
         } else {
             atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 1u);
         }
@@ -564,7 +572,6 @@ __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Fr
 // ------------------------------------------------------------------------------------------------
 // K4 — per-tile rasteriser
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t SMALL_MAX = 16;   // triangles whose whole bbox is at most this wide and high take the per-triangle path
 
 struct RasterShared {
     union {                                               // 32 KB
@@ -642,7 +649,7 @@ __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_
 // pixel drop its weights for shading.  Keys are depth << 32 | ~order: larger 1/z wins, on equal depth the
 // earlier triangle in the reference's processing order wins (strict '>' at render.cpp:364).
 template <int PASS>
-__device__ __forceinline__ void walk_small(const Frame &f, uint32_t view, uint32_t slot, uint4 head, uint32_t tx0,
+__device__ __forceinline__ bool walk_small(const Frame &f, uint32_t view, uint32_t slot, uint4 head, uint32_t tx0,
                                            uint32_t ty0, uint32_t ylo_t, uint32_t yhi_t, RasterShared &sh) {
     const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
     const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
@@ -653,6 +660,7 @@ __device__ __forceinline__ void walk_small(const Frame &f, uint32_t view, uint32
     float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y), wy2 = __uint_as_float(q1.z);
     const unsigned long long key_lo = (unsigned long long)(~head.z);
     const uint32_t y_end = min(ymax, yhi_t - 1u), x_end = min(xmax, tx0 + TILE_W - 1u);
+    bool won = false;
     for (uint32_t y = ymin; y <= y_end; y++) {
         if (y >= ylo_t) {
             float w0 = wy0, w1 = wy1, w2 = wy2;
@@ -663,7 +671,7 @@ __device__ __forceinline__ void walk_small(const Frame &f, uint32_t view, uint32
                         const uint32_t idx = (y - ty0) * TILE_W + (x - tx0);
                         const unsigned long long key = ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo;
                         if (PASS == 1) {
-                            if (key > sh.k.keys[idx]) { atomicMax(&sh.k.keys[idx], key); }
+                            if (key > sh.k.keys[idx]) { atomicMax(&sh.k.keys[idx], key); won = true; }
                         } else if (sh.k.keys[idx] == key) {
                             const uint32_t pc = x - tx0;
                             sh.u.state[(y - ty0) * TILE_W + (pc & ~7u) + ((pc & 7u) ^ ((pc >> 3) & 7u))] =
@@ -676,6 +684,7 @@ __device__ __forceinline__ void walk_small(const Frame &f, uint32_t view, uint32
         }
         wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
     }
+    return won;
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
@@ -695,11 +704,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 
     // ---- this tile's triangle list (unordered: depth keys carry the order) ---------------------
     if (tid == 0) { sh.n_list = 0; sh.n_big = 0; sh.any_small = 0; }
+    if (f.direct_bin) {   // in-tile keys are only used when small triangles are walked in the tile (small scenes)
 #pragma unroll
-    for (int i = 0; i < (TILE_W * TILE_H) / RASTER_THREADS; i++) { sh.k.keys[i * RASTER_THREADS + tid] = 0ull; }
+        for (int i = 0; i < (TILE_W * TILE_H) / RASTER_THREADS; i++) { sh.k.keys[i * RASTER_THREADS + tid] = 0ull; }
+    }
     __syncthreads();
     uint32_t n;
-    const uint32_t *list;
+    uint32_t *list;
     if (f.direct_bin) {
         // small scene: collect straight from the survivors' heads (bbox overlap clamped to the band, plus the
         // conservative outside test); at most SORT_CAP survivors exist by construction of this mode
@@ -737,7 +748,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
             const uint32_t bwid = (head.x >> 16) - (head.x & 0xFFFFu), bhgt = (head.y >> 16) - (head.y & 0xFFFFu);
             if (bwid < SMALL_MAX && bhgt < SMALL_MAX) {
                 sh.any_small = 1u;
-                walk_small<1>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh);
+                if (walk_small<1>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh)) { list[i] = slot | WON; }
             } else {
                 sh.bigq[atomicAdd(&sh.n_big, 1u)] = slot;
             }
@@ -810,19 +821,39 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         __syncthreads();
     }
 
+    if (!f.direct_bin) {
+        // general path: the small triangles' keys are final in HBM/L2 (flat passes ran before this kernel);
+        // a big-triangle candidate takes the pixel where its key is larger.  Every pixel belongs to exactly one
+        // thread of one tile CTA, so plain loads/stores suffice.  Shading happens in shade_flat.
+        if (y >= ylo_t && y < yhi_t) {
+            const size_t rbase = (size_t)view * f.out_view_stride + out_row(f, y, tile_a) * f.W;
+#pragma unroll
+            for (int j = 0; j < SEG; j++) {
+                const uint32_t x = sx0 + j;
+                if (win[j] != NO_TRI && x < f.W) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(depth[j]) << 32) |
+                                                   (unsigned long long)(~f.head[(size_t)view * f.setup_cap + win[j]].z);
+                    if (key > f.keys[rbase + x]) {
+                        f.keys[rbase + x] = key;
+                        f.pstate[rbase + x] = make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
     // ---- phase 2: per-pixel winners into shared memory (pixel-per-lane layout for coherent shading) ----
     const bool any_small = sh.any_small != 0;
     if (any_small) {
 #pragma unroll
         for (int j = 0; j < SEG; j++) { sh.u.state[swizzled(row, seg, j)] = make_uint4(0u, 0u, 0u, NO_TRI); }
         __syncthreads();
-        for (uint32_t cbase = 0; cbase < n; cbase += RASTER_THREADS) {   // small winners drop their weights
-            const uint32_t i = cbase + tid;
-            if (i < n) {
-                const uint32_t slot = list[i];
-                const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
-                const uint32_t bwid = (head.x >> 16) - (head.x & 0xFFFFu), bhgt = (head.y >> 16) - (head.y & 0xFFFFu);
-                if (bwid < SMALL_MAX && bhgt < SMALL_MAX) { walk_small<2>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh); }
+        for (uint32_t i = tid; i < n; i += RASTER_THREADS) {   // small triangles that ever led a pixel drop their weights where they won
+            const uint32_t e = list[i];
+            if (e & WON) {
+                const uint32_t slot = e & ~WON;
+                walk_small<2>(f, view, slot, f.head[(size_t)view * f.setup_cap + slot], tx0, ty0, ylo_t, yhi_t, sh);
             }
         }
         __syncthreads();
@@ -927,6 +958,103 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Flat path for small triangles (general, binned mode).  Dense fields put thousands of tiny triangles into
+// the busiest tiles; a tile CTA would then run as long as its list.  Instead every small survivor is walked by
+// one thread over its whole bounding box (no tiles, no binning, no duplication), publishing 64-bit depth keys
+// with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
+    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
+    uint4 *pstate = f.pstate + (size_t)view * f.out_view_stride;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        uint4 *hp = f.head + (size_t)view * f.setup_cap + slot;
+        const uint4 head = *hp;
+        const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+        if (!is_small_bbox(xmin, xmax, ymin, ymax)) { continue; }
+        if (PASS == 2 && !(head.w & WON)) { continue; }
+        const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+        const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+        const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
+        const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
+        const float rz0 = __uint_as_float(q3.y), rz1 = __uint_as_float(q3.z), rz2 = __uint_as_float(q3.w);
+        float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y), wy2 = __uint_as_float(q1.z);
+        const unsigned long long key_lo = (unsigned long long)(~head.z);
+        const uint32_t y_end = min(ymax, f.y1 - 1u);
+        bool won = false;
+        for (uint32_t y = ymin; y <= y_end; y++) {
+            const uint32_t a = y / TILE_H;
+            if (y >= f.y0 && owns_row(f, a)) {
+                const size_t rbase = out_row(f, y, a) * f.W;
+                float w0 = wy0, w1 = wy1, w2 = wy2;
+                for (uint32_t x = xmin; x <= xmax; x++) {
+                    if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                                  // render.cpp:362
+                        const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
+                        if (ooz > 0.f) {                                                 // depth starts at 0, strict '>'
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo;
+                            if (PASS == 1) {
+                                if (key > keys[rbase + x]) { atomicMax(&keys[rbase + x], key); won = true; }
+                            } else if (keys[rbase + x] == key) {
+                                pstate[rbase + x] = make_uint4(__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), slot);
+                            }
+                        }
+                    }
+                    w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+                }
+            }
+            wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
+        }
+        if (PASS == 1 && won) { hp->w = head.w | WON; }
+    }
+}
+
+// Deferred shading of the general path: one pixel per thread, 4 consecutive pixels per thread for 16-byte
+// (or 12-byte, 24-bit transport) stores.  rows [row0, row0 + nrows) of the (compacted) output.
+__global__ void __launch_bounds__(256) shade_flat(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t groups_per_row = (f.W + 3u) / 4u;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups_per_row * nrows) { return; }
+    const uint32_t r = row0 + g / groups_per_row, x0 = (g % groups_per_row) * 4u;
+    const size_t base = (size_t)view * f.out_view_stride + (size_t)r * f.W + x0;
+    uint32_t rgb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        rgb[k] = kBackground;
+        if (x0 + k < f.W && f.keys[base + k] != 0ull) {
+            const uint4 st = f.pstate[base + k];
+            rgb[k] = shade_pixel(f, view, st.w, __uint_as_float(st.x), __uint_as_float(st.y), __uint_as_float(st.z));
+        }
+    }
+    if (f.out_packed24) {
+        uint8_t *o = reinterpret_cast<uint8_t *>(f.out) + base * 3u;
+        if (x0 + 3u < f.W && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+            o32[0] = rgb[0] | (rgb[1] << 24); o32[1] = (rgb[1] >> 8) | (rgb[2] << 16); o32[2] = (rgb[2] >> 16) | (rgb[3] << 8);
+        } else {
+            for (int k = 0; k < 4 && x0 + k < f.W; k++) { o[3 * k] = rgb[k] & 255u; o[3 * k + 1] = (rgb[k] >> 8) & 255u; o[3 * k + 2] = rgb[k] >> 16; }
+        }
+    } else {
+        uint32_t *o = f.out + base;
+        if (x0 + 3u < f.W && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+            *reinterpret_cast<uint4 *>(o) = make_uint4(rgb[0], rgb[1], rgb[2], rgb[3]);
+        } else {
+            for (int k = 0; k < 4 && x0 + k < f.W; k++) { o[k] = rgb[k]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) keys_reset(const __grid_constant__ Frame f) {
+    const size_t n2 = ((size_t)f.n_views * f.out_view_stride + 1u) / 2u;   // pairs of keys
+    uint4 *k = reinterpret_cast<uint4 *>(f.keys);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        k[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int g_sm_count = 148;
@@ -952,12 +1080,31 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
     bin_big<<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
     frame_finalize<<<f.n_views, 256, 0, s>>>(f); launches++;
+    // small triangles: flat visibility passes over the survivor list (keys in HBM/L2)
+    keys_reset<<<persistent, 256, 0, s>>>(f); launches++;
+    const uint32_t flat_blocks = min(persistent * 2u, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
+    small_flat<1><<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
+    small_flat<2><<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
     return launches;
 }
 
 int launch_raster(const Frame &f, cudaStream_t s) {
     tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
-    return 1;
+    if (f.direct_bin) { return 1; }
+    // general path: the tile kernel only resolved the big triangles; shade the rows it covered
+    uint32_t row0, nrows;
+    if (f.row_stride == 1u) {
+        const uint32_t ya = (f.tile_row0 + f.raster_row0) * TILE_H, yb = ya + f.raster_rows * TILE_H;
+        const uint32_t lo = max(ya, f.y0), hi = min(yb, f.y1);
+        row0 = lo - f.y0; nrows = hi > lo ? hi - lo : 0u;
+    } else {
+        row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
+    }
+    if (nrows) {
+        const uint32_t groups = ((f.W + 3u) / 4u) * nrows;
+        shade_flat<<<dim3(ceil_div(groups, 256), f.n_views), 256, 0, s>>>(f, row0, nrows);
+    }
+    return 2;
 }
 
 int launch_geometry_small(const Frame &f, cudaStream_t s) {

@@ -100,6 +100,9 @@ struct Frame {
     uint32_t tile_cap;          // capacity of every tile's list
     uint32_t *big_list;
     uint32_t big_cap;
+    // general path: per-pixel depth keys (depth << 32 | ~order) and winners (w0, w1, w2, slot), indexed like `out`
+    unsigned long long *keys;
+    uint4 *pstate;
     // output
     uint32_t *out;
     unsigned long long out_view_stride;  // pixels

@@ -72,6 +72,8 @@ struct S3RRenderer {
     DevBuf<SetupVis> vis;
     DevBuf<SetupShade> shade;
     DevBuf<uint4> head;
+    DevBuf<unsigned long long> keys;   // general path: per-pixel depth keys ...
+    DevBuf<uint4> pstate;              // ... and winners
     DevBuf<uint32_t> worklist;
     DevBuf<uint32_t> sticky;
     uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
@@ -154,7 +156,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->worklist.release();
+    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->worklist.release(); r->keys.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
@@ -461,7 +463,13 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.entries = r->entries.p; f.tile_cap = r->tile_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out;
+    f.keys = r->keys.p; f.pstate = r->pstate.p;
     f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
+    if (!uses_direct_bin(r)) {   // general path: per-pixel keys and winners for the flat passes
+        CUDA_TRY(r->keys.ensure((size_t)n_views * f.out_view_stride + 2));
+        CUDA_TRY(r->pstate.ensure((size_t)n_views * f.out_view_stride + 2));
+        f.keys = r->keys.p; f.pstate = r->pstate.p;
+    }
     f.out_packed24 = packed24 ? 1 : 0;
     f.use_tma = r->opt_tma && (W % (packed24 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
