@@ -222,6 +222,10 @@ __device__ __forceinline__ uint32_t abs_row(const Frame &f, uint32_t l) { return
 __device__ __forceinline__ size_t out_row(const Frame &f, uint32_t yy, uint32_t a) {
     return f.row_stride == 1u ? (size_t)(yy - f.y0) : (size_t)(a / f.row_stride) * TILE_H + (yy - a * TILE_H);
 }
+// pixel row of output row r (inverse of out_row)
+__device__ __forceinline__ uint32_t pixel_y(const Frame &f, uint32_t r) {
+    return f.row_stride == 1u ? r + f.y0 : ((r / TILE_H) * f.row_stride + f.row_phase) * TILE_H + r % TILE_H;
+}
 __device__ __forceinline__ uint32_t owned_rows_in(const Frame &f, uint32_t a0, uint32_t a1) {   // #owned rows in [a0, a1]
     if (f.row_stride == 1u) { return a1 - a0 + 1u; }
     const uint32_t first = a0 + (f.row_phase + f.row_stride - a0 % f.row_stride) % f.row_stride;
@@ -285,6 +289,7 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
 #pragma unroll
     for (int i = 0; i < 8; i++) { ds[i] = ss[i]; }
     f.head[(size_t)view * f.setup_cap + slot] = sv[0];   // bbox + order key + kind: all binning needs
+    if (!f.direct_bin) { f.slot_of[(size_t)view * 2u * f.T + v.order] = slot; }   // lets a depth key find its triangle again
 }
 
 __device__ __forceinline__ bool is_small_bbox(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
@@ -963,18 +968,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 // one thread over its whole bounding box (no tiles, no binning, no duplication), publishing 64-bit depth keys
 // with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int PASS>
 __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame f) {
     const uint32_t view = blockIdx.y;
-    const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
-    uint4 *pstate = f.pstate + (size_t)view * f.out_view_stride;
+    const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-        uint4 *hp = f.head + (size_t)view * f.setup_cap + slot;
-        const uint4 head = *hp;
+        const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
         const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
         if (!is_small_bbox(xmin, xmax, ymin, ymax)) { continue; }
-        if (PASS == 2 && !(head.w & WON)) { continue; }
         const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
         const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
         const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
@@ -983,22 +984,17 @@ __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame 
         float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y), wy2 = __uint_as_float(q1.z);
         const unsigned long long key_lo = (unsigned long long)(~head.z);
         const uint32_t y_end = min(ymax, f.y1 - 1u);
-        bool won = false;
         for (uint32_t y = ymin; y <= y_end; y++) {
             const uint32_t a = y / TILE_H;
             if (y >= f.y0 && owns_row(f, a)) {
-                const size_t rbase = out_row(f, y, a) * f.W;
+                unsigned long long *krow = keys + out_row(f, y, a) * f.W;
                 float w0 = wy0, w1 = wy1, w2 = wy2;
                 for (uint32_t x = xmin; x <= xmax; x++) {
                     if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                                  // render.cpp:362
                         const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
-                        if (ooz > 0.f) {                                                 // depth starts at 0, strict '>'
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo;
-                            if (PASS == 1) {
-                                if (key > keys[rbase + x]) { atomicMax(&keys[rbase + x], key); won = true; }
-                            } else if (keys[rbase + x] == key) {
-                                pstate[rbase + x] = make_uint4(__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), slot);
-                            }
+                        if (ooz > 0.f) {   // depth starts at 0, strict '>' (render.cpp:364).  No load, no returned value:
+                                           // a fire-and-forget red.max that never stalls the walk
+                            atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo);
                         }
                     }
                     w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
@@ -1006,7 +1002,6 @@ __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame 
             }
             wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
         }
-        if (PASS == 1 && won) { hp->w = head.w | WON; }
     }
 }
 
@@ -1023,9 +1018,28 @@ __global__ void __launch_bounds__(256) shade_flat(const __grid_constant__ Frame 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         rgb[k] = kBackground;
-        if (x0 + k < f.W && f.keys[base + k] != 0ull) {
-            const uint4 st = f.pstate[base + k];
-            rgb[k] = shade_pixel(f, view, st.w, __uint_as_float(st.x), __uint_as_float(st.y), __uint_as_float(st.z));
+        const unsigned long long key = x0 + k < f.W ? f.keys[base + k] : 0ull;
+        if (key != 0ull) {
+            // the key's low word is ~order: find the triangle again.  A big winner left its exact weights in pstate;
+            // a small winner's weights are the triangle's own walk to this pixel (at most 15 + 15 true steps).
+            const uint32_t slot = f.slot_of[(size_t)view * 2u * f.T + (~(uint32_t)key)];
+            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+            float w0, w1, w2;
+            if (is_small_bbox(xmin, xmax, ymin, ymax)) {
+                const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+                const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+                const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
+                const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
+                w0 = __uint_as_float(q1.x); w1 = __uint_as_float(q1.y); w2 = __uint_as_float(q1.z);
+                const uint32_t py = pixel_y(f, r), px = x0 + k;
+                for (uint32_t s = ymin; s < py; s++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+                for (uint32_t s = xmin; s < px; s++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
+            } else {
+                const uint4 st = f.pstate[base + k];
+                w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);
+            }
+            rgb[k] = shade_pixel(f, view, slot, w0, w1, w2);
         }
     }
     if (f.out_packed24) {
@@ -1083,8 +1097,7 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     // small triangles: flat visibility passes over the survivor list (keys in HBM/L2)
     keys_reset<<<persistent, 256, 0, s>>>(f); launches++;
     const uint32_t flat_blocks = min(persistent * 2u, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
-    small_flat<1><<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
-    small_flat<2><<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
+    small_flat<<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
     return launches;
 }
 

@@ -37,6 +37,7 @@ constexpr int BATCH = 8;                    // triangles staged per visibility b
 constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
+constexpr uint32_t SMALL_CLASSES = 4;       // small triangles are walked class by class so that warps see similar trip counts
 
 constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
 constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.cpp:92 (binary32 value of the reference build)
@@ -44,6 +45,7 @@ constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:9
 
 enum Counter : uint32_t {
     C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7, C_WORK = 8,
+    C_SMALL0 = 12,   // .. +3: small survivors per bbox-area class (general path)
     C_COUNT = 16
 };
 
@@ -89,6 +91,8 @@ struct Frame {
     float4 *rv;
     SetupVis *vis;
     SetupShade *shade;
+    uint32_t *small_list; // [views][SMALL_CLASSES][setup_cap] small survivors by bbox-area class
+    uint32_t *slot_of;    // [views][2T] order key -> survivor slot (written for survivors only)
     uint4 *head;          // per survivor: {xmin | xmax << 16, ymin | ymax << 16, order, kind}
     uint32_t *worklist;   // [views][T] classify -> setup work items
     uint32_t setup_cap;
