@@ -130,6 +130,22 @@ __device__ __forceinline__ Corner clip_vertex(const Corner &a, const Corner &b, 
     return c;
 }
 
+// The coverage half of the setup (render.cpp:318-334): barycentric weights at the first pixel centre, their
+// per-pixel / per-row increments, 1/z per corner.  One function for every place that needs these values (setup
+// records, the classify kernel's direct walk, deferred shading) so that all of them produce the same bits.
+struct VisCore { float ws[3], dx[3], dy[3], rz[3]; };
+
+__device__ __forceinline__ void vis_core(float3 a, float3 b, float3 c, float area, uint32_t xmin, uint32_t ymin, VisCore &o) {
+    const float inv_area = __frcp_rn(area);  // 1 / area
+    const float px = (float)xmin + 0.5f, py = (float)ymin + 0.5f;
+    o.ws[0] = edge_fn(b.x, b.y, c.x, c.y, px, py) * inv_area;
+    o.ws[1] = edge_fn(c.x, c.y, a.x, a.y, px, py) * inv_area;
+    o.ws[2] = edge_fn(a.x, a.y, b.x, b.y, px, py) * inv_area;
+    o.dx[0] = (b.y - c.y) * inv_area; o.dx[1] = (c.y - a.y) * inv_area; o.dx[2] = (a.y - b.y) * inv_area;
+    o.dy[0] = (c.x - b.x) * inv_area; o.dy[1] = (a.x - c.x) * inv_area; o.dy[2] = (b.x - a.x) * inv_area;
+    o.rz[0] = __frcp_rn(a.z); o.rz[1] = __frcp_rn(b.z); o.rz[2] = __frcp_rn(c.z);  // 1 / z
+}
+
 // render.cpp:311-359.  Returns false when the triangle is culled.
 __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, const Corner &d2, uint32_t order,
                                            const Frame &f, SetupVis &v, SetupShade &s) {
@@ -141,19 +157,15 @@ __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, c
     if (min_x >= f.fw || min_y >= f.fh) { return false; }
     const float area = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, d2.rv.x, d2.rv.y);
     if (area < 10) { return false; }
-    const float inv_area = __frcp_rn(area);  // 1 / area
     const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
     const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
-    const float px = (float)xmin + 0.5f, py = (float)ymin + 0.5f;
     v.xmin = (uint16_t)xmin; v.xmax = (uint16_t)xmax; v.ymin = (uint16_t)ymin; v.ymax = (uint16_t)ymax;
     v.order = order;
     v.kind = d0.kind;
-    v.wstart[0] = edge_fn(d1.rv.x, d1.rv.y, d2.rv.x, d2.rv.y, px, py) * inv_area;
-    v.wstart[1] = edge_fn(d2.rv.x, d2.rv.y, d0.rv.x, d0.rv.y, px, py) * inv_area;
-    v.wstart[2] = edge_fn(d0.rv.x, d0.rv.y, d1.rv.x, d1.rv.y, px, py) * inv_area;
-    v.dx[0] = (d1.rv.y - d2.rv.y) * inv_area; v.dx[1] = (d2.rv.y - d0.rv.y) * inv_area; v.dx[2] = (d0.rv.y - d1.rv.y) * inv_area;
-    v.dy[0] = (d2.rv.x - d1.rv.x) * inv_area; v.dy[1] = (d0.rv.x - d2.rv.x) * inv_area; v.dy[2] = (d1.rv.x - d0.rv.x) * inv_area;
-    v.rvz[0] = __frcp_rn(d0.rv.z); v.rvz[1] = __frcp_rn(d1.rv.z); v.rvz[2] = __frcp_rn(d2.rv.z);  // 1 / z
+    VisCore vc;
+    vis_core(d0.rv, d1.rv, d2.rv, area, xmin, ymin, vc);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v.wstart[k] = vc.ws[k]; v.dx[k] = vc.dx[k]; v.dy[k] = vc.dy[k]; v.rvz[k] = vc.rz[k]; }
     const Corner *d[3] = {&d0, &d1, &d2};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -215,12 +227,15 @@ __device__ __forceinline__ bool tile_outside_triangle(const SetupVis &v, uint32_
 // submission iff it meets the band [y0, y1) and a % row_stride == row_phase.  row_stride == 1 is the
 // contiguous band; row_stride == n GPUs interleaves the tile rows for load balance.  The local row index
 // (grid row, tile arrays, compacted output) is a - tile_row0 resp. a / row_stride.
-__device__ __forceinline__ bool owns_row(const Frame &f, uint32_t a) { return f.row_stride == 1u || a % f.row_stride == f.row_phase; }
-__device__ __forceinline__ uint32_t local_row(const Frame &f, uint32_t a) { return f.row_stride == 1u ? a - f.tile_row0 : a / f.row_stride; }
+// a / row_stride and a % row_stride without a hardware division (exact for a * row_stride < 2^32; row_stride > 1)
+__device__ __forceinline__ uint32_t div_stride(const Frame &f, uint32_t a) { return __umulhi(a, f.rs_magic); }
+__device__ __forceinline__ uint32_t mod_stride(const Frame &f, uint32_t a) { return a - div_stride(f, a) * f.row_stride; }
+__device__ __forceinline__ bool owns_row(const Frame &f, uint32_t a) { return f.row_stride == 1u || mod_stride(f, a) == f.row_phase; }
+__device__ __forceinline__ uint32_t local_row(const Frame &f, uint32_t a) { return f.row_stride == 1u ? a - f.tile_row0 : div_stride(f, a); }
 __device__ __forceinline__ uint32_t abs_row(const Frame &f, uint32_t l) { return f.row_stride == 1u ? l + f.tile_row0 : l * f.row_stride + f.row_phase; }
 // output row of pixel row yy (inside absolute tile row a)
 __device__ __forceinline__ size_t out_row(const Frame &f, uint32_t yy, uint32_t a) {
-    return f.row_stride == 1u ? (size_t)(yy - f.y0) : (size_t)(a / f.row_stride) * TILE_H + (yy - a * TILE_H);
+    return f.row_stride == 1u ? (size_t)(yy - f.y0) : (size_t)(div_stride(f, a) * TILE_H + (yy - a * TILE_H));
 }
 // pixel row of output row r (inverse of out_row)
 __device__ __forceinline__ uint32_t pixel_y(const Frame &f, uint32_t r) {
@@ -228,8 +243,8 @@ __device__ __forceinline__ uint32_t pixel_y(const Frame &f, uint32_t r) {
 }
 __device__ __forceinline__ uint32_t owned_rows_in(const Frame &f, uint32_t a0, uint32_t a1) {   // #owned rows in [a0, a1]
     if (f.row_stride == 1u) { return a1 - a0 + 1u; }
-    const uint32_t first = a0 + (f.row_phase + f.row_stride - a0 % f.row_stride) % f.row_stride;
-    return first > a1 ? 0u : (a1 - first) / f.row_stride + 1u;
+    const uint32_t first = a0 + mod_stride(f, f.row_phase + f.row_stride - mod_stride(f, a0));
+    return first > a1 ? 0u : div_stride(f, a1 - first) + 1u;
 }
 
 struct TileRange { uint32_t tx0, tx1, a0, a1; bool empty; };   // tile columns and ABSOLUTE tile rows, clamped to the band
@@ -469,17 +484,144 @@ __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, ui
     __syncthreads();
 }
 
-// K2a: classify every input triangle (light: ~32 registers, full occupancy) and append the work items of
-// each CTA to the global work list with one atomic per CTA.
+// K2a: classify every input triangle and, for the common case, finish its visibility right here.
+//
+// A triangle that does not straddle the near plane and whose screen bounding box is under 16 x 16 pixels needs
+// nothing but its three raster-space vertices to be rasterised: the thread that classified it computes the
+// coverage setup (vis_core) into shared memory and cuts the box into (triangle, row) work items; the whole CTA then
+// walks those items — replaying the reference's own additions from the box's first pixel (render.cpp:374-379) — and
+// publishes depth << 32 | ~order keys with fire-and-forget 64-bit atomicMax.  No setup record, no attribute
+// gather, no bin entry is ever written for such a triangle; the pixels it wins are shaded from the raw scene
+// (shade_tiles).  Everything else (straddling or larger triangles) is appended to the work list of K2b.
+struct WalkShared {
+    float par[12][256];        // per classified thread: ws[3], dx[3], dy[3], rz[3]  (SoA: conflict-free)
+    uint32_t xy[256];          // xmin | ymin << 16
+    uint32_t bw[256];          // xmax - xmin
+    uint16_t items[256 * SMALL_MAX];   // owner thread | row << 8
+    uint32_t n_items;
+};
+
 __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
-    const uint32_t view = blockIdx.y, tid = threadIdx.x;
-    classify_body(f, view, blockIdx.x, sh);
+    __shared__ WalkShared wsh;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    if (tid == 0) { sh.count = 0; wsh.n_items = 0; }
+    if (tid < 4) { sh.stats[tid] = 0; }
+    __syncthreads();
+
+    const uint32_t t = blockIdx.x * 256u + tid;
+    uint32_t cls = 0;  // 0 rejected, 1 work item (recorded setup), 2 work item that straddles the near plane, 3 walked here
+    bool near_rej = false, culled = false;
+    if (t < f.T) {
+        const float4 *rv = f.rv + (size_t)view * f.Vpad;
+        const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
+        if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
+            near_rej = true;
+        } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
+            cls = 2;
+        } else {
+            // the order of the three culls does not matter for the result (all are 'continue's before any side
+            // effect, render.cpp:311-317); the area test removes ~80 % of a dense field, so it goes first
+            const float area = edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y);
+            culled = true;
+            if (!(area < 10)) {
+                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+                const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
+                // screen partition: a triangle whose rows cannot meet this submission's rows contributes nothing
+                // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
+                if (!off && !(max_y < f.band_lo || min_y >= f.band_hi)) {
+                    const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
+                    const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                    const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
+                    if (f.direct_small && is_small_bbox(xmin, xmax, ymin, ymax)) {
+                        // box rows this submission owns (bit r: row ymin + r).  Under 16 rows meet at most two tile rows.
+                        const uint32_t lo = ylo - ymin, hi = yhi - ymin;
+                        uint32_t rows = (2u << hi) - (1u << lo);
+                        if (f.row_stride != 1u) {
+                            const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
+                            const uint32_t split = (a0 + 1u) * TILE_H - ymin;   // first box row inside tile row a0 + 1
+                            const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
+                            rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
+                        }
+                        if (rows) {
+                            culled = false;
+                            cls = 3;
+                            VisCore vc;
+                            vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
+                                     area, xmin, ymin, vc);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                wsh.par[k][tid] = vc.ws[k]; wsh.par[3 + k][tid] = vc.dx[k];
+                                wsh.par[6 + k][tid] = vc.dy[k]; wsh.par[9 + k][tid] = vc.rz[k];
+                            }
+                            wsh.xy[tid] = xmin | (ymin << 16);
+                            wsh.bw[tid] = xmax - xmin;
+                            uint32_t pos = atomicAdd(&wsh.n_items, (uint32_t)__popc(rows));
+                            while (rows) {   // one work item per owned box row
+                                const uint32_t r = (uint32_t)__ffs((int)rows) - 1u;
+                                rows &= rows - 1u;
+                                wsh.items[pos++] = (uint16_t)(tid | (r << 8));
+                            }
+                        }
+                    } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
+                        culled = false;
+                        cls = 1;
+                    }
+                }
+            }
+        }
+    }
+    {   // warp-ballot compaction of the work items into shared memory
+        const uint32_t m_near = __ballot_sync(0xFFFFFFFFu, near_rej), m_cull = __ballot_sync(0xFFFFFFFFu, culled);
+        const uint32_t m_clip = __ballot_sync(0xFFFFFFFFu, cls == 2), m_work = __ballot_sync(0xFFFFFFFFu, cls == 1 || cls == 2);
+        const uint32_t m_direct = __ballot_sync(0xFFFFFFFFu, cls == 3);
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (m_near) { atomicAdd(&sh.stats[0], __popc(m_near)); }
+            if (m_clip) { atomicAdd(&sh.stats[1], __popc(m_clip)); }
+            if (m_cull) { atomicAdd(&sh.stats[3], __popc(m_cull)); }
+            if (m_direct) { atomicAdd(&sh.stats[2], __popc(m_direct)); }   // stats[2] counts direct walks in this kernel
+            if (m_work) { base = atomicAdd(&sh.count, __popc(m_work)); }
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (cls == 1 || cls == 2) { sh.list[base + __popc(m_work & ((1u << lane) - 1u))] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
+    }
+    __syncthreads();
     const uint32_t count = sh.count;
     if (tid == 0 && count) { sh.base = atomicAdd(f.counters + view * C_COUNT + C_WORK, count); }
+    if (tid == 0 && sh.stats[0]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR, sh.stats[0]); }
+    if (tid == 1 && sh.stats[1]) { atomicAdd(f.counters + view * C_COUNT + C_CLIPPED, sh.stats[1]); }
+    if (tid == 2 && sh.stats[2]) { atomicAdd(f.counters + view * C_COUNT + C_DIRECT, sh.stats[2]); }
+    if (tid == 3 && sh.stats[3]) { atomicAdd(f.counters + view * C_COUNT + C_CULLED, sh.stats[3]); }
+    const uint32_t n_items = wsh.n_items;
+    if (count == 0 && n_items == 0) { return; }
     __syncthreads();
     if (tid < count) { f.worklist[(size_t)view * f.T + sh.base + tid] = sh.list[tid]; }
-    if (tid < 4 && sh.stats[tid]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR + tid, sh.stats[tid]); }
+
+    // ---- the direct walk: one (triangle, row) item per thread and pass ------------------------------
+    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
+    for (uint32_t i = tid; i < n_items; i += 256u) {
+        const uint32_t it = wsh.items[i], o = it & 255u, r = it >> 8;
+        float w0 = wsh.par[0][o], w1 = wsh.par[1][o], w2 = wsh.par[2][o];
+        const float dy0 = wsh.par[6][o], dy1 = wsh.par[7][o], dy2 = wsh.par[8][o];
+        for (uint32_t k = 0; k < r; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+        const float dx0 = wsh.par[3][o], dx1 = wsh.par[4][o], dx2 = wsh.par[5][o];
+        const float rz0 = wsh.par[9][o], rz1 = wsh.par[10][o], rz2 = wsh.par[11][o];
+        const uint32_t xy = wsh.xy[o], y = (xy >> 16) + r, a = y / TILE_H;
+        unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+        const unsigned long long key_lo = (unsigned long long)(~(blockIdx.x * 256u + o));
+        const uint32_t bw = wsh.bw[o];
+        for (uint32_t x = 0; x <= bw; x++) {
+            if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                                  // render.cpp:362
+                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
+                if (ooz > 0.f) {   // depth starts at 0, strict '>' (render.cpp:364)
+                    atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo);
+                }
+            }
+            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+        }
+    }
 }
 
 // K2b: dense setup over the compacted work list (persistent grid-stride; every lane has a survivor
@@ -601,14 +743,8 @@ __device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115
 }
 
 // render.cpp:363-372 + getColor (:339-359) + getTextureColor (:124-132) for one winning pixel
-__device__ __forceinline__ uint32_t shade_pixel(const Frame &f, uint32_t view, uint32_t slot, float w0, float w1, float w2) {
-    const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
-    const float rz0 = vp->rvz[0], rz1 = vp->rvz[1], rz2 = vp->rvz[2];
-    const uint4 *sp = reinterpret_cast<const uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
-    SetupShade s;
-    uint4 *sd = reinterpret_cast<uint4 *>(&s);
-#pragma unroll
-    for (int i = 0; i < 8; i++) { sd[i] = sp[i]; }
+__device__ __forceinline__ uint32_t shade_math(const Frame &f, float rz0, float rz1, float rz2, const SetupShade &s,
+                                               float w0, float w1, float w2) {
     const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;
     const float b0 = w0 / ooz, b1 = w1 / ooz, b2 = w2 / ooz;
     const float3 c0 = make_float3(s.cv[0], s.cv[1], s.cv[2]), c1 = make_float3(s.cv[3], s.cv[4], s.cv[5]),
@@ -642,6 +778,18 @@ __device__ __forceinline__ uint32_t shade_pixel(const Frame &f, uint32_t view, u
     const uint32_t r = (uint32_t)(int)(shade * base.x) & 255u, g = (uint32_t)(int)(shade * base.y) & 255u,
                    b = (uint32_t)(int)(shade * base.z) & 255u;
     return (((r << 8) + g) << 8) + b;  // RGB(), render.cpp:8
+}
+
+// the same, from a setup record
+__device__ __forceinline__ uint32_t shade_pixel(const Frame &f, uint32_t view, uint32_t slot, float w0, float w1, float w2) {
+    const SetupVis *vp = f.vis + (size_t)view * f.setup_cap + slot;
+    const float rz0 = vp->rvz[0], rz1 = vp->rvz[1], rz2 = vp->rvz[2];
+    const uint4 *sp = reinterpret_cast<const uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
+    SetupShade s;
+    uint4 *sd = reinterpret_cast<uint4 *>(&s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sd[i] = sp[i]; }
+    return shade_math(f, rz0, rz1, rz2, s, w0, w1, w2);
 }
 
 __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_t j) {
@@ -829,7 +977,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     if (!f.direct_bin) {
         // general path: the small triangles' keys are final in HBM/L2 (flat passes ran before this kernel);
         // a big-triangle candidate takes the pixel where its key is larger.  Every pixel belongs to exactly one
-        // thread of one tile CTA, so plain loads/stores suffice.  Shading happens in shade_flat.
+        // thread of one tile CTA, so plain loads/stores suffice.  Shading happens in shade_tiles.
         if (y >= ylo_t && y < yhi_t) {
             const size_t rbase = (size_t)view * f.out_view_stride + out_row(f, y, tile_a) * f.W;
 #pragma unroll
@@ -1005,24 +1153,97 @@ __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame 
     }
 }
 
-// Deferred shading of the general path: one pixel per thread, 4 consecutive pixels per thread for 16-byte
-// (or 12-byte, 24-bit transport) stores.  rows [row0, row0 + nrows) of the (compacted) output.
-__global__ void __launch_bounds__(256) shade_flat(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
-    const uint32_t view = blockIdx.y;
-    const uint32_t groups_per_row = (f.W + 3u) / 4u;
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= groups_per_row * nrows) { return; }
-    const uint32_t r = row0 + g / groups_per_row, x0 = (g % groups_per_row) * 4u;
-    const size_t base = (size_t)view * f.out_view_stride + (size_t)r * f.W + x0;
-    uint32_t rgb[4];
+// Deferred shading of the general path (visibility buffer -> colour).  One CTA per 32 x 32 block of output pixels:
+//   1. read the block's depth keys, clear them for the next frame (so no separate reset pass exists) and compact the
+//      covered pixels into a list — background pixels cost nothing beyond this;
+//   2. one covered pixel per lane: the key's low word is ~order.  An unclipped triangle under 16 x 16 pixels has no
+//      record: its three corners are gathered and set up right here (the same make_setup the recorded path runs,
+//      hence the same bits) — attributes and normals of triangles that win no pixel are never read.  Recorded
+//      triangles are found through slot_of.  Small winners replay their own walk to the pixel (<= 15 + 15 true
+//      additions, render.cpp:374-379); big winners left their exact weights in pstate (tile_raster);
+//   3. the colour block goes out in 16-byte (or 12-byte, 24-bit transport) pieces.
+constexpr uint32_t SHADE_B = 32;   // block edge in pixels
+
+struct ShadeShared {
+    __align__(16) uint32_t colour[SHADE_B][SHADE_B];
+    uint32_t order[SHADE_B * SHADE_B];
+    uint16_t pix[SHADE_B * SHADE_B];
+    uint32_t count;
+};
+
+__global__ void __launch_bounds__(256) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+    __shared__ ShadeShared sh;
+    const uint32_t view = blockIdx.z, tid = threadIdx.x, lane = lane_id();
+    const uint32_t bx0 = blockIdx.x * SHADE_B, br0 = blockIdx.y * SHADE_B;       // block origin: pixel column, row within [row0, row0 + nrows)
+    const bool broken = f.counters[view * C_COUNT + C_OVERFLOW] != 0;            // incomplete lists: the host renders the frame again
+    if (tid == 0) { sh.count = 0; }
+    __syncthreads();
+    const size_t vbase = (size_t)view * f.out_view_stride;
+    {   // ---- 1. keys -> compacted list of covered pixels -------------------------------------------
+        const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u;   // this thread's 4 pixels: block row pr, columns pc .. pc + 3
+        uint32_t ord[4] = {0u, 0u, 0u, 0u}, mask = 0;
+        if (br0 + pr < nrows) {
+            unsigned long long *kp = f.keys + vbase + (size_t)(row0 + br0 + pr) * f.W + bx0 + pc;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        rgb[k] = kBackground;
-        const unsigned long long key = x0 + k < f.W ? f.keys[base + k] : 0ull;
-        if (key != 0ull) {
-            // the key's low word is ~order: find the triangle again.  A big winner left its exact weights in pstate;
-            // a small winner's weights are the triangle's own walk to this pixel (at most 15 + 15 true steps).
-            const uint32_t slot = f.slot_of[(size_t)view * 2u * f.T + (~(uint32_t)key)];
+            for (int k = 0; k < 4; k++) {
+                if (bx0 + pc + k < f.W) {
+                    const unsigned long long key = kp[k];
+                    if (key != 0ull) { kp[k] = 0ull; ord[k] = ~(uint32_t)key; mask |= 1u << k; }
+                }
+            }
+        }
+        *reinterpret_cast<uint4 *>(&sh.colour[pr][pc]) = make_uint4(kBackground, kBackground, kBackground, kBackground);
+        // warp-aggregated append (keeps the row-major order inside a warp: neighbours share triangles)
+        const uint32_t n = __popc(mask);
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 31 && total) { base = atomicAdd(&sh.count, total); }
+        uint32_t j = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - n;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (mask & (1u << k)) { sh.order[j] = ord[k]; sh.pix[j] = (uint16_t)(pr * SHADE_B + pc + k); j++; }
+        }
+    }
+    __syncthreads();
+    // ---- 2. shade, one covered pixel per lane -----------------------------------------------------
+    const uint32_t count = broken ? 0u : sh.count;
+    const Cam cam = load_cam(f.cams + 12 * view);
+#pragma unroll 1
+    for (uint32_t i = tid; i < count; i += 256u) {
+        const uint32_t order = sh.order[i], p = sh.pix[i], pr = p / SHADE_B, pc = p % SHADE_B;
+        const uint32_t px = bx0 + pc, py = pixel_y(f, row0 + br0 + pr);
+        uint32_t rgb;
+        bool direct = false;
+        uint32_t i0 = 0, i1 = 0, i2 = 0;
+        if (f.direct_small && order < f.T) {
+            // the classify kernel's own routing rule: not straddling the near plane, screen box under 16 x 16
+            i0 = __ldg(f.vi0 + order); i1 = __ldg(f.vi1 + order); i2 = __ldg(f.vi2 + order);
+            const float4 *rv = f.rv + (size_t)view * f.Vpad;
+            const float4 r0 = rv[i0], r1 = rv[i1], r2 = rv[i2];
+            if (!(fminf(fminf(r0.z, r1.z), r2.z) < kNear)) {
+                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+                const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
+                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                direct = is_small_bbox(xmin, xmax, ymin, ymax);
+            }
+        }
+        if (direct) {
+            const Corner d0 = gather_corner(f, cam, view, i0, __ldg(f.ai0 + order));
+            const Corner d1 = gather_corner(f, cam, view, i1, __ldg(f.ai1 + order));
+            const Corner d2 = gather_corner(f, cam, view, i2, __ldg(f.ai2 + order));
+            SetupVis v;
+            SetupShade s;
+            make_setup(d0, d1, d2, order, f, v, s);
+            float w0 = v.wstart[0], w1 = v.wstart[1], w2 = v.wstart[2];
+            for (uint32_t k = v.ymin; k < py; k++) { w0 = add_rn(w0, v.dy[0]); w1 = add_rn(w1, v.dy[1]); w2 = add_rn(w2, v.dy[2]); }   // render.cpp:378
+            for (uint32_t k = v.xmin; k < px; k++) { w0 = add_rn(w0, v.dx[0]); w1 = add_rn(w1, v.dx[1]); w2 = add_rn(w2, v.dx[2]); }   // render.cpp:374
+            rgb = shade_math(f, v.rvz[0], v.rvz[1], v.rvz[2], s, w0, w1, w2);
+        } else {
+            const uint32_t slot = f.slot_of[(size_t)view * 2u * f.T + order];
             const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             float w0, w1, w2;
@@ -1032,16 +1253,23 @@ __global__ void __launch_bounds__(256) shade_flat(const __grid_constant__ Frame 
                 const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
                 const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
                 w0 = __uint_as_float(q1.x); w1 = __uint_as_float(q1.y); w2 = __uint_as_float(q1.z);
-                const uint32_t py = pixel_y(f, r), px = x0 + k;
-                for (uint32_t s = ymin; s < py; s++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
-                for (uint32_t s = xmin; s < px; s++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
+                for (uint32_t k = ymin; k < py; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+                for (uint32_t k = xmin; k < px; k++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
             } else {
-                const uint4 st = f.pstate[base + k];
+                const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + pr) * f.W + px];
                 w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);
             }
-            rgb[k] = shade_pixel(f, view, slot, w0, w1, w2);
+            rgb = shade_pixel(f, view, slot, w0, w1, w2);
         }
+        sh.colour[pr][pc] = rgb;
     }
+    __syncthreads();
+    // ---- 3. write-out: 4 consecutive pixels per thread --------------------------------------------
+    const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u, x0 = bx0 + pc;
+    if (br0 + pr >= nrows || x0 >= f.W) { return; }
+    const uint4 c = *reinterpret_cast<const uint4 *>(&sh.colour[pr][pc]);
+    const uint32_t rgb[4] = {c.x, c.y, c.z, c.w};
+    const size_t base = vbase + (size_t)(row0 + br0 + pr) * f.W + x0;
     if (f.out_packed24) {
         uint8_t *o = reinterpret_cast<uint8_t *>(f.out) + base * 3u;
         if (x0 + 3u < f.W && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
@@ -1057,14 +1285,6 @@ __global__ void __launch_bounds__(256) shade_flat(const __grid_constant__ Frame 
         } else {
             for (int k = 0; k < 4 && x0 + k < f.W; k++) { o[k] = rgb[k]; }
         }
-    }
-}
-
-__global__ void __launch_bounds__(256) keys_reset(const __grid_constant__ Frame f) {
-    const size_t n2 = ((size_t)f.n_views * f.out_view_stride + 1u) / 2u;   // pairs of keys
-    uint4 *k = reinterpret_cast<uint4 *>(f.keys);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-        k[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -1094,8 +1314,7 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
     bin_big<<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
     frame_finalize<<<f.n_views, 256, 0, s>>>(f); launches++;
-    // small triangles: flat visibility passes over the survivor list (keys in HBM/L2)
-    keys_reset<<<persistent, 256, 0, s>>>(f); launches++;
+    // recorded small triangles (clipped or spawned ones): flat visibility pass over the survivor list
     const uint32_t flat_blocks = min(persistent * 2u, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
     small_flat<<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
     return launches;
@@ -1114,8 +1333,7 @@ int launch_raster(const Frame &f, cudaStream_t s) {
         row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
     }
     if (nrows) {
-        const uint32_t groups = ((f.W + 3u) / 4u) * nrows;
-        shade_flat<<<dim3(ceil_div(groups, 256), f.n_views), 256, 0, s>>>(f, row0, nrows);
+        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, 0, s>>>(f, row0, nrows);
     }
     return 2;
 }

@@ -12,7 +12,9 @@
 //
 //   per view (frame scratch, strided by view)
 //     rv                  float4[Vpad]       raster-space vertices (x, y, z, -) from the vertex stage
-//     vis / shade         64 B + 128 B per surviving triangle (compacted)
+//     vis / shade         64 B + 128 B per *recorded* surviving triangle (compacted): clipped, spawned or larger than
+//                         16 x 16 pixels.  Small unclipped survivors never get a record (visibility-buffer path).
+//     keys                u64[pixels]        general path: depth << 32 | ~order per pixel (atomicMax); zero = background
 //     tile_count, entries (u32 survivor slots, tile_cap per tile, unordered), big_list, counters
 //
 // Screen tiles are TILE_W x TILE_H pixels, aligned to the full frame's origin (so a band-partitioned
@@ -37,7 +39,6 @@ constexpr int BATCH = 8;                    // triangles staged per visibility b
 constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
-constexpr uint32_t SMALL_CLASSES = 4;       // small triangles are walked class by class so that warps see similar trip counts
 
 constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
 constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.cpp:92 (binary32 value of the reference build)
@@ -45,7 +46,7 @@ constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:9
 
 enum Counter : uint32_t {
     C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7, C_WORK = 8,
-    C_SMALL0 = 12,   // .. +3: small survivors per bbox-area class (general path)
+    C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
     C_COUNT = 16
 };
 
@@ -86,13 +87,13 @@ struct Frame {
     float band_lo, band_hi;   // (float)y0, (float)y1: early band reject in the classify pass
     uint32_t tiles_x, tile_row0, tiles_y, n_tiles;   // tiles_y: tile rows this submission owns
     uint32_t row_stride, row_phase;                  // tile-row ownership: a % row_stride == row_phase (1, 0 = contiguous band)
+    uint32_t rs_magic;                               // floor(2^32 / row_stride) + 1: a / row_stride == umulhi(a, rs_magic) for a * row_stride < 2^32
     uint32_t raster_row0, raster_rows;   // tile rows [raster_row0, raster_row0 + raster_rows) of the band go in one raster launch
     // per-view scratch
     float4 *rv;
     SetupVis *vis;
     SetupShade *shade;
-    uint32_t *small_list; // [views][SMALL_CLASSES][setup_cap] small survivors by bbox-area class
-    uint32_t *slot_of;    // [views][2T] order key -> survivor slot (written for survivors only)
+    uint32_t *slot_of;    // [views][2T] order key -> survivor slot (written for recorded survivors only)
     uint4 *head;          // per survivor: {xmin | xmax << 16, ymin | ymax << 16, order, kind}
     uint32_t *worklist;   // [views][T] classify -> setup work items
     uint32_t setup_cap;
@@ -111,6 +112,7 @@ struct Frame {
     uint32_t *out;
     unsigned long long out_view_stride;  // pixels
     int use_tma;
+    int direct_small;   // 1 (general path): small unclipped survivors are walked by the classify kernel and shaded from the raw scene
     int direct_bin;     // 1: no bin arrays — every raster CTA collects its triangles from the setup list itself
     int out_packed24;   // 1: `out` is a byte buffer with 3 bytes per pixel (B, G, R), used for host transport
 };

@@ -72,7 +72,7 @@ struct S3RRenderer {
     DevBuf<SetupVis> vis;
     DevBuf<SetupShade> shade;
     DevBuf<uint4> head;
-    DevBuf<uint32_t> small_list, slot_of;
+    DevBuf<uint32_t> slot_of;
     DevBuf<unsigned long long> keys;   // general path: per-pixel depth keys ...
     DevBuf<uint4> pstate;              // ... and winners
     DevBuf<uint32_t> worklist;
@@ -105,7 +105,7 @@ struct S3RRenderer {
     uint8_t *staging = nullptr;
     size_t staging_bytes = 0;
     HostCopier *copier = nullptr;
-    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1;
+    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1;
     std::vector<HostPin> pins;
 };
 
@@ -157,7 +157,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->small_list.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->pstate.release();
+    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
@@ -234,7 +234,7 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
     r->V = V; r->Vpad = px.size(); r->I = I; r->T = T; r->A = A; r->n_texels = n_texels;
     r->has_scene = true;
     r->views_cap = 0;  // scratch is re-sized on the next render
-    r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->small_list.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+    r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
     return S3R_OK;
 }
 
@@ -384,7 +384,6 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     CUDA_TRY(r->shade.ensure(vc * r->setup_cap));
     CUDA_TRY(r->head.ensure(vc * r->setup_cap));
     if (!uses_direct_bin(r)) {
-        CUDA_TRY(r->small_list.ensure(vc * SMALL_CLASSES * (size_t)r->setup_cap));
         CUDA_TRY(r->slot_of.ensure(vc * 2ull * std::max<uint64_t>(r->T, 1)));
     }
     CUDA_TRY(r->worklist.ensure(vc * std::max<uint64_t>(r->T, 1)));
@@ -459,7 +458,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.W = W; f.H = H; f.y0 = y0; f.y1 = y1;
     f.fw = (float)W; f.fh = (float)H; f.half_w = f.fw / 2; f.half_h = f.fh / 2;  // screen_size / 2, render.cpp:284,288
     f.factor = r->factor_override != 0.f ? r->factor_override : s3r_factor(H);
-    f.rv = r->rv.p; f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.small_list = r->small_list.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
+    f.rv = r->rv.p; f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
     f.band_lo = (float)y0; f.band_hi = (float)y1;
     f.counters = r->counters.p;
     f.sticky = r->sticky.p;
@@ -471,7 +470,12 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.keys = r->keys.p; f.pstate = r->pstate.p;
     f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
     if (!uses_direct_bin(r)) {   // general path: per-pixel keys and winners for the flat passes
-        CUDA_TRY(r->keys.ensure((size_t)n_views * f.out_view_stride + 2));
+        // keys are all zero between frames: allocation clears them, shade_tiles clears what a frame has set
+        if ((size_t)n_views * f.out_view_stride + 2 > r->keys.n) {
+            CUDA_TRY(cudaStreamSynchronize(s));
+            CUDA_TRY(r->keys.ensure((size_t)n_views * f.out_view_stride + 2));
+            CUDA_TRY(cudaMemsetAsync(r->keys.p, 0, r->keys.n * sizeof(unsigned long long), s));
+        }
         CUDA_TRY(r->pstate.ensure((size_t)n_views * f.out_view_stride + 2));
         f.keys = r->keys.p; f.pstate = r->pstate.p;
     }
@@ -481,6 +485,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
     f.direct_bin = uses_direct_bin(r) ? 1 : 0;
+    f.direct_small = !f.direct_bin && r->opt_direct_small ? 1 : 0;
+    f.rs_magic = row_stride > 1 ? (uint32_t)((1ull << 32) / row_stride) + 1u : 0u;
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
@@ -567,7 +573,7 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
         r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * r->T + 16, (uint64_t)need_setups + need_setups / 2 + 1024);
         r->big_cap = std::max(r->big_cap, r->setup_cap / 16u);
         // vis/shade are view-strided by setup_cap: force reallocation
-        r->vis.release(); r->shade.release(); r->head.release(); r->small_list.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
     }
     if (overflow & 2u) { r->tile_cap = std::max(r->tile_cap, need_entries + need_entries / 2 + 64); r->entries.release(); }
     if (overflow & 4u) { r->big_cap = std::max(r->big_cap, need_big + need_big / 2 + 64); r->big_list.release(); }
@@ -736,7 +742,7 @@ extern "C" int s3r_get_stats(S3RRenderer *r, uint32_t view, S3RStats *out) {
     memset(out, 0, sizeof(*out));
     out->triangles_in = (uint32_t)r->T;
     out->near_rejected = c[C_NEAR]; out->clipped = c[C_CLIPPED]; out->spawned = c[C_SPAWNED]; out->culled = c[C_CULLED];
-    out->setups = c[C_SETUPS]; out->bin_entries = c[C_ENTRIES]; out->big_triangles = c[C_BIG]; out->overflow = c[C_OVERFLOW];
+    out->setups = c[C_SETUPS] + c[C_DIRECT]; out->bin_entries = c[C_ENTRIES]; out->big_triangles = c[C_BIG]; out->overflow = c[C_OVERFLOW];
     return S3R_OK;
 }
 
@@ -829,6 +835,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!r || !name) { return fail(S3R_E_ARG, "null argument"); }
     if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
+    if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "pack24")) { r->opt_pack24 = value != 0; return S3R_OK; }
     if (!strcmp(name, "host_bands")) { r->opt_host_bands = (int)std::max<int64_t>(1, value); return S3R_OK; }
     if (!strcmp(name, "copy_threads")) {
@@ -848,7 +855,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
         if (value < 1) { return fail(S3R_E_ARG, "setup_capacity < 1"); }
         cudaStreamSynchronize(r->stream);
         r->setup_cap = (uint32_t)value; r->tile_cap = 4; r->big_cap = 4;
-        r->vis.release(); r->shade.release(); r->head.release(); r->small_list.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
         return S3R_OK;
     }
     return fail(S3R_E_ARG, std::string("unknown option ") + name);

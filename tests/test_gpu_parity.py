@@ -73,7 +73,9 @@ def test_stage_dumps_are_bit_exact(gpu_renderer, renderer_lib, oracle_port):
     osc = oracle_port.OracleScene(sc)
     m = renderer_lib.camera_path(S.input_script("spin", 12))[11]
     W, H = 480, 270
+    gpu_renderer.set_option("direct_small", 0)  # every survivor gets a setup record (the default walks small ones record-free)
     gpu_renderer.render(m, W, H)
+    gpu_renderer.set_option("direct_small", 1)
     _, rv = osc.vertex_stage(m, W, H)
     assert np.array_equal(gpu_renderer.raster_vertices().view(np.uint32), rv.view(np.uint32))
     want = osc.render(m, W, H, want_setups=True)["setups"]
@@ -139,10 +141,12 @@ def test_tma_and_plain_write_out_agree(gpu_renderer, renderer_lib):
     assert_same(b, a, 'plain vs TMA write-out')
 
 
-def test_capacity_regrowth_is_transparent(renderer_lib, oracle_port):
+@pytest.mark.parametrize("direct_small", [1, 0])
+def test_capacity_regrowth_is_transparent(direct_small, renderer_lib, oracle_port):
     sc = S.icosahedron_field(2000, seed=3, extent=60)
     r = renderer_lib.Renderer(0)
     r.load_scene(sc)
+    r.set_option("direct_small", direct_small)
     r.set_option("setup_capacity", 8)  # far too small: forces the overflow -> regrow -> re-render path
     m = renderer_lib.camera_path(S.input_script("spin", 5))[4]
     got = r.render(m, 640, 360)[0]
@@ -298,9 +302,15 @@ def test_fused_and_multi_kernel_geometry_agree(renderer_lib, oracle_port):
         a = r.render(mats[f], 1280, 720)[0]
         sa, la = r.setups(), r.stats()
         r.set_option("fused_small", 0)
-        b = r.render(mats[f], 1280, 720)[0]
+        c = r.render(mats[f], 1280, 720)[0]   # general path, small triangles walked record-free (the default)
+        lc = r.stats()
+        r.set_option("direct_small", 0)
+        b = r.render(mats[f], 1280, 720)[0]   # general path, every survivor recorded
         sb, lb = r.setups(), r.stats()
+        r.set_option("direct_small", 1)
         assert_same(a, b, f"fused vs general frame {f}")
+        assert_same(a, c, f"fused vs general (record-free small triangles) frame {f}")
+        assert lc["setups"] == lb["setups"] and lc["culled"] == lb["culled"]
         assert sa.tobytes() == sb.tobytes()
         geo = ('triangles_in', 'near_rejected', 'clipped', 'spawned', 'culled', 'setups', 'overflow')
         assert {k: la[k] for k in geo} == {k: lb[k] for k in geo}  # the fused path keeps no bin statistics
