@@ -494,19 +494,22 @@ __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, ui
 // gather, no bin entry is ever written for such a triangle; the pixels it wins are shaded from the raw scene
 // (shade_tiles).  Everything else (straddling or larger triangles) is appended to the work list of K2b.
 struct WalkShared {
-    float par[12][256];        // per classified thread: ws[3], dx[3], dy[3], rz[3]  (SoA: conflict-free)
+    float par[12][256];        // by owner thread.  classify: corners (x, y, z) x 3 + area;  setup pass: ws[3], dx[3], dy[3], rz[3]
+    float ck[9][256];          // row-start weights at box rows 4, 8, 12 (checkpoints: a row item replays at most 3 row steps)
     uint32_t xy[256];          // xmin | ymin << 16
-    uint32_t bw[256];          // xmax - xmin
-    uint16_t items[256 * SMALL_MAX];   // owner thread | row << 8
-    uint32_t n_items;
+    uint32_t bwrows[256];      // xmax - xmin | owned-row mask << 16
+    uint16_t items[256 * SMALL_MAX];   // owner thread | row << 8, grouped by box-width class
+    uint8_t surv[256];         // owner threads of the boxes to walk (compacted)
+    uint32_t n_surv;
+    uint32_t cls_count[4];     // row items per box-width class (width 1-4, 5-8, 9-12, 13-16 pixels)
 };
 
 __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
     __shared__ WalkShared wsh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
-    if (tid == 0) { sh.count = 0; wsh.n_items = 0; }
-    if (tid < 4) { sh.stats[tid] = 0; }
+    if (tid == 0) { sh.count = 0; wsh.n_surv = 0; }
+    if (tid < 4) { sh.stats[tid] = 0; wsh.cls_count[tid] = 0; }
     __syncthreads();
 
     const uint32_t t = blockIdx.x * 256u + tid;
@@ -544,25 +547,15 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
                             const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
                             rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
                         }
-                        if (rows) {
+                        if (rows) {   // park the corners; the setup itself runs densely packed below
                             culled = false;
                             cls = 3;
-                            VisCore vc;
-                            vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
-                                     area, xmin, ymin, vc);
-#pragma unroll
-                            for (int k = 0; k < 3; k++) {
-                                wsh.par[k][tid] = vc.ws[k]; wsh.par[3 + k][tid] = vc.dx[k];
-                                wsh.par[6 + k][tid] = vc.dy[k]; wsh.par[9 + k][tid] = vc.rz[k];
-                            }
+                            wsh.par[0][tid] = r0.x; wsh.par[1][tid] = r0.y; wsh.par[2][tid] = r0.z;
+                            wsh.par[3][tid] = r1.x; wsh.par[4][tid] = r1.y; wsh.par[5][tid] = r1.z;
+                            wsh.par[6][tid] = r2.x; wsh.par[7][tid] = r2.y; wsh.par[8][tid] = r2.z;
+                            wsh.par[9][tid] = area;
                             wsh.xy[tid] = xmin | (ymin << 16);
-                            wsh.bw[tid] = xmax - xmin;
-                            uint32_t pos = atomicAdd(&wsh.n_items, (uint32_t)__popc(rows));
-                            while (rows) {   // one work item per owned box row
-                                const uint32_t r = (uint32_t)__ffs((int)rows) - 1u;
-                                rows &= rows - 1u;
-                                wsh.items[pos++] = (uint16_t)(tid | (r << 8));
-                            }
+                            wsh.bwrows[tid] = (xmax - xmin) | (rows << 16);
                         }
                     } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
                         culled = false;
@@ -572,53 +565,90 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
             }
         }
     }
-    {   // warp-ballot compaction of the work items into shared memory
+    {   // warp-ballot compaction: work items for K2b, boxes to walk here
         const uint32_t m_near = __ballot_sync(0xFFFFFFFFu, near_rej), m_cull = __ballot_sync(0xFFFFFFFFu, culled);
         const uint32_t m_clip = __ballot_sync(0xFFFFFFFFu, cls == 2), m_work = __ballot_sync(0xFFFFFFFFu, cls == 1 || cls == 2);
         const uint32_t m_direct = __ballot_sync(0xFFFFFFFFu, cls == 3);
-        uint32_t base = 0;
+        uint32_t base = 0, dbase = 0;
         if (lane == 0) {
             if (m_near) { atomicAdd(&sh.stats[0], __popc(m_near)); }
             if (m_clip) { atomicAdd(&sh.stats[1], __popc(m_clip)); }
             if (m_cull) { atomicAdd(&sh.stats[3], __popc(m_cull)); }
-            if (m_direct) { atomicAdd(&sh.stats[2], __popc(m_direct)); }   // stats[2] counts direct walks in this kernel
             if (m_work) { base = atomicAdd(&sh.count, __popc(m_work)); }
+            if (m_direct) { dbase = atomicAdd(&wsh.n_surv, __popc(m_direct)); }
         }
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (cls == 1 || cls == 2) { sh.list[base + __popc(m_work & ((1u << lane) - 1u))] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
+        dbase = __shfl_sync(0xFFFFFFFFu, dbase, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (cls == 1 || cls == 2) { sh.list[base + __popc(m_work & below)] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
+        if (cls == 3) { wsh.surv[dbase + __popc(m_direct & below)] = (uint8_t)tid; }
     }
     __syncthreads();
-    const uint32_t count = sh.count;
+    const uint32_t count = sh.count, n_surv = wsh.n_surv;
     if (tid == 0 && count) { sh.base = atomicAdd(f.counters + view * C_COUNT + C_WORK, count); }
     if (tid == 0 && sh.stats[0]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR, sh.stats[0]); }
     if (tid == 1 && sh.stats[1]) { atomicAdd(f.counters + view * C_COUNT + C_CLIPPED, sh.stats[1]); }
-    if (tid == 2 && sh.stats[2]) { atomicAdd(f.counters + view * C_COUNT + C_DIRECT, sh.stats[2]); }
+    if (tid == 2 && n_surv) { atomicAdd(f.counters + view * C_COUNT + C_DIRECT, n_surv); }
     if (tid == 3 && sh.stats[3]) { atomicAdd(f.counters + view * C_COUNT + C_CULLED, sh.stats[3]); }
-    const uint32_t n_items = wsh.n_items;
-    if (count == 0 && n_items == 0) { return; }
+    if (count == 0 && n_surv == 0) { return; }
+
+    // ---- coverage setup of the boxes to walk, one per lane, densely packed --------------------------
+    uint32_t o = 0, my_cls = 0, my_rows = 0, my_off = 0;
+    if (tid < n_surv) {
+        o = wsh.surv[tid];
+        const float3 a = make_float3(wsh.par[0][o], wsh.par[1][o], wsh.par[2][o]);
+        const float3 b = make_float3(wsh.par[3][o], wsh.par[4][o], wsh.par[5][o]);
+        const float3 c = make_float3(wsh.par[6][o], wsh.par[7][o], wsh.par[8][o]);
+        const uint32_t xy = wsh.xy[o], br = wsh.bwrows[o];
+        VisCore vc;
+        vis_core(a, b, c, wsh.par[9][o], xy & 0xFFFFu, xy >> 16, vc);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            wsh.par[k][o] = vc.ws[k]; wsh.par[3 + k][o] = vc.dx[k]; wsh.par[6 + k][o] = vc.dy[k]; wsh.par[9 + k][o] = vc.rz[k];
+        }
+        my_rows = br >> 16;
+        float w0 = vc.ws[0], w1 = vc.ws[1], w2 = vc.ws[2];
+        const uint32_t top = 31u - (uint32_t)__clz((int)my_rows);   // last owned box row
+        for (uint32_t r = 1; r <= (top & ~3u); r++) {              // render.cpp:378, row by row; keep rows 4, 8, 12
+            w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
+            if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][o] = w0; wsh.ck[3 * g + 1][o] = w1; wsh.ck[3 * g + 2][o] = w2; }
+        }
+        my_cls = (br & 0xFFFFu) >> 2;
+        my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(my_rows));
+    }
     __syncthreads();
     if (tid < count) { f.worklist[(size_t)view * f.T + sh.base + tid] = sh.list[tid]; }
+    const uint32_t c0 = wsh.cls_count[0], c1 = wsh.cls_count[1], c2 = wsh.cls_count[2], n_items = c0 + c1 + c2 + wsh.cls_count[3];
+    if (tid < n_surv) {
+        uint32_t pos = my_off + (my_cls > 0u ? c0 : 0u) + (my_cls > 1u ? c1 : 0u) + (my_cls > 2u ? c2 : 0u);
+        while (my_rows) {   // one work item per owned box row
+            const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
+            my_rows &= my_rows - 1u;
+            wsh.items[pos++] = (uint16_t)(o | (r << 8));
+        }
+    }
+    __syncthreads();
 
     // ---- the direct walk: one (triangle, row) item per thread and pass ------------------------------
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     for (uint32_t i = tid; i < n_items; i += 256u) {
-        const uint32_t it = wsh.items[i], o = it & 255u, r = it >> 8;
-        float w0 = wsh.par[0][o], w1 = wsh.par[1][o], w2 = wsh.par[2][o];
-        const float dy0 = wsh.par[6][o], dy1 = wsh.par[7][o], dy2 = wsh.par[8][o];
-        for (uint32_t k = 0; k < r; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
-        const float dx0 = wsh.par[3][o], dx1 = wsh.par[4][o], dx2 = wsh.par[5][o];
-        const float rz0 = wsh.par[9][o], rz1 = wsh.par[10][o], rz2 = wsh.par[11][o];
-        const uint32_t xy = wsh.xy[o], y = (xy >> 16) + r, a = y / TILE_H;
+        const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
+        float w0, w1, w2;
+        if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
+        else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
+        const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
+        for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+        const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
+        const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
+        const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
         unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
-        const unsigned long long key_lo = (unsigned long long)(~(blockIdx.x * 256u + o));
-        const uint32_t bw = wsh.bw[o];
+        const unsigned long long key_lo = (unsigned long long)(~(blockIdx.x * 256u + ow));
+        const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
         for (uint32_t x = 0; x <= bw; x++) {
-            if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                                  // render.cpp:362
-                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
-                if (ooz > 0.f) {   // depth starts at 0, strict '>' (render.cpp:364)
-                    atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo);
-                }
-            }
+            const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+            const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
+            // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+            if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
             w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
         }
     }

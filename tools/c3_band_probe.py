@@ -1,5 +1,5 @@
 """tools/c3_band_probe.py — development aid: renders one 1/8 screen band of the C3 scene on a single GPU
-(what each rank does in the 8-GPU configuration) so that ncu can list its kernels."""
+(what each rank does in the 8-GPU configuration; C3_WORLD=1 C3_PHASE=0 renders the whole frame) so that ncu can list its kernels."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
@@ -14,15 +14,16 @@ r.load_scene_file(path)
 inp = np.zeros(4, S.INPUT_DTYPE)
 mats = R.camera_path(inp)
 W, H = 3840, 2160
-rows, _, _ = R.rows_layout(H, 8, 3)
+world, phase = int(os.environ.get("C3_WORLD", "8")), int(os.environ.get("C3_PHASE", "3"))
+rows, _, _ = R.rows_layout(H, world, phase)
 out = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
 for rep in range(3):
     for f in range(4):
-        r.render_device_rows(mats[f], W, H, 8, 3, out.data_ptr())
+        r.render_device_rows(mats[f], W, H, world, phase, out.data_ptr())
     while r.finish():
         pass
 r.set_option("timing", 1); r.timing()
 for f in range(4):
-    r.render_device_rows(mats[f], W, H, 8, 3, out.data_ptr())
+    r.render_device_rows(mats[f], W, H, world, phase, out.data_ptr())
 r.finish()
 print(r.timing(), r.stats())
