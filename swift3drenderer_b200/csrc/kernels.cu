@@ -493,164 +493,176 @@ __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, ui
 // publishes depth << 32 | ~order keys with fire-and-forget 64-bit atomicMax.  No setup record, no attribute
 // gather, no bin entry is ever written for such a triangle; the pixels it wins are shaded from the raw scene
 // (shade_tiles).  Everything else (straddling or larger triangles) is appended to the work list of K2b.
+constexpr uint32_t CLS_PER_CTA = 1024;   // triangles per classify CTA (four per thread)
+
 struct WalkShared {
-    float par[12][256];        // by owner thread.  classify: corners (x, y, z) x 3 + area;  setup pass: ws[3], dx[3], dy[3], rz[3]
-    float ck[9][256];          // row-start weights at box rows 4, 8, 12 (checkpoints: a row item replays at most 3 row steps)
-    uint32_t xy[256];          // xmin | ymin << 16
-    uint32_t bwrows[256];      // xmax - xmin | owned-row mask << 16
-    uint16_t items[256 * SMALL_MAX];   // owner thread | row << 8, grouped by box-width class
-    uint8_t surv[256];         // owner threads of the boxes to walk (compacted)
-    uint32_t n_surv;
-    uint32_t cls_count[4];     // row items per box-width class (width 1-4, 5-8, 9-12, 13-16 pixels)
+    uint32_t cand[CLS_PER_CTA];        // triangles that passed the front tests (| ITEM_STRADDLE)
+    float par[12][256];                // per parked box: ws[3], dx[3], dy[3], rz[3]  (SoA: conflict-free)
+    float ck[9][256];                  // row-start weights at box rows 4, 8, 12 (checkpoints: a row item replays at most 3 row steps)
+    uint32_t xy[256];                  // xmin | ymin << 16
+    uint32_t bwrows[256];              // xmax - xmin | owned-row mask << 16
+    uint32_t tri[256];                 // order key of the box's triangle
+    uint16_t items[256 * SMALL_MAX];   // parked slot | row << 8, grouped by box-width class
+    uint32_t n_cand;
+    uint32_t cls_count[4];             // row items per box-width class (width 1-4, 5-8, 9-12, 13-16 pixels)
+    uint32_t stats[4];                 // near-rejected, clipped, walked here, culled
+    uint32_t work_base;
 };
 
 __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
-    __shared__ SetupShared sh;
     __shared__ WalkShared wsh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
-    if (tid == 0) { sh.count = 0; wsh.n_surv = 0; }
-    if (tid < 4) { sh.stats[tid] = 0; wsh.cls_count[tid] = 0; }
+    if (tid == 0) { wsh.n_cand = 0; }
+    if (tid < 4) { wsh.stats[tid] = 0; }
     __syncthreads();
+    const float4 *rv = f.rv + (size_t)view * f.Vpad;
+    uint32_t n_near = 0, n_clip = 0, n_cull = 0, n_direct = 0;   // per-thread statistics, reduced once at the end
 
-    const uint32_t t = blockIdx.x * 256u + tid;
-    uint32_t cls = 0;  // 0 rejected, 1 work item (recorded setup), 2 work item that straddles the near plane, 3 walked here
-    bool near_rej = false, culled = false;
-    if (t < f.T) {
-        const float4 *rv = f.rv + (size_t)view * f.Vpad;
-        const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
-        if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
-            near_rej = true;
-        } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
-            cls = 2;
-        } else {
-            // the order of the three culls does not matter for the result (all are 'continue's before any side
-            // effect, render.cpp:311-317); the area test removes ~80 % of a dense field, so it goes first
-            const float area = edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y);
-            culled = true;
-            if (!(area < 10)) {
+    // ---- front: near reject, straddle, area cull, screen/band reject (render.cpp:306-317), 4 triangles per thread ----
+#pragma unroll 2
+    for (uint32_t pass = 0; pass < CLS_PER_CTA / 256u; pass++) {
+        const uint32_t t = blockIdx.x * CLS_PER_CTA + pass * 256u + tid;
+        uint32_t cand = 0;   // 1 candidate, 2 candidate that straddles the near plane
+        if (t < f.T) {
+            const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
+            if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
+                n_near++;
+            } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
+                cand = 2; n_clip++;
+            } else {
+                // the order of the three culls does not matter for the result (all are 'continue's before any side
+                // effect, render.cpp:311-317); the area test removes ~80 % of a dense field, so it goes first
                 const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
                 const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
-                const bool off = (max_x < 0 || max_y < 0) || (min_x >= f.fw || min_y >= f.fh);
                 // screen partition: a triangle whose rows cannot meet this submission's rows contributes nothing
                 // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
-                if (!off && !(max_y < f.band_lo || min_y >= f.band_hi)) {
-                    const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
-                    const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
-                    const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
-                    if (f.direct_small && is_small_bbox(xmin, xmax, ymin, ymax)) {
-                        // box rows this submission owns (bit r: row ymin + r).  Under 16 rows meet at most two tile rows.
-                        const uint32_t lo = ylo - ymin, hi = yhi - ymin;
-                        uint32_t rows = (2u << hi) - (1u << lo);
-                        if (f.row_stride != 1u) {
-                            const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
-                            const uint32_t split = (a0 + 1u) * TILE_H - ymin;   // first box row inside tile row a0 + 1
-                            const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
-                            rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
-                        }
-                        if (rows) {   // park the corners; the setup itself runs densely packed below
-                            culled = false;
-                            cls = 3;
-                            wsh.par[0][tid] = r0.x; wsh.par[1][tid] = r0.y; wsh.par[2][tid] = r0.z;
-                            wsh.par[3][tid] = r1.x; wsh.par[4][tid] = r1.y; wsh.par[5][tid] = r1.z;
-                            wsh.par[6][tid] = r2.x; wsh.par[7][tid] = r2.y; wsh.par[8][tid] = r2.z;
-                            wsh.par[9][tid] = area;
-                            wsh.xy[tid] = xmin | (ymin << 16);
-                            wsh.bwrows[tid] = (xmax - xmin) | (rows << 16);
-                        }
-                    } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
-                        culled = false;
-                        cls = 1;
+                const bool off = (max_x < 0 || max_y < f.band_lo) || (min_x >= f.fw || min_y >= f.band_hi);
+                if (edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10 || off) { n_cull++; } else { cand = 1; }
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
+        uint32_t base = 0;
+        if (lane == 0 && m) { base = atomicAdd(&wsh.n_cand, __popc(m)); }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (cand) { wsh.cand[base + __popc(m & ((1u << lane) - 1u))] = t | (cand == 2 ? ITEM_STRADDLE : 0u); }
+    }
+    __syncthreads();
+    const uint32_t n_cand = wsh.n_cand;
+
+    // ---- candidates, densely packed, 256 per round: exact boxes, row ownership, coverage setup, walk ------------
+    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
+    for (uint32_t cbase = 0; cbase < n_cand; cbase += 256u) {
+        if (tid < 4) { wsh.cls_count[tid] = 0; }
+        __syncthreads();
+        uint32_t route = 0;   // 1 work item for K2b, 3 walked here
+        uint32_t item = 0, my_cls = 0, my_rows = 0, my_off = 0;
+        if (cbase + tid < n_cand) {
+            item = wsh.cand[cbase + tid];
+            if (item & ITEM_STRADDLE) {
+                route = 1;
+            } else {
+                const float4 r0 = rv[__ldg(f.vi0 + item)], r1 = rv[__ldg(f.vi1 + item)], r2 = rv[__ldg(f.vi2 + item)];
+                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+                const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
+                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
+                if (f.direct_small && is_small_bbox(xmin, xmax, ymin, ymax)) {
+                    // box rows this submission owns (bit r: row ymin + r).  Under 16 rows meet at most two tile rows.
+                    const uint32_t lo = ylo - ymin, hi = yhi - ymin;
+                    uint32_t rows = (2u << hi) - (1u << lo);
+                    if (f.row_stride != 1u) {
+                        const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
+                        const uint32_t split = (a0 + 1u) * TILE_H - ymin;   // first box row inside tile row a0 + 1
+                        const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
+                        rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
                     }
+                    if (rows) {
+                        route = 3; n_direct++;
+                        VisCore vc;
+                        vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
+                                 edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y), xmin, ymin, vc);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            wsh.par[k][tid] = vc.ws[k]; wsh.par[3 + k][tid] = vc.dx[k]; wsh.par[6 + k][tid] = vc.dy[k]; wsh.par[9 + k][tid] = vc.rz[k];
+                        }
+                        wsh.xy[tid] = xmin | (ymin << 16);
+                        wsh.bwrows[tid] = (xmax - xmin) | (rows << 16);
+                        wsh.tri[tid] = item;
+                        float w0 = vc.ws[0], w1 = vc.ws[1], w2 = vc.ws[2];
+                        const uint32_t top = 31u - (uint32_t)__clz((int)rows);   // last owned box row
+                        for (uint32_t r = 1; r <= (top & ~3u); r++) {          // render.cpp:378, row by row; keep rows 4, 8, 12
+                            w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
+                            if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
+                        }
+                        my_rows = rows;
+                        my_cls = (xmax - xmin) >> 2;
+                        my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(rows));
+                    } else {
+                        n_cull++;
+                    }
+                } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
+                    route = 1;
+                } else {
+                    n_cull++;
                 }
             }
         }
-    }
-    {   // warp-ballot compaction: work items for K2b, boxes to walk here
-        const uint32_t m_near = __ballot_sync(0xFFFFFFFFu, near_rej), m_cull = __ballot_sync(0xFFFFFFFFu, culled);
-        const uint32_t m_clip = __ballot_sync(0xFFFFFFFFu, cls == 2), m_work = __ballot_sync(0xFFFFFFFFu, cls == 1 || cls == 2);
-        const uint32_t m_direct = __ballot_sync(0xFFFFFFFFu, cls == 3);
-        uint32_t base = 0, dbase = 0;
-        if (lane == 0) {
-            if (m_near) { atomicAdd(&sh.stats[0], __popc(m_near)); }
-            if (m_clip) { atomicAdd(&sh.stats[1], __popc(m_clip)); }
-            if (m_cull) { atomicAdd(&sh.stats[3], __popc(m_cull)); }
-            if (m_work) { base = atomicAdd(&sh.count, __popc(m_work)); }
-            if (m_direct) { dbase = atomicAdd(&wsh.n_surv, __popc(m_direct)); }
+        {   // work items for K2b: one global atomic per warp
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, route == 1);
+            uint32_t base = 0;
+            if (lane == 0 && m) { base = atomicAdd(f.counters + view * C_COUNT + C_WORK, __popc(m)); }
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (route == 1) { f.worklist[(size_t)view * f.T + base + __popc(m & ((1u << lane) - 1u))] = item; }
         }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        dbase = __shfl_sync(0xFFFFFFFFu, dbase, 0);
-        const uint32_t below = (1u << lane) - 1u;
-        if (cls == 1 || cls == 2) { sh.list[base + __popc(m_work & below)] = t | (cls == 2 ? ITEM_STRADDLE : 0u); }
-        if (cls == 3) { wsh.surv[dbase + __popc(m_direct & below)] = (uint8_t)tid; }
+        __syncthreads();
+        const uint32_t c0 = wsh.cls_count[0], c1 = wsh.cls_count[1], c2 = wsh.cls_count[2], n_items = c0 + c1 + c2 + wsh.cls_count[3];
+        if (route == 3) {
+            uint32_t pos = my_off + (my_cls > 0u ? c0 : 0u) + (my_cls > 1u ? c1 : 0u) + (my_cls > 2u ? c2 : 0u);
+            while (my_rows) {   // one work item per owned box row
+                const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
+                my_rows &= my_rows - 1u;
+                wsh.items[pos++] = (uint16_t)(tid | (r << 8));
+            }
+        }
+        __syncthreads();
+        // the direct walk: one (triangle, row) item per thread and pass
+        for (uint32_t i = tid; i < n_items; i += 256u) {
+            const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
+            float w0, w1, w2;
+            if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
+            else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
+            const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
+            for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+            const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
+            const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
+            const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
+            unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+            const unsigned long long key_lo = (unsigned long long)(~wsh.tri[ow]);
+            const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
+            for (uint32_t x = 0; x <= bw; x++) {
+                const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
+                // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+                if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+            }
+        }
+        __syncthreads();   // parked boxes and items are rewritten by the next round
     }
-    __syncthreads();
-    const uint32_t count = sh.count, n_surv = wsh.n_surv;
-    if (tid == 0 && count) { sh.base = atomicAdd(f.counters + view * C_COUNT + C_WORK, count); }
-    if (tid == 0 && sh.stats[0]) { atomicAdd(f.counters + view * C_COUNT + C_NEAR, sh.stats[0]); }
-    if (tid == 1 && sh.stats[1]) { atomicAdd(f.counters + view * C_COUNT + C_CLIPPED, sh.stats[1]); }
-    if (tid == 2 && n_surv) { atomicAdd(f.counters + view * C_COUNT + C_DIRECT, n_surv); }
-    if (tid == 3 && sh.stats[3]) { atomicAdd(f.counters + view * C_COUNT + C_CULLED, sh.stats[3]); }
-    if (count == 0 && n_surv == 0) { return; }
 
-    // ---- coverage setup of the boxes to walk, one per lane, densely packed --------------------------
-    uint32_t o = 0, my_cls = 0, my_rows = 0, my_off = 0;
-    if (tid < n_surv) {
-        o = wsh.surv[tid];
-        const float3 a = make_float3(wsh.par[0][o], wsh.par[1][o], wsh.par[2][o]);
-        const float3 b = make_float3(wsh.par[3][o], wsh.par[4][o], wsh.par[5][o]);
-        const float3 c = make_float3(wsh.par[6][o], wsh.par[7][o], wsh.par[8][o]);
-        const uint32_t xy = wsh.xy[o], br = wsh.bwrows[o];
-        VisCore vc;
-        vis_core(a, b, c, wsh.par[9][o], xy & 0xFFFFu, xy >> 16, vc);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            wsh.par[k][o] = vc.ws[k]; wsh.par[3 + k][o] = vc.dx[k]; wsh.par[6 + k][o] = vc.dy[k]; wsh.par[9 + k][o] = vc.rz[k];
-        }
-        my_rows = br >> 16;
-        float w0 = vc.ws[0], w1 = vc.ws[1], w2 = vc.ws[2];
-        const uint32_t top = 31u - (uint32_t)__clz((int)my_rows);   // last owned box row
-        for (uint32_t r = 1; r <= (top & ~3u); r++) {              // render.cpp:378, row by row; keep rows 4, 8, 12
-            w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
-            if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][o] = w0; wsh.ck[3 * g + 1][o] = w1; wsh.ck[3 * g + 2][o] = w2; }
-        }
-        my_cls = (br & 0xFFFFu) >> 2;
-        my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(my_rows));
+    // ---- statistics: one shared-memory atomic per warp, one global atomic per CTA and counter --------------------
+    n_near = __reduce_add_sync(0xFFFFFFFFu, n_near); n_clip = __reduce_add_sync(0xFFFFFFFFu, n_clip);
+    n_direct = __reduce_add_sync(0xFFFFFFFFu, n_direct); n_cull = __reduce_add_sync(0xFFFFFFFFu, n_cull);
+    if (lane == 0) {
+        if (n_near) { atomicAdd(&wsh.stats[0], n_near); }
+        if (n_clip) { atomicAdd(&wsh.stats[1], n_clip); }
+        if (n_direct) { atomicAdd(&wsh.stats[2], n_direct); }
+        if (n_cull) { atomicAdd(&wsh.stats[3], n_cull); }
     }
     __syncthreads();
-    if (tid < count) { f.worklist[(size_t)view * f.T + sh.base + tid] = sh.list[tid]; }
-    const uint32_t c0 = wsh.cls_count[0], c1 = wsh.cls_count[1], c2 = wsh.cls_count[2], n_items = c0 + c1 + c2 + wsh.cls_count[3];
-    if (tid < n_surv) {
-        uint32_t pos = my_off + (my_cls > 0u ? c0 : 0u) + (my_cls > 1u ? c1 : 0u) + (my_cls > 2u ? c2 : 0u);
-        while (my_rows) {   // one work item per owned box row
-            const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
-            my_rows &= my_rows - 1u;
-            wsh.items[pos++] = (uint16_t)(o | (r << 8));
-        }
-    }
-    __syncthreads();
-
-    // ---- the direct walk: one (triangle, row) item per thread and pass ------------------------------
-    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
-    for (uint32_t i = tid; i < n_items; i += 256u) {
-        const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
-        float w0, w1, w2;
-        if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
-        else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
-        const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
-        for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
-        const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
-        const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
-        const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
-        unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
-        const unsigned long long key_lo = (unsigned long long)(~(blockIdx.x * 256u + ow));
-        const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
-        for (uint32_t x = 0; x <= bw; x++) {
-            const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
-            const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
-            // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-            if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
-            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
-        }
+    if (tid < 4 && wsh.stats[tid]) {
+        atomicAdd(f.counters + view * C_COUNT + (tid == 2u ? (uint32_t)C_DIRECT : (uint32_t)C_NEAR + tid), wsh.stats[tid]);   // C_NEAR, C_CLIPPED, C_DIRECT, C_CULLED
     }
 }
 
@@ -1340,7 +1352,7 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
     frame_reset<<<dim3(ceil_div(max(f.n_tiles, (uint32_t)C_COUNT), 256), f.n_views), 256, 0, s>>>(f); launches++;
     vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
-    triangle_classify<<<dim3(max(1u, ceil_div(f.T, 256)), f.n_views), 256, 0, s>>>(f); launches++;
+    triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++;
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
     bin_big<<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
     frame_finalize<<<f.n_views, 256, 0, s>>>(f); launches++;
