@@ -1196,45 +1196,61 @@ __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame 
 }
 
 // Deferred shading of the general path (visibility buffer -> colour).  One CTA per 32 x 32 block of output pixels:
-//   1. read the block's depth keys, clear them for the next frame (so no separate reset pass exists) and compact the
-//      covered pixels into a list — background pixels cost nothing beyond this;
-//   2. one covered pixel per lane: the key's low word is ~order.  An unclipped triangle under 16 x 16 pixels has no
-//      record: its three corners are gathered and set up right here (the same make_setup the recorded path runs,
-//      hence the same bits) — attributes and normals of triangles that win no pixel are never read.  Recorded
-//      triangles are found through slot_of.  Small winners replay their own walk to the pixel (<= 15 + 15 true
-//      additions, render.cpp:374-379); big winners left their exact weights in pstate (tile_raster);
-//   3. the colour block goes out in 16-byte (or 12-byte, 24-bit transport) pieces.
-constexpr uint32_t SHADE_B = 32;   // block edge in pixels
+//   1. read the block's depth keys, clear them for the next frame (so no separate reset pass exists), compact the
+//      covered pixels into a list and find the block's distinct triangles with a shared-memory hash set (the key's
+//      low word is ~order) — background pixels cost nothing beyond this;
+//   2. one distinct triangle per lane: an unclipped triangle under 16 x 16 pixels has no record, so its three corners
+//      are gathered and set up right here (the same make_setup the recorded path runs, hence the same bits);
+//      attributes and normals of triangles that win no pixel are never read.  Recorded triangles are copied from
+//      their records (found through slot_of).  The setups are staged in shared memory, 256 per pass;
+//   3. one covered pixel per lane: small winners replay their own walk to the pixel (<= 15 + 15 true additions,
+//      render.cpp:374-379), big winners left their exact weights in pstate (tile_raster); shade (render.cpp:363-372);
+//   4. the colour block goes out in 16-byte (or 12-byte, 24-bit transport) pieces.
+constexpr uint32_t SHADE_B = 32;          // block edge in pixels
+constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_B;
+constexpr uint32_t SHADE_TAB = 2048;      // hash slots (load factor <= 0.5)
+constexpr uint32_t SHADE_TRIS = 256;      // triangle setups staged per pass (one per thread)
+constexpr uint32_t SHADE_WORDS = 47;      // words per staged setup (odd: distinct triangles fall into distinct banks)
+constexpr uint32_t SHADE_EMPTY = 0xFFFFFFFFu;
 
 struct ShadeShared {
     __align__(16) uint32_t colour[SHADE_B][SHADE_B];
-    uint32_t order[SHADE_B * SHADE_B];
-    uint16_t pix[SHADE_B * SHADE_B];
-    uint32_t count;
+    uint32_t tab[SHADE_TAB];              // hash set of orders; after numbering: slot -> triangle number
+    uint32_t tri_order[SHADE_PIX];        // triangle number -> order
+    uint16_t pix[SHADE_PIX];              // covered pixel list: position in the block ...
+    uint16_t pslot[SHADE_PIX];            // ... and its triangle's hash slot
+    uint32_t setup[SHADE_TRIS][SHADE_WORDS];   // ws[3] dx[3] dy[3] rz[3] | xmin|ymin<<16 | big | SetupShade[32]
+    uint32_t count, n_tri;
 };
 
-__global__ void __launch_bounds__(256) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
-    __shared__ ShadeShared sh;
+__global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ShadeShared &sh = *reinterpret_cast<ShadeShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tid = threadIdx.x, lane = lane_id();
     const uint32_t bx0 = blockIdx.x * SHADE_B, br0 = blockIdx.y * SHADE_B;       // block origin: pixel column, row within [row0, row0 + nrows)
     const bool broken = f.counters[view * C_COUNT + C_OVERFLOW] != 0;            // incomplete lists: the host renders the frame again
-    if (tid == 0) { sh.count = 0; }
-    __syncthreads();
+    if (tid == 0) { sh.count = 0; sh.n_tri = 0; }
     const size_t vbase = (size_t)view * f.out_view_stride;
-    {   // ---- 1. keys -> compacted list of covered pixels -------------------------------------------
-        const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u;   // this thread's 4 pixels: block row pr, columns pc .. pc + 3
-        uint32_t ord[4] = {0u, 0u, 0u, 0u}, mask = 0;
-        if (br0 + pr < nrows) {
-            unsigned long long *kp = f.keys + vbase + (size_t)(row0 + br0 + pr) * f.W + bx0 + pc;
+    // ---- 1. keys -> compacted list of covered pixels + distinct triangles ---------------------------
+    const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u;   // this thread's 4 pixels: block row pr, columns pc .. pc + 3
+    uint32_t ord[4] = {0u, 0u, 0u, 0u}, mask = 0;
+    if (br0 + pr < nrows) {
+        unsigned long long *kp = f.keys + vbase + (size_t)(row0 + br0 + pr) * f.W + bx0 + pc;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (bx0 + pc + k < f.W) {
-                    const unsigned long long key = kp[k];
-                    if (key != 0ull) { kp[k] = 0ull; ord[k] = ~(uint32_t)key; mask |= 1u << k; }
-                }
+        for (int k = 0; k < 4; k++) {
+            if (bx0 + pc + k < f.W) {
+                const unsigned long long key = kp[k];
+                if (key != 0ull) { kp[k] = 0ull; ord[k] = ~(uint32_t)key; mask |= 1u << k; }
             }
         }
-        *reinterpret_cast<uint4 *>(&sh.colour[pr][pc]) = make_uint4(kBackground, kBackground, kBackground, kBackground);
+    }
+    if (broken) { mask = 0; }
+    *reinterpret_cast<uint4 *>(&sh.colour[pr][pc]) = make_uint4(kBackground, kBackground, kBackground, kBackground);
+    const bool any = __syncthreads_or(mask != 0u);
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < (int)(SHADE_TAB / 256u); k++) { sh.tab[k * 256u + tid] = SHADE_EMPTY; }
+        __syncthreads();
         // warp-aggregated append (keeps the row-major order inside a warp: neighbours share triangles)
         const uint32_t n = __popc(mask);
         uint32_t incl = n;
@@ -1244,70 +1260,116 @@ __global__ void __launch_bounds__(256) shade_tiles(const __grid_constant__ Frame
         uint32_t base = 0;
         if (lane == 31 && total) { base = atomicAdd(&sh.count, total); }
         uint32_t j = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - n;
+        uint32_t last_order = SHADE_EMPTY, last_slot = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (mask & (1u << k)) { sh.order[j] = ord[k]; sh.pix[j] = (uint16_t)(pr * SHADE_B + pc + k); j++; }
+            if (mask & (1u << k)) {
+                uint32_t h = last_slot;
+                if (ord[k] != last_order) {   // insert into the hash set (linear probing)
+                    h = (ord[k] * 2654435761u) >> 21;
+                    while (true) {
+                        const uint32_t prev = atomicCAS(&sh.tab[h], SHADE_EMPTY, ord[k]);
+                        if (prev == SHADE_EMPTY || prev == ord[k]) { break; }
+                        h = (h + 1u) & (SHADE_TAB - 1u);
+                    }
+                    last_order = ord[k]; last_slot = h;
+                }
+                sh.pix[j] = (uint16_t)(pr * SHADE_B + pc + k); sh.pslot[j] = (uint16_t)h; j++;
+            }
         }
-    }
-    __syncthreads();
-    // ---- 2. shade, one covered pixel per lane -----------------------------------------------------
-    const uint32_t count = broken ? 0u : sh.count;
-    const Cam cam = load_cam(f.cams + 12 * view);
+        __syncthreads();
+        // number the distinct triangles
+#pragma unroll
+        for (int k = 0; k < (int)(SHADE_TAB / 256u); k++) {
+            const uint32_t slot = k * 256u + tid, o = sh.tab[slot];
+            if (o != SHADE_EMPTY) { const uint32_t id = atomicAdd(&sh.n_tri, 1u); sh.tri_order[id] = o; sh.tab[slot] = id; }
+        }
+        __syncthreads();
+        const uint32_t count = sh.count, n_tri = sh.n_tri;
+        const Cam cam = load_cam(f.cams + 12 * view);
 #pragma unroll 1
-    for (uint32_t i = tid; i < count; i += 256u) {
-        const uint32_t order = sh.order[i], p = sh.pix[i], pr = p / SHADE_B, pc = p % SHADE_B;
-        const uint32_t px = bx0 + pc, py = pixel_y(f, row0 + br0 + pr);
-        uint32_t rgb;
-        bool direct = false;
-        uint32_t i0 = 0, i1 = 0, i2 = 0;
-        if (f.direct_small && order < f.T) {
-            // the classify kernel's own routing rule: not straddling the near plane, screen box under 16 x 16
-            i0 = __ldg(f.vi0 + order); i1 = __ldg(f.vi1 + order); i2 = __ldg(f.vi2 + order);
-            const float4 *rv = f.rv + (size_t)view * f.Vpad;
-            const float4 r0 = rv[i0], r1 = rv[i1], r2 = rv[i2];
-            if (!(fminf(fminf(r0.z, r1.z), r2.z) < kNear)) {
-                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
-                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
-                const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
-                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
-                direct = is_small_bbox(xmin, xmax, ymin, ymax);
+        for (uint32_t tb = 0; tb < n_tri; tb += SHADE_TRIS) {
+            // ---- 2. setups of this pass's triangles ------------------------------------------------
+            if (tb + tid < n_tri) {
+                const uint32_t order = sh.tri_order[tb + tid];
+                uint32_t *dst = sh.setup[tid];
+                bool direct = false;
+                Corner d0, d1, d2;
+                if (f.direct_small && order < f.T) {
+                    // all gathers of the triangle are issued before anything is decided: two dependent round trips
+                    // (indices, then vertices + attributes) instead of three
+                    const uint32_t i0 = __ldg(f.vi0 + order), i1 = __ldg(f.vi1 + order), i2 = __ldg(f.vi2 + order);
+                    const uint32_t a0 = __ldg(f.ai0 + order), a1 = __ldg(f.ai1 + order), a2 = __ldg(f.ai2 + order);
+                    d0 = gather_corner(f, cam, view, i0, a0); d1 = gather_corner(f, cam, view, i1, a1); d2 = gather_corner(f, cam, view, i2, a2);
+                    // the classify kernel's own routing rule: not straddling the near plane, screen box under 16 x 16
+                    if (!(fminf(fminf(d0.rv.z, d1.rv.z), d2.rv.z) < kNear)) {
+                        const float max_x = fmaxf(fmaxf(d0.rv.x, d1.rv.x), d2.rv.x), max_y = fmaxf(fmaxf(d0.rv.y, d1.rv.y), d2.rv.y);
+                        const float min_x = fminf(fminf(d0.rv.x, d1.rv.x), d2.rv.x), min_y = fminf(fminf(d0.rv.y, d1.rv.y), d2.rv.y);
+                        const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
+                        const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
+                        direct = is_small_bbox(xmin, xmax, ymin, ymax);
+                    }
+                }
+                if (direct) {
+                    SetupVis v;
+                    SetupShade s;
+                    make_setup(d0, d1, d2, order, f, v, s);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        dst[k] = __float_as_uint(v.wstart[k]); dst[3 + k] = __float_as_uint(v.dx[k]);
+                        dst[6 + k] = __float_as_uint(v.dy[k]); dst[9 + k] = __float_as_uint(v.rvz[k]);
+                    }
+                    dst[12] = (uint32_t)v.xmin | ((uint32_t)v.ymin << 16);
+                    dst[13] = 0u;
+                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(&s);
+#pragma unroll
+                    for (int k = 0; k < 32; k++) { dst[14 + k] = sw[k]; }
+                } else {
+                    const uint32_t slot = f.slot_of[(size_t)view * 2u * f.T + order];
+                    const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+                    const uint4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+                    const uint32_t xmin = q0.x & 0xFFFFu, xmax = q0.x >> 16, ymin = q0.y & 0xFFFFu, ymax = q0.y >> 16;
+                    dst[0] = q1.x; dst[1] = q1.y; dst[2] = q1.z; dst[3] = q1.w; dst[4] = q2.x; dst[5] = q2.y;
+                    dst[6] = q2.z; dst[7] = q2.w; dst[8] = q3.x; dst[9] = q3.y; dst[10] = q3.z; dst[11] = q3.w;
+                    dst[12] = xmin | (ymin << 16);
+                    dst[13] = is_small_bbox(xmin, xmax, ymin, ymax) ? 0u : 1u;
+                    const uint4 *sp = reinterpret_cast<const uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { const uint4 q = sp[k]; dst[14 + 4 * k] = q.x; dst[15 + 4 * k] = q.y; dst[16 + 4 * k] = q.z; dst[17 + 4 * k] = q.w; }
+                }
             }
-        }
-        if (direct) {
-            const Corner d0 = gather_corner(f, cam, view, i0, __ldg(f.ai0 + order));
-            const Corner d1 = gather_corner(f, cam, view, i1, __ldg(f.ai1 + order));
-            const Corner d2 = gather_corner(f, cam, view, i2, __ldg(f.ai2 + order));
-            SetupVis v;
-            SetupShade s;
-            make_setup(d0, d1, d2, order, f, v, s);
-            float w0 = v.wstart[0], w1 = v.wstart[1], w2 = v.wstart[2];
-            for (uint32_t k = v.ymin; k < py; k++) { w0 = add_rn(w0, v.dy[0]); w1 = add_rn(w1, v.dy[1]); w2 = add_rn(w2, v.dy[2]); }   // render.cpp:378
-            for (uint32_t k = v.xmin; k < px; k++) { w0 = add_rn(w0, v.dx[0]); w1 = add_rn(w1, v.dx[1]); w2 = add_rn(w2, v.dx[2]); }   // render.cpp:374
-            rgb = shade_math(f, v.rvz[0], v.rvz[1], v.rvz[2], s, w0, w1, w2);
-        } else {
-            const uint32_t slot = f.slot_of[(size_t)view * 2u * f.T + order];
-            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
-            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
-            float w0, w1, w2;
-            if (is_small_bbox(xmin, xmax, ymin, ymax)) {
-                const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
-                const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
-                const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
-                const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
-                w0 = __uint_as_float(q1.x); w1 = __uint_as_float(q1.y); w2 = __uint_as_float(q1.z);
-                for (uint32_t k = ymin; k < py; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
-                for (uint32_t k = xmin; k < px; k++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
-            } else {
-                const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + pr) * f.W + px];
-                w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);
+            __syncthreads();
+            // ---- 3. shade, one covered pixel per lane ---------------------------------------------
+#pragma unroll 1
+            for (uint32_t i = tid; i < count; i += 256u) {
+                const uint32_t id = sh.tab[sh.pslot[i]] - tb;
+                if (id >= SHADE_TRIS) { continue; }
+                const uint32_t *src = sh.setup[id];
+                const uint32_t p = sh.pix[i], qr = p / SHADE_B, qc = p % SHADE_B;
+                const uint32_t px = bx0 + qc, py = pixel_y(f, row0 + br0 + qr);
+                float w0, w1, w2;
+                if (src[13] == 0u) {
+                    const uint32_t xy = src[12];
+                    w0 = __uint_as_float(src[0]); w1 = __uint_as_float(src[1]); w2 = __uint_as_float(src[2]);
+                    const float dy0 = __uint_as_float(src[6]), dy1 = __uint_as_float(src[7]), dy2 = __uint_as_float(src[8]);
+                    for (uint32_t k = xy >> 16; k < py; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }       // render.cpp:378
+                    const float dx0 = __uint_as_float(src[3]), dx1 = __uint_as_float(src[4]), dx2 = __uint_as_float(src[5]);
+                    for (uint32_t k = xy & 0xFFFFu; k < px; k++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
+                } else {
+                    const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + qr) * f.W + px];
+                    w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);
+                }
+                SetupShade s;
+                uint32_t *sw = reinterpret_cast<uint32_t *>(&s);
+#pragma unroll
+                for (int k = 0; k < 32; k++) { sw[k] = src[14 + k]; }
+                sh.colour[qr][qc] = shade_math(f, __uint_as_float(src[9]), __uint_as_float(src[10]), __uint_as_float(src[11]), s, w0, w1, w2);
             }
-            rgb = shade_pixel(f, view, slot, w0, w1, w2);
+            __syncthreads();
         }
-        sh.colour[pr][pc] = rgb;
     }
-    __syncthreads();
-    // ---- 3. write-out: 4 consecutive pixels per thread --------------------------------------------
-    const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u, x0 = bx0 + pc;
+    // ---- 4. write-out: 4 consecutive pixels per thread --------------------------------------------
+    const uint32_t x0 = bx0 + pc;
     if (br0 + pr >= nrows || x0 >= f.W) { return; }
     const uint4 c = *reinterpret_cast<const uint4 *>(&sh.colour[pr][pc]);
     const uint32_t rgb[4] = {c.x, c.y, c.z, c.w};
@@ -1342,7 +1404,14 @@ cudaError_t configure_kernels() {
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     e = cudaFuncSetAttribute(tile_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared));
     if (e != cudaSuccess) { return e; }
-    return cudaFuncSetAttribute(tile_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(tile_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
+    // both keep ~40 KB of static shared memory per CTA: without the carve-out hint the driver may leave too little for 4-6 CTAs per SM
+    e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
+    return cudaFuncSetAttribute(triangle_classify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -1375,7 +1444,7 @@ int launch_raster(const Frame &f, cudaStream_t s) {
         row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
     }
     if (nrows) {
-        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, 0, s>>>(f, row0, nrows);
+        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, sizeof(ShadeShared), s>>>(f, row0, nrows);
     }
     return 2;
 }
