@@ -1,6 +1,5 @@
 // kernels.cu — hand-written sm_100a kernels of the frame pipeline.
 //
-//   frame_reset        zero per-view counters and tile histograms
 //   vertex_stage       K1  model/view/projection over planar float4 position streams   (render.cpp:285-289)
 //   triangle_setup     K2  gather, near reject, near-plane clip (0/1/2 out), cull, setup,
 //                          warp-ballot + block-scan compaction                          (render.cpp:297-359, 212-262)
@@ -66,10 +65,6 @@ __device__ __forceinline__ void reset_body(const Frame &f, uint32_t view, uint32
     for (uint32_t t = i; t < f.n_tiles; t += stride) { f.tile_count[view * f.tile_stride + t] = 0; }
 }
 
-__global__ void __launch_bounds__(256) frame_reset(const __grid_constant__ Frame f) {
-    reset_body(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1 — vertex stage: 4 vertices per thread, float4 loads of the planar streams, float4 stores.
 // ------------------------------------------------------------------------------------------------
@@ -88,6 +83,8 @@ __device__ __forceinline__ void vertex_body(const Frame &f, const Cam &cam, uint
 }
 
 __global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Frame f) {
+    // first kernel of a frame: also zeroes the per-view counters and tile histograms (no separate reset launch)
+    reset_body(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     if (i4 >= f.Vpad) { return; }
     vertex_body(f, load_cam(f.cams + 12 * blockIdx.y), blockIdx.y, i4);
@@ -260,7 +257,7 @@ __device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, u
 
 // Single-pass binning: every tile owns a fixed-capacity list (tile_cap slots); one atomic reserves the
 // position.  Lists are unordered (the depth keys carry the order).  Overflowing tiles are detected by
-// frame_finalize; the host regrows tile_cap and renders the frame again.
+// post_setup's closing step; the host regrows tile_cap and renders the frame again.
 __device__ __forceinline__ void bin_one(const Frame &f, uint32_t view, uint32_t tile, uint32_t slot) {
     const uint32_t pos = atomicAdd(f.tile_count + view * f.tile_stride + tile, 1u);
     if (pos < f.tile_cap) { f.entries[((size_t)view * f.tile_stride + tile) * f.tile_cap + pos] = slot; }
@@ -687,8 +684,7 @@ __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__
 // tile can restore the reference's processing order with one sort.
 // ------------------------------------------------------------------------------------------------
 // Triangles over more than BIG_TILES tiles: one CTA per triangle, threads over its tiles.
-__global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y;
+__device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view) {
     const uint32_t n = min(f.counters[view * C_COUNT + C_BIG], f.big_cap);
     for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
         const uint32_t slot = f.big_list[(size_t)view * f.big_cap + b];
@@ -708,28 +704,26 @@ __global__ void __launch_bounds__(256) bin_big(const __grid_constant__ Frame f) 
 }
 
 // After all binning: total and longest tile list, overflow bits, and the cross-submission record the host
-// reads back (one CTA per view).
-__global__ void __launch_bounds__(256) frame_finalize(const __grid_constant__ Frame f) {
-    __shared__ uint32_t s_sum, s_max;
-    const uint32_t view = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) { s_sum = 0; s_max = 0; }
-    __syncthreads();
+// reads back (one CTA per view: the last one to finish post_setup).
+__device__ __forceinline__ void finalize_body(const Frame &f, uint32_t view, uint32_t *s_sum, uint32_t *s_max) {
+    const uint32_t tid = threadIdx.x;
     uint32_t sum = 0, mx = 0;
     for (uint32_t t = tid; t < f.n_tiles; t += 256u) {
-        const uint32_t c = f.tile_count[view * f.tile_stride + t];
+        const uint32_t c = __ldcg(f.tile_count + view * f.tile_stride + t);
         sum += c; mx = max(mx, c);
     }
-    atomicAdd(&s_sum, sum);
-    atomicMax(&s_max, mx);
+    atomicAdd(s_sum, sum);
+    atomicMax(s_max, mx);
     __syncthreads();
     if (tid == 0) {
         uint32_t *c = f.counters + view * C_COUNT;
-        c[C_ENTRIES] = s_sum;
-        if (s_max > f.tile_cap) { c[C_OVERFLOW] |= 2u; }
-        if (c[C_OVERFLOW]) { atomicOr(f.sticky + 0, c[C_OVERFLOW]); }
-        atomicMax(f.sticky + 1, c[C_SETUPS]);
-        atomicMax(f.sticky + 2, s_max);
-        atomicMax(f.sticky + 3, c[C_BIG]);
+        const uint32_t overflow = __ldcg(c + C_OVERFLOW) | (*s_max > f.tile_cap ? 2u : 0u);
+        c[C_ENTRIES] = *s_sum;
+        c[C_OVERFLOW] = overflow;
+        if (overflow) { atomicOr(f.sticky + 0, overflow); }
+        atomicMax(f.sticky + 1, __ldcg(c + C_SETUPS));
+        atomicMax(f.sticky + 2, *s_max);
+        atomicMax(f.sticky + 3, __ldcg(c + C_BIG));
     }
 }
 
@@ -896,6 +890,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     // A capacity overflow anywhere upstream makes the lists incomplete: the host regrows the
     // buffers and renders the frame again, so this launch only has to stay in bounds.
     if (f.counters[view * C_COUNT + C_OVERFLOW] != 0) { return; }
+    // general path: a tile no recorded triangle was binned into has nothing to add to the visibility buffer
+    if (!f.direct_bin && f.tile_count[view * f.tile_stride + tile] == 0u) { return; }
 
     // ---- this tile's triangle list (unordered: depth keys carry the order) ---------------------
     if (tid == 0) { sh.n_list = 0; sh.n_big = 0; sh.any_small = 0; }
@@ -1158,8 +1154,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 // one thread over its whole bounding box (no tiles, no binning, no duplication), publishing 64-bit depth keys
 // with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame f) {
+__global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame f) {
+    __shared__ uint32_t s_sum, s_max, s_last;
     const uint32_t view = blockIdx.y;
+    bin_big_body(f, view);   // K3 for the triangles the setup kernel left to a whole CTA
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
@@ -1192,6 +1190,16 @@ __global__ void __launch_bounds__(256) small_flat(const __grid_constant__ Frame 
             }
             wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
         }
+    }
+    // the last CTA of the view to get here closes the frame's geometry (tile statistics, overflow record)
+    if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) { s_last = atomicAdd(f.counters + view * C_COUNT + C_DONE, 1u) == gridDim.x - 1u ? 1u : 0u; }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        finalize_body(f, view, &s_sum, &s_max);
     }
 }
 
@@ -1419,15 +1427,12 @@ static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b
 int launch_geometry(const Frame &f, cudaStream_t s) {
     int launches = 0;
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
-    frame_reset<<<dim3(ceil_div(max(f.n_tiles, (uint32_t)C_COUNT), 256), f.n_views), 256, 0, s>>>(f); launches++;
-    vertex_stage<<<dim3(ceil_div(f.Vpad / 4, 256), f.n_views), 256, 0, s>>>(f); launches++;
+    vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++;
     triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++;
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
-    bin_big<<<dim3(min(persistent, f.big_cap), f.n_views), 256, 0, s>>>(f); launches++;
-    frame_finalize<<<f.n_views, 256, 0, s>>>(f); launches++;
-    // recorded small triangles (clipped or spawned ones): flat visibility pass over the survivor list
-    const uint32_t flat_blocks = min(persistent * 2u, max(1u, ceil_div(min(2u * f.T, f.setup_cap), 256)));
-    small_flat<<<dim3(flat_blocks, f.n_views), 256, 0, s>>>(f); launches++;
+    // cooperative binning of the big triangles, flat visibility pass over the recorded small ones (clipped or spawned),
+    // and — by the last CTA to finish — the frame's tile statistics and overflow record
+    post_setup<<<dim3(persistent, f.n_views), 256, 0, s>>>(f); launches++;
     return launches;
 }
 

@@ -46,6 +46,7 @@ constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:9
 
 enum Counter : uint32_t {
     C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7, C_WORK = 8,
+    C_DONE = 10,     // CTAs of post_setup that have finished (the last one closes the frame's geometry)
     C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
     C_COUNT = 16
 };
