@@ -54,6 +54,14 @@ __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by,
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// n sequential additions of d onto s (render.cpp:374-379): true steps when the target is near, the exact
+// jump (walk.cuh) otherwise.  Both give the same bits; the loop is cheaper for short distances.
+__device__ __forceinline__ float walk_near(float s, float d, uint32_t n) {
+    if (n > 24u) { return walk_jump(s, d, n); }
+    for (uint32_t i = 0; i < n; i++) { s = add_rn(s, d); }
+    return s;
+}
+
 constexpr uint32_t WON = 0x80000000u;   // mark: this small triangle passed a depth pre-check in pass 1
 constexpr uint32_t SMALL_MAX = 16;      // triangles whose whole bbox is narrower and lower than this take the per-triangle path
 
@@ -307,6 +315,11 @@ __device__ __forceinline__ void store_setup(const Frame &f, uint32_t view, uint3
 __device__ __forceinline__ bool is_small_bbox(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
     return xmax - xmin < SMALL_MAX && ymax - ymin < SMALL_MAX;
 }
+// Recorded triangles whose box stays under flat_max pixels in both directions are walked row by row straight into the
+// visibility buffer (post_setup); only larger ones pay for tile binning and the tile kernel.
+__device__ __forceinline__ bool is_flat_bbox(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
+    return xmax - xmin < f.flat_max && ymax - ymin < f.flat_max;
+}
 
 // K3 for one survivor, fused into setup: triangles over few tiles are binned right here (with the
 // conservative outside test), everything larger goes to the cooperative big list.
@@ -346,7 +359,7 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
         if (slot < f.setup_cap) {
             store_setup(f, view, slot, v, s);
             // general path: only triangles too large for the flat per-triangle walk are binned into tiles
-            if (!f.direct_bin && !is_small_bbox(v.xmin, v.xmax, v.ymin, v.ymax)) { count_tiles(f, view, slot, v); }
+            if (!f.direct_bin && !is_flat_bbox(f, v.xmin, v.xmax, v.ymin, v.ymax)) { count_tiles(f, view, slot, v); }
         } else {
             atomicOr(f.counters + view * C_COUNT + C_OVERFLOW, 1u);
         }
@@ -711,6 +724,14 @@ __device__ __forceinline__ void finalize_body(const Frame &f, uint32_t view, uin
     for (uint32_t t = tid; t < f.n_tiles; t += 256u) {
         const uint32_t c = __ldcg(f.tile_count + view * f.tile_stride + t);
         sum += c; mx = max(mx, c);
+        // the tile kernel's work queue: one item per RASTER_CHUNK entries of a non-empty bin list
+        const uint32_t n = min(c, f.tile_cap), chunks = (n + RASTER_CHUNK - 1u) / RASTER_CHUNK;
+        if (chunks) {
+            const uint32_t base = atomicAdd(f.counters + view * C_COUNT + C_ITEMS, chunks);
+            for (uint32_t k = 0; k < chunks && base + k < f.items_cap; k++) {
+                f.raster_items[(size_t)view * f.items_cap + base + k] = make_uint2(t, k * RASTER_CHUNK);
+            }
+        }
     }
     atomicAdd(s_sum, sum);
     atomicMax(s_max, mx);
@@ -760,6 +781,7 @@ struct RasterShared {
     union {                                               // 32 KB
         struct {
             float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];   // big triangles: exact weights at each 8-pixel segment start
+            float rowstart[BATCH][TILE_H][3];                 // ... and at the start of each of their rows (x = xmin)
             SetupVis batch[BATCH];
         } big;
         uint4 state[TILE_W * TILE_H];                     // later: per-pixel winners (w0, w1, w2, slot) for shading
@@ -876,10 +898,14 @@ __device__ __forceinline__ bool walk_small(const Frame &f, uint32_t view, uint32
     return won;
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
-    const uint32_t view = blockIdx.z, tile_x = blockIdx.x, tile_y = blockIdx.y + f.raster_row0, tid = threadIdx.x;
+// One tile (TILE_W x TILE_H pixels).  DIRECT (small scenes): the CTA collects the tile's triangles from the survivor
+// list itself, resolves visibility, shades and writes the colour tile.  !DIRECT (general path): the CTA resolves
+// entries [e0, e1) of the tile's bin list — recorded triangles too large for the flat walk — and merges its winners
+// into the visibility buffer with 64-bit atomicMax, so that a long list can be shared by several CTAs.
+template <bool DIRECT>
+__device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh, uint32_t view, uint32_t tile_x, uint32_t tile_y,
+                                                uint32_t e0, uint32_t e1) {
+    const uint32_t tid = threadIdx.x;
     const uint32_t tile = tile_y * f.tiles_x + tile_x;               // tile_y: local row index
     const uint32_t tile_a = abs_row(f, tile_y);                      // absolute tile row
     const uint32_t tx0 = tile_x * TILE_W, ty0 = tile_a * TILE_H;
@@ -890,19 +916,17 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     // A capacity overflow anywhere upstream makes the lists incomplete: the host regrows the
     // buffers and renders the frame again, so this launch only has to stay in bounds.
     if (f.counters[view * C_COUNT + C_OVERFLOW] != 0) { return; }
-    // general path: a tile no recorded triangle was binned into has nothing to add to the visibility buffer
-    if (!f.direct_bin && f.tile_count[view * f.tile_stride + tile] == 0u) { return; }
 
     // ---- this tile's triangle list (unordered: depth keys carry the order) ---------------------
     if (tid == 0) { sh.n_list = 0; sh.n_big = 0; sh.any_small = 0; }
-    if (f.direct_bin) {   // in-tile keys are only used when small triangles are walked in the tile (small scenes)
+    if (DIRECT) {   // in-tile keys are only used when small triangles are walked in the tile (small scenes)
 #pragma unroll
         for (int i = 0; i < (TILE_W * TILE_H) / RASTER_THREADS; i++) { sh.k.keys[i * RASTER_THREADS + tid] = 0ull; }
     }
     __syncthreads();
     uint32_t n;
     uint32_t *list;
-    if (f.direct_bin) {
+    if (DIRECT) {
         // small scene: collect straight from the survivors' heads (bbox overlap clamped to the band, plus the
         // conservative outside test); at most SORT_CAP survivors exist by construction of this mode
         const uint32_t n_setups = min(f.counters[view * C_COUNT + C_SETUPS], min(f.setup_cap, (uint32_t)SORT_CAP));
@@ -919,8 +943,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         n = sh.n_list;
         list = sh.slots;
     } else {
-        n = min(f.tile_count[view * f.tile_stride + tile], f.tile_cap);
-        list = f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap;
+        n = e1 - e0;
+        list = f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap + e0;
     }
 
     float depth[SEG], bw0[SEG], bw1[SEG], bw2[SEG];
@@ -954,10 +978,28 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
                     reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.bigq[base + b])[q];
             }
             __syncthreads();
-            // stage A: exact weights at the first walked pixel of every (triangle, row, segment).  One work
-            // item per (triangle, row, barycentric component): jump down the rows from the triangle's own
-            // ymin, jump along the row from its own xmin to the tile, then take true steps through the
-            // tile, dropping the value at every 8-pixel segment boundary.
+            // stage A1: the row-start weights (render.cpp:378-379) of every batch triangle for this tile's rows.  One
+            // thread per (triangle, component): a single exact jump from the triangle's own ymin to its first row in
+            // the tile, then true additions row by row — rows are consecutive, so only the first one needs a jump.
+            if (tid < nb * 3u) {
+                const uint32_t b = tid / 3u, c = tid % 3u;
+                const SetupVis &v = sh.u.big.batch[b];
+                const uint32_t y_first = max(ty0, (uint32_t)v.ymin), y_last = min(ty0 + TILE_H - 1u, (uint32_t)v.ymax);
+                if (y_first <= y_last) {
+                    const float d = v.dy[c];
+                    float w = walk_near(v.wstart[c], d, y_first - v.ymin);
+                    for (uint32_t yy = y_first; ; yy++) {
+                        sh.u.big.rowstart[b][yy - ty0][c] = w;
+                        if (yy == y_last) { break; }
+                        w = add_rn(w, d);
+                    }
+                }
+            }
+            __syncthreads();
+            // stage A2: exact weights at the first walked pixel of every (triangle, row, segment).  One work item per
+            // (triangle, row, component): from the row start, get to the tile's first column (true steps when it is
+            // near, the exact jump otherwise — render.cpp:374), then true steps through the tile, dropping the value
+            // at every 8-pixel segment boundary.
             for (uint32_t item = tid; item < nb * (TILE_H * 3u); item += RASTER_THREADS) {
                 const uint32_t b = item / (TILE_H * 3u), rc = item % (TILE_H * 3u), r = rc / 3u, c = rc % 3u;
                 const SetupVis &v = sh.u.big.batch[b];
@@ -966,8 +1008,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
                 const uint32_t xs = max(tx0, (uint32_t)v.xmin), xe = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
                 if (xs > xe) { continue; }
                 const float d = v.dx[c];
-                const float wy = walk_jump(v.wstart[c], v.dy[c], yy - v.ymin);   // render.cpp:378-379
-                float w = walk_jump(wy, d, xs - v.xmin);                         // render.cpp:374
+                float w = walk_near(sh.u.big.rowstart[b][r][c], d, xs - v.xmin);
                 uint32_t x = xs, k = (xs - tx0) / SEG;
                 while (true) {
                     sh.u.big.segstart[b][r][k][c] = w;
@@ -1012,21 +1053,22 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
         __syncthreads();
     }
 
-    if (!f.direct_bin) {
-        // general path: the small triangles' keys are final in HBM/L2 (flat passes ran before this kernel);
-        // a big-triangle candidate takes the pixel where its key is larger.  Every pixel belongs to exactly one
-        // thread of one tile CTA, so plain loads/stores suffice.  Shading happens in shade_tiles.
+    if (!DIRECT) {
+        // general path: a candidate takes the pixel where its key beats what the flat walks and the other CTAs working
+        // on this tile have published.  Shading (shade_tiles) finds the triangle through the key's order and re-derives
+        // the weights at the pixel with the exact jump, so nothing but the key has to be stored.
         if (y >= ylo_t && y < yhi_t) {
-            const size_t rbase = (size_t)view * f.out_view_stride + out_row(f, y, tile_a) * f.W;
+            unsigned long long *krow = f.keys + (size_t)view * f.out_view_stride + out_row(f, y, tile_a) * f.W;
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const uint32_t x = sx0 + j;
                 if (win[j] != NO_TRI && x < f.W) {
                     const unsigned long long key = ((unsigned long long)__float_as_uint(depth[j]) << 32) |
                                                    (unsigned long long)(~f.head[(size_t)view * f.setup_cap + win[j]].z);
-                    if (key > f.keys[rbase + x]) {
-                        f.keys[rbase + x] = key;
-                        f.pstate[rbase + x] = make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+                    // the best candidate so far also leaves its exact weights, tagged with its slot: a later, better
+                    // candidate overwrites them; shading checks the tag and falls back to the exact jump on a mismatch
+                    if (atomicMax(krow + x, key) < key) {
+                        f.pstate[(size_t)(krow - f.keys) + x] = make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
                     }
                 }
             }
@@ -1148,6 +1190,32 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
     }
 }
 
+__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    raster_one_tile<true>(f, *reinterpret_cast<RasterShared *>(smem_raw), blockIdx.z, blockIdx.x, blockIdx.y + f.raster_row0, 0u, 0u);
+}
+
+// General path: persistent CTAs pop (tile, chunk of its bin list) items from the queue post_setup built.  A tile with
+// a long list is shared by as many CTAs as it has chunks, so the busiest tile no longer sets the kernel's duration.
+__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster_queue(const __grid_constant__ Frame f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
+    const uint32_t view = blockIdx.y;
+    uint32_t *c = f.counters + view * C_COUNT;
+    const uint32_t n_items = min(c[C_ITEMS], f.items_cap);
+    while (true) {
+        __syncthreads();   // the previous item's shared-memory state is dead
+        if (threadIdx.x == 0) { sh.n_list = atomicAdd(c + C_QHEAD, 1u); }
+        __syncthreads();
+        const uint32_t i = sh.n_list;
+        if (i >= n_items) { return; }
+        __syncthreads();
+        const uint2 item = f.raster_items[(size_t)view * f.items_cap + i];   // {tile, first entry}
+        const uint32_t n = min(f.tile_count[view * f.tile_stride + item.x], f.tile_cap);
+        raster_one_tile<false>(f, sh, view, item.x % f.tiles_x, item.x / f.tiles_x, item.y, min(n, item.y + RASTER_CHUNK));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Flat path for small triangles (general, binned mode).  Dense fields put thousands of tiny triangles into
 // the busiest tiles; a tile CTA would then run as long as its list.  Instead every small survivor is walked by
@@ -1155,41 +1223,61 @@ __global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_co
 // with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame f) {
-    __shared__ uint32_t s_sum, s_max, s_last;
+    __shared__ uint32_t s_sum, s_max, s_last, s_warp[8], s_pref[257];
     const uint32_t view = blockIdx.y;
     bin_big_body(f, view);   // K3 for the triangles the setup kernel left to a whole CTA
+    // Flat walk of the recorded triangles under flat_max x flat_max pixels: 256 survivors per CTA and round, one work
+    // item per (triangle, box row) found by binary search in the prefix sums of the rows, so that every lane walks one
+    // row whatever the mix of box sizes.  Exactly the reference's own additions (render.cpp:374-379).
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-        const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
-        const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
-        if (!is_small_bbox(xmin, xmax, ymin, ymax)) { continue; }
-        const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
-        const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
-        const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
-        const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
-        const float rz0 = __uint_as_float(q3.y), rz1 = __uint_as_float(q3.z), rz2 = __uint_as_float(q3.w);
-        float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y), wy2 = __uint_as_float(q1.z);
-        const unsigned long long key_lo = (unsigned long long)(~head.z);
-        const uint32_t y_end = min(ymax, f.y1 - 1u);
-        for (uint32_t y = ymin; y <= y_end; y++) {
-            const uint32_t a = y / TILE_H;
-            if (y >= f.y0 && owns_row(f, a)) {
-                unsigned long long *krow = keys + out_row(f, y, a) * f.W;
-                float w0 = wy0, w1 = wy1, w2 = wy2;
-                for (uint32_t x = xmin; x <= xmax; x++) {
-                    if (w0 >= 0 && w1 >= 0 && w2 >= 0) {                                  // render.cpp:362
-                        const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;              // render.cpp:363
-                        if (ooz > 0.f) {   // depth starts at 0, strict '>' (render.cpp:364).  No load, no returned value:
-                                           // a fire-and-forget red.max that never stalls the walk
-                            atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo);
-                        }
-                    }
-                    w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
-                }
-            }
-            wy0 = add_rn(wy0, dy0); wy1 = add_rn(wy1, dy1); wy2 = add_rn(wy2, dy2);       // render.cpp:378
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    for (uint32_t g0 = blockIdx.x * 256u; g0 < n; g0 += gridDim.x * 256u) {
+        uint32_t rows = 0;
+        if (g0 + tid < n) {
+            const uint4 head = f.head[(size_t)view * f.setup_cap + g0 + tid];
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+            const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
+            if (is_flat_bbox(f, xmin, xmax, ymin, ymax) && ylo <= yhi) { rows = yhi - ylo + 1u; }
         }
+        uint32_t incl = rows;   // block-wide inclusive scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
+        if (lane == 31) { s_warp[warp] = incl; }
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { if ((uint32_t)w < warp) { before += s_warp[w]; } }
+        s_pref[tid + 1] = before + incl;
+        if (tid == 0) { s_pref[0] = 0; }
+        __syncthreads();
+        const uint32_t total = s_pref[256];
+        for (uint32_t i = tid; i < total; i += 256u) {
+            uint32_t lo = 0, hi = 256;   // largest j with s_pref[j] <= i
+            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_pref[mid] <= i) { lo = mid; } else { hi = mid; } }
+            const uint32_t slot = g0 + lo;
+            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu;
+            const uint32_t y = max(ymin, f.y0) + (i - s_pref[lo]), a = y / TILE_H;
+            if (!owns_row(f, a)) { continue; }
+            const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+            const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+            const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
+            const float rz0 = __uint_as_float(q3.y), rz1 = __uint_as_float(q3.z), rz2 = __uint_as_float(q3.w);
+            float w0 = walk_near(__uint_as_float(q1.x), __uint_as_float(q2.z), y - ymin);   // render.cpp:378
+            float w1 = walk_near(__uint_as_float(q1.y), __uint_as_float(q2.w), y - ymin);
+            float w2 = walk_near(__uint_as_float(q1.z), __uint_as_float(q3.x), y - ymin);
+            const unsigned long long key_lo = (unsigned long long)(~head.z);
+            unsigned long long *krow = keys + out_row(f, y, a) * f.W;
+            for (uint32_t x = xmin; x <= xmax; x++) {
+                const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
+                // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+                if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+            }
+        }
+        __syncthreads();   // s_pref is rewritten by the next round
     }
     // the last CTA of the view to get here closes the frame's geometry (tile statistics, overflow record)
     if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
@@ -1212,7 +1300,7 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
 //      attributes and normals of triangles that win no pixel are never read.  Recorded triangles are copied from
 //      their records (found through slot_of).  The setups are staged in shared memory, 256 per pass;
 //   3. one covered pixel per lane: small winners replay their own walk to the pixel (<= 15 + 15 true additions,
-//      render.cpp:374-379), big winners left their exact weights in pstate (tile_raster); shade (render.cpp:363-372);
+//      render.cpp:374-379), winners of the tile path get there with the exact jump; shade (render.cpp:363-372);
 //   4. the colour block goes out in 16-byte (or 12-byte, 24-bit transport) pieces.
 constexpr uint32_t SHADE_B = 32;          // block edge in pixels
 constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_B;
@@ -1340,7 +1428,7 @@ __global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Fr
                     dst[0] = q1.x; dst[1] = q1.y; dst[2] = q1.z; dst[3] = q1.w; dst[4] = q2.x; dst[5] = q2.y;
                     dst[6] = q2.z; dst[7] = q2.w; dst[8] = q3.x; dst[9] = q3.y; dst[10] = q3.z; dst[11] = q3.w;
                     dst[12] = xmin | (ymin << 16);
-                    dst[13] = is_small_bbox(xmin, xmax, ymin, ymax) ? 0u : 1u;
+                    dst[13] = is_flat_bbox(f, xmin, xmax, ymin, ymax) ? 0u : 1u + slot;   // tile path: tag of its pstate entries
                     const uint4 *sp = reinterpret_cast<const uint4 *>(f.shade + (size_t)view * f.setup_cap + slot);
 #pragma unroll
                     for (int k = 0; k < 8; k++) { const uint4 q = sp[k]; dst[14 + 4 * k] = q.x; dst[15 + 4 * k] = q.y; dst[16 + 4 * k] = q.z; dst[17 + 4 * k] = q.w; }
@@ -1360,12 +1448,23 @@ __global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Fr
                     const uint32_t xy = src[12];
                     w0 = __uint_as_float(src[0]); w1 = __uint_as_float(src[1]); w2 = __uint_as_float(src[2]);
                     const float dy0 = __uint_as_float(src[6]), dy1 = __uint_as_float(src[7]), dy2 = __uint_as_float(src[8]);
-                    for (uint32_t k = xy >> 16; k < py; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }       // render.cpp:378
-                    const float dx0 = __uint_as_float(src[3]), dx1 = __uint_as_float(src[4]), dx2 = __uint_as_float(src[5]);
-                    for (uint32_t k = xy & 0xFFFFu; k < px; k++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
-                } else {
-                    const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + qr) * f.W + px];
-                    w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);
+                    const uint32_t ny = py - (xy >> 16), nx = px - (xy & 0xFFFFu);
+                    if (ny < SMALL_MAX && nx < SMALL_MAX) {
+                        for (uint32_t k = 0; k < ny; k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }       // render.cpp:378
+                        const float dx0 = __uint_as_float(src[3]), dx1 = __uint_as_float(src[4]), dx2 = __uint_as_float(src[5]);
+                        for (uint32_t k = 0; k < nx; k++) { w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2); }   // render.cpp:374
+                    } else {   // a flat-walked box larger than 16 x 16: same values, by the exact jump where the way is long
+                        w0 = walk_near(walk_near(w0, dy0, ny), __uint_as_float(src[3]), nx);
+                        w1 = walk_near(walk_near(w1, dy1, ny), __uint_as_float(src[4]), nx);
+                        w2 = walk_near(walk_near(w2, dy2, ny), __uint_as_float(src[5]), nx);
+                    }
+                } else if (const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + qr) * f.W + px]; st.w + 1u == src[13]) {
+                    w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);   // left by the tile kernel
+                } else {   // (another CTA's candidate raced the winner's note) exact jump down the rows, then along the row
+                    const uint32_t xy = src[12], ny = py - (xy >> 16), nx = px - (xy & 0xFFFFu);
+                    w0 = walk_near(walk_near(__uint_as_float(src[0]), __uint_as_float(src[6]), ny), __uint_as_float(src[3]), nx);
+                    w1 = walk_near(walk_near(__uint_as_float(src[1]), __uint_as_float(src[7]), ny), __uint_as_float(src[4]), nx);
+                    w2 = walk_near(walk_near(__uint_as_float(src[2]), __uint_as_float(src[8]), ny), __uint_as_float(src[5]), nx);
                 }
                 SetupShade s;
                 uint32_t *sw = reinterpret_cast<uint32_t *>(&s);
@@ -1414,6 +1513,10 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(tile_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(tile_raster_queue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared));
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(tile_raster_queue, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
     // both keep ~40 KB of static shared memory per CTA: without the carve-out hint the driver may leave too little for 4-6 CTAs per SM
     e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
     if (e != cudaSuccess) { return e; }
@@ -1437,8 +1540,12 @@ int launch_geometry(const Frame &f, cudaStream_t s) {
 }
 
 int launch_raster(const Frame &f, cudaStream_t s) {
-    tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
-    if (f.direct_bin) { return 1; }
+    if (f.direct_bin) {
+        tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+        return 1;
+    }
+    // general path (always one raster launch per frame): the queue holds every non-empty tile of the submission
+    tile_raster_queue<<<dim3((uint32_t)g_sm_count * 3u, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
     // general path: the tile kernel only resolved the big triangles; shade the rows it covered
     uint32_t row0, nrows;
     if (f.row_stride == 1u) {

@@ -39,6 +39,7 @@ constexpr int BATCH = 8;                    // triangles staged per visibility b
 constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
+constexpr uint32_t RASTER_CHUNK = 64;       // bin-list entries one tile-kernel work item resolves (general path)
 
 constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
 constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.cpp:92 (binary32 value of the reference build)
@@ -46,6 +47,8 @@ constexpr uint32_t kBackground = 0x001E1E1Eu;   // RGB(30, 30, 30), render.cpp:9
 
 enum Counter : uint32_t {
     C_SETUPS = 0, C_ENTRIES = 1, C_BIG = 2, C_OVERFLOW = 3, C_NEAR = 4, C_CLIPPED = 5, C_SPAWNED = 6, C_CULLED = 7, C_WORK = 8,
+    C_ITEMS = 11,    // (tile, chunk) items in the tile kernel's work queue (general path)
+    C_QHEAD = 12,    // ... and how many of them have been taken
     C_DONE = 10,     // CTAs of post_setup that have finished (the last one closes the frame's geometry)
     C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
     C_COUNT = 16
@@ -106,13 +109,16 @@ struct Frame {
     uint32_t tile_cap;          // capacity of every tile's list
     uint32_t *big_list;
     uint32_t big_cap;
-    // general path: per-pixel depth keys (depth << 32 | ~order) and winners (w0, w1, w2, slot), indexed like `out`
+    // general path: per-pixel depth keys (depth << 32 | ~order), indexed like `out`; the tile kernel's work queue
     unsigned long long *keys;
-    uint4 *pstate;
+    uint4 *pstate;         // exact weights + slot of the tile kernel's best candidate per pixel (checked by tag)
+    uint2 *raster_items;   // [views][items_cap] {tile, first entry of the chunk}
+    uint32_t items_cap;
     // output
     uint32_t *out;
     unsigned long long out_view_stride;  // pixels
     int use_tma;
+    uint32_t flat_max;  // recorded triangles under flat_max x flat_max pixels are walked flat (post_setup), larger ones by tiles
     int direct_small;   // 1 (general path): small unclipped survivors are walked by the classify kernel and shaded from the raw scene
     int direct_bin;     // 1: no bin arrays — every raster CTA collects its triangles from the setup list itself
     int out_packed24;   // 1: `out` is a byte buffer with 3 bytes per pixel (B, G, R), used for host transport

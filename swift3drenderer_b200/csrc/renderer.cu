@@ -74,7 +74,10 @@ struct S3RRenderer {
     DevBuf<uint4> head;
     DevBuf<uint32_t> slot_of;
     DevBuf<unsigned long long> keys;   // general path: per-pixel depth keys ...
-    DevBuf<uint4> pstate;              // ... and winners
+    DevBuf<uint2> raster_items;        // ... and the tile kernel's work queue
+    DevBuf<uint4> pstate;              // weights of the tile kernel's winners
+    int opt_flat_max = 128;
+    uint32_t items_cap = 0;
     DevBuf<uint32_t> worklist;
     DevBuf<uint32_t> sticky;
     uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
@@ -157,7 +160,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->pstate.release();
+    r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
@@ -395,7 +398,11 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     }
     CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
     // bin lists exist only for scenes that do not take the in-kernel collection path
-    if (!uses_direct_bin(r)) { CUDA_TRY(r->entries.ensure(vc * (size_t)r->tile_stride * r->tile_cap)); }
+    if (!uses_direct_bin(r)) {
+        CUDA_TRY(r->entries.ensure(vc * (size_t)r->tile_stride * r->tile_cap));
+        r->items_cap = r->tile_stride * (1u + r->tile_cap / RASTER_CHUNK);   // every non-empty tile + every full chunk
+        CUDA_TRY(r->raster_items.ensure(vc * (size_t)r->items_cap));
+    }
     CUDA_TRY(r->big_list.ensure(vc * r->big_cap));
     CUDA_TRY(r->cams.ensure(vc * 12));
     if (r->cams_pinned_views < vc) {
@@ -465,9 +472,10 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.tile_count = r->tile_count.p;
     f.tile_stride = r->tile_stride;
     f.entries = r->entries.p; f.tile_cap = r->tile_cap;
+    f.raster_items = r->raster_items.p; f.items_cap = r->items_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out;
-    f.keys = r->keys.p; f.pstate = r->pstate.p;
+    f.keys = r->keys.p;
     f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
     if (!uses_direct_bin(r)) {   // general path: per-pixel keys and winners for the flat passes
         // keys are all zero between frames: allocation clears them, shade_tiles clears what a frame has set
@@ -476,8 +484,9 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
             CUDA_TRY(r->keys.ensure((size_t)n_views * f.out_view_stride + 2));
             CUDA_TRY(cudaMemsetAsync(r->keys.p, 0, r->keys.n * sizeof(unsigned long long), s));
         }
+        f.keys = r->keys.p;
         CUDA_TRY(r->pstate.ensure((size_t)n_views * f.out_view_stride + 2));
-        f.keys = r->keys.p; f.pstate = r->pstate.p;
+        f.pstate = r->pstate.p;
     }
     f.out_packed24 = packed24 ? 1 : 0;
     f.use_tma = r->opt_tma && (W % (packed24 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
@@ -486,13 +495,14 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
     f.direct_bin = uses_direct_bin(r) ? 1 : 0;
     f.direct_small = !f.direct_bin && r->opt_direct_small ? 1 : 0;
+    f.flat_max = (uint32_t)r->opt_flat_max;
     f.rs_magic = row_stride > 1 ? (uint32_t)((1ull << 32) / row_stride) + 1u : 0u;
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
-    const int nb = std::max(1, std::min<int>(raster_bands, (int)f.tiles_y));
+    const int nb = f.direct_bin ? std::max(1, std::min<int>(raster_bands, (int)f.tiles_y)) : 1;   // the general path's tile queue spans the frame
     for (int b = 0; b < nb; b++) {
         f.raster_row0 = (uint32_t)((uint64_t)f.tiles_y * b / nb);
         f.raster_rows = (uint32_t)((uint64_t)f.tiles_y * (b + 1) / nb) - f.raster_row0;
@@ -666,7 +676,8 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
         for (int attempt = 0; attempt < 8; attempt++) {
             // ---- enqueue: geometry, banded raster, one D2H per band/slice on the copy stream -----
             uint32_t band_rows[S3RRenderer::MAX_SLICES];
-            const int bands = nv == 1 ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
+            // band-pipelined raster/copy for the tile-kernel path only (see render_chunk)
+            const int bands = nv == 1 && uses_direct_bin(r) ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
             int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream, bands, band_rows, packed);
             if (rc) { return rc; }
             r->last_views = nv; r->last_W = W; r->last_H = H;
@@ -836,6 +847,10 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
+    if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
+        if (value < 16 || value > 65536) { return fail(S3R_E_ARG, "flat_max out of range"); }
+        r->opt_flat_max = (int)value; return S3R_OK;
+    }
     if (!strcmp(name, "pack24")) { r->opt_pack24 = value != 0; return S3R_OK; }
     if (!strcmp(name, "host_bands")) { r->opt_host_bands = (int)std::max<int64_t>(1, value); return S3R_OK; }
     if (!strcmp(name, "copy_threads")) {
