@@ -357,3 +357,62 @@ def test_interleaved_tile_rows_reassemble_to_the_whole_frame(gpu_renderer, rende
                     assert gpu_renderer.finish() is False
                     frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
                 assert_same(frame, whole, f"{W}x{H} interleaved over {world}")
+
+
+def _general_scenes():
+    """Scenes that take the general (visibility-buffer) path: > 2048 triangles."""
+    return (("clip", lambda: S.clip_stress_scene(3000), "spin", 9),          # straddlers, spawned, big and mid-size triangles
+            ("dense", lambda: S.icosahedron_field(20000, seed=9, extent=40, r_range=(0.3, 1.0)), "spin", 5))  # tiny triangles
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_general_path_variants_agree_with_the_oracle(which, gpu_renderer, renderer_lib, oracle_port):
+    """Every routing of the general path must give the reference's frame: record-free direct walk on/off, and the
+    flat-walk / tile-kernel split at different box sizes (16 = everything recorded goes to tiles ... 4096 = none)."""
+    name, build, script, fidx = _general_scenes()[which]
+    sc = build()
+    gpu_renderer.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script(script, 12))[fidx]
+    W, H = 800, 450
+    want = oracle_port.OracleScene(sc).render(m, W, H)["pixels"]
+    try:
+        for direct in (1, 0):
+            for flat in (16, 128, 4096):
+                gpu_renderer.set_option("direct_small", direct)
+                gpu_renderer.set_option("flat_max", flat)
+                assert_same(gpu_renderer.render(m, W, H)[0], want, f"{name} direct_small={direct} flat_max={flat}")
+    finally:
+        gpu_renderer.set_option("direct_small", 1)
+        gpu_renderer.set_option("flat_max", 128)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_general_path_bands_rows_and_batches(which, gpu_renderer, renderer_lib):
+    """Screen bands, interleaved tile rows and multi-view batches of the general path reassemble to the whole frame."""
+    import torch
+    name, build, script, fidx = _general_scenes()[which]
+    gpu_renderer.load_scene(build())
+    mats = renderer_lib.camera_path(S.input_script(script, 12))
+    m = mats[fidx]
+    W, H = 800, 450
+    whole = gpu_renderer.render(m, W, H)[0]
+    assert len(np.unique(whole)) > 50
+    for n in (2, 5):
+        edges = [H * k // n for k in range(n + 1)]
+        parts = [gpu_renderer.render(m, W, H, y0=edges[k], y1=edges[k + 1])[0] for k in range(n)]
+        assert_same(np.concatenate(parts, 0), whole, f"{name}: {n} bands")
+    th = renderer_lib.tile_height()
+    for world in (2, 8):
+        frame = np.zeros((H, W), np.uint32)
+        for phase in range(world):
+            rows, frame_rows, buf_rows = renderer_lib.rows_layout(H, world, phase, th)
+            if rows == 0:
+                continue
+            buf = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
+            gpu_renderer.render_device_rows(m, W, H, world, phase, buf.data_ptr())
+            assert gpu_renderer.finish() is False
+            frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
+        assert_same(frame, whole, f"{name}: interleaved over {world}")
+    batch = gpu_renderer.render(mats[3:9], W, H)
+    for k in range(6):
+        assert_same(batch[k], gpu_renderer.render(mats[3 + k], W, H)[0], f"{name}: view {k} of a batch")
