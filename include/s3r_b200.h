@@ -112,6 +112,24 @@ S3R_API int s3r_render_device_rows(S3RRenderer *r, const float *cameras, uint32_
                                    uint32_t height, uint32_t row_stride, uint32_t row_phase, uint32_t *dev_out,
                                    void *stream);
 S3R_API uint32_t s3r_tile_height(void);
+
+/* ---- fused frame assembly over peer memory (multi-GPU screen partition) -----------------------
+ * Replaces "render my rows, then all-gather" by "store my rows straight into every rank's frame":
+ * the shading kernel writes each finished pixel row to its absolute position in up to 16 full-size
+ * (n_views x height x width) destination frames — the rank's own and its NVLink peers'.  Frames are plain
+ * device allocations shared through CUDA IPC:
+ *   s3r_peer_frame_alloc   allocates `bytes` on the renderer's device, returns the pointer and a 64-byte
+ *                          IPC handle to send to the other ranks (any transport);
+ *   s3r_peer_frame_open    maps another process's allocation (peer access is enabled on demand);
+ *   s3r_set_peer_frames    the destinations of the following s3r_render_device / _rows calls (n = 0
+ *                          switches back to `dev_out`, which may be NULL while destinations are set).
+ * The caller orders frames across ranks (a barrier / tiny all-reduce per frame, or a ring of frames).
+ * General path only (scenes over 2048 triangles); other scenes return S3R_E_ARG while destinations are set. */
+S3R_API int s3r_peer_frame_alloc(S3RRenderer *r, uint64_t bytes, void **dev_ptr, unsigned char ipc_handle_out[64]);
+S3R_API int s3r_peer_frame_open(S3RRenderer *r, const unsigned char ipc_handle[64], void **dev_ptr);
+S3R_API int s3r_peer_frame_release(S3RRenderer *r, void *dev_ptr);   /* frees (own) or unmaps (opened) */
+S3R_API int s3r_set_peer_frames(S3RRenderer *r, void *const *dev_ptrs, uint32_t n);
+S3R_API int s3r_copy_from_device(S3RRenderer *r, void *host_dst, const void *dev_src, uint64_t bytes);   /* test helper */
 S3R_API int s3r_finish(S3RRenderer *r);
 S3R_API int s3r_render_host(S3RRenderer *r, const float *cameras, uint32_t n_views, uint32_t width, uint32_t height,
                     uint32_t y0, uint32_t y1, uint32_t *host_out);

@@ -1481,6 +1481,21 @@ __global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Fr
     const uint4 c = *reinterpret_cast<const uint4 *>(&sh.colour[pr][pc]);
     const uint32_t rgb[4] = {c.x, c.y, c.z, c.w};
     const size_t base = vbase + (size_t)(row0 + br0 + pr) * f.W + x0;
+    if (f.n_peers) {
+        // fused assembly: this row goes to its absolute place in every rank's frame (one 16-byte store per
+        // destination; remote ones travel over NVLink while the CTA's other warps are still shading)
+        const uint32_t py = pixel_y(f, row0 + br0 + pr);
+        if (py < f.H) {
+            const size_t at = ((size_t)view * f.H + py) * f.W + x0;
+            const bool wide = x0 + 3u < f.W && (at & 3u) == 0;
+            for (uint32_t k = 0; k < f.n_peers; k++) {
+                uint32_t *o = f.peer_out[k] + at;
+                if (wide) { *reinterpret_cast<uint4 *>(o) = make_uint4(rgb[0], rgb[1], rgb[2], rgb[3]); }
+                else { for (int q = 0; q < 4 && x0 + q < f.W; q++) { o[q] = rgb[q]; } }
+            }
+        }
+        return;
+    }
     if (f.out_packed24) {
         uint8_t *o = reinterpret_cast<uint8_t *>(f.out) + base * 3u;
         if (x0 + 3u < f.W && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {

@@ -39,6 +39,7 @@ constexpr int BATCH = 8;                    // triangles staged per visibility b
 constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
+constexpr int MAX_PEERS = 16;              // destinations of the fused frame assembly (ranks of one NVSwitch domain)
 constexpr uint32_t RASTER_CHUNK = 64;       // bin-list entries one tile-kernel work item resolves (general path)
 
 constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
@@ -115,6 +116,10 @@ struct Frame {
     uint2 *raster_items;   // [views][items_cap] {tile, first entry of the chunk}
     uint32_t items_cap;
     // output
+    // fused frame assembly (multi-GPU, general path): every owned pixel row is stored straight into the full-size
+    // frames of all ranks (own HBM + NVLink peer memory) at its absolute position; `out` is not written then
+    uint32_t *peer_out[MAX_PEERS];
+    uint32_t n_peers;
     uint32_t *out;
     unsigned long long out_view_stride;  // pixels
     int use_tma;

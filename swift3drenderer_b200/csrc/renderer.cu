@@ -110,6 +110,10 @@ struct S3RRenderer {
     HostCopier *copier = nullptr;
     int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1;
     std::vector<HostPin> pins;
+    // fused frame assembly
+    std::vector<void *> own_frames, opened_frames;
+    uint32_t *peer_out[MAX_PEERS] = {};
+    uint32_t n_peers = 0;
 };
 
 // --------------------------------------------------------------------------------------------------
@@ -157,6 +161,8 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     if (!r) { return; }
     cudaSetDevice(r->device);
     cudaStreamSynchronize(r->stream);
+    for (void *p : r->opened_frames) { cudaIpcCloseMemHandle(p); }
+    for (void *p : r->own_frames) { cudaFree(p); }
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
@@ -475,6 +481,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.raster_items = r->raster_items.p; f.items_cap = r->items_cap;
     f.big_list = r->big_list.p; f.big_cap = r->big_cap;
     f.out = dev_out;
+    f.n_peers = r->n_peers;
+    for (uint32_t k = 0; k < r->n_peers; k++) { f.peer_out[k] = r->peer_out[k]; }
     f.keys = r->keys.p;
     f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
     if (!uses_direct_bin(r)) {   // general path: per-pixel keys and winners for the flat passes
@@ -494,6 +502,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
     f.direct_bin = uses_direct_bin(r) ? 1 : 0;
+    if (f.n_peers && (f.direct_bin || packed24)) { return fail(S3R_E_ARG, "peer frames need the general path (scene over 2048 triangles) and device output"); }
     f.direct_small = !f.direct_bin && r->opt_direct_small ? 1 : 0;
     f.flat_max = (uint32_t)r->opt_flat_max;
     f.rs_magic = row_stride > 1 ? (uint32_t)((1ull << 32) / row_stride) + 1u : 0u;
@@ -522,7 +531,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
 
 extern "C" int s3r_render_device(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
                                  uint32_t y0, uint32_t y1, uint32_t *dev_out, void *stream) {
-    if (!r || !cams || !dev_out) { return fail(S3R_E_ARG, "null argument"); }
+    if (!r || !cams || (!dev_out && r->n_peers == 0)) { return fail(S3R_E_ARG, "null argument"); }
     if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
     if (W == 0 || H == 0 || W > 65535 || H > 65535 || y0 >= y1 || y1 > H || n_views == 0) {
         return fail(S3R_E_ARG, "bad frame geometry");
@@ -545,7 +554,7 @@ extern "C" uint32_t s3r_tile_height(void) { return (uint32_t)TILE_H; }
 
 extern "C" int s3r_render_device_rows(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H,
                                       uint32_t row_stride, uint32_t row_phase, uint32_t *dev_out, void *stream) {
-    if (!r || !cams || !dev_out) { return fail(S3R_E_ARG, "null argument"); }
+    if (!r || !cams || (!dev_out && r->n_peers == 0)) { return fail(S3R_E_ARG, "null argument"); }
     if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
     if (W == 0 || H == 0 || W > 65535 || H > 65535 || n_views == 0 || row_stride == 0 || row_phase >= row_stride) {
         return fail(S3R_E_ARG, "bad frame geometry");
@@ -738,6 +747,68 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
             }
         }
     }
+    return S3R_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// fused frame assembly over peer memory
+// --------------------------------------------------------------------------------------------------
+extern "C" int s3r_peer_frame_alloc(S3RRenderer *r, uint64_t bytes, void **dev_ptr, unsigned char handle_out[64]) {
+    if (!r || !dev_ptr || !handle_out || bytes == 0) { return fail(S3R_E_ARG, "null argument"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CUDA_TRY(cudaSetDevice(r->device));
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(S3R_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    r->own_frames.push_back(p);
+    *dev_ptr = p;
+    return S3R_OK;
+}
+
+extern "C" int s3r_peer_frame_open(S3RRenderer *r, const unsigned char handle[64], void **dev_ptr) {
+    if (!r || !dev_ptr || !handle) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    r->opened_frames.push_back(p);
+    *dev_ptr = p;
+    return S3R_OK;
+}
+
+extern "C" int s3r_peer_frame_release(S3RRenderer *r, void *dev_ptr) {
+    if (!r || !dev_ptr) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (uint32_t k = 0; k < r->n_peers; k++) { if (r->peer_out[k] == dev_ptr) { r->n_peers = 0; } }
+    for (size_t i = 0; i < r->own_frames.size(); i++) {
+        if (r->own_frames[i] == dev_ptr) { r->own_frames.erase(r->own_frames.begin() + (long)i); CUDA_TRY(cudaFree(dev_ptr)); return S3R_OK; }
+    }
+    for (size_t i = 0; i < r->opened_frames.size(); i++) {
+        if (r->opened_frames[i] == dev_ptr) { r->opened_frames.erase(r->opened_frames.begin() + (long)i); CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr)); return S3R_OK; }
+    }
+    return fail(S3R_E_ARG, "not a peer frame of this renderer");
+}
+
+extern "C" int s3r_set_peer_frames(S3RRenderer *r, void *const *dev_ptrs, uint32_t n) {
+    if (!r || (n && !dev_ptrs) || n > (uint32_t)MAX_PEERS) { return fail(S3R_E_ARG, "bad peer frame list"); }
+    for (uint32_t k = 0; k < n; k++) {
+        if (!dev_ptrs[k]) { return fail(S3R_E_ARG, "null peer frame"); }
+        r->peer_out[k] = static_cast<uint32_t *>(dev_ptrs[k]);
+    }
+    r->n_peers = n;
+    return S3R_OK;
+}
+
+extern "C" int s3r_copy_from_device(S3RRenderer *r, void *host_dst, const void *dev_src, uint64_t bytes) {
+    if (!r || !host_dst || !dev_src) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
     return S3R_OK;
 }
 

@@ -7,6 +7,9 @@ Two partitions (BASELINE.json north_star):
   runs the geometry stages on the whole scene and rasterises only its band (each triangle's barycentric
   walk starts at the triangle's own ymin, so a band boundary changes no pixel); ``assemble_bands``
   concatenates the bands on every rank with one all-gather (NCCL over NVLink on GPUs; gloo in the CPU test).
+  ``PeerFrames`` is the fused alternative: no collective moves pixels at all — every rank's shading kernel stores
+  its rows straight into the full-size frames of all ranks over NVLink peer memory (CUDA IPC), and a one-element
+  all-reduce per frame orders the frames.
 """
 from __future__ import annotations
 
@@ -95,3 +98,51 @@ def render_banded(render_band: Callable[[int, int], torch.Tensor], height: int, 
     wraps ``Renderer.render_device(..., y0=y0, y1=y1)``); returns the assembled frame."""
     y0, y1 = band_edges(height, world)[rank]
     return assemble_bands(render_band(y0, y1), height, rank, world, group)
+
+
+class PeerFrames:
+    """Fused frame assembly: a ring of full-size frames on every rank, each mapped by all other ranks.
+
+    ``render(...)`` makes this rank's renderer store its tile rows into ring slot ``k`` of EVERY rank
+    (``Renderer.set_peer_frames`` + ``render_device_rows``); ``fence()`` is the per-frame ordering point (a
+    one-element all-reduce, stream-ordered).  After the fence of frame k every rank holds the complete frame in
+    its own slot ``k % ring``.  Ranks must be processes of one node (CUDA IPC over NVLink / NVSwitch)."""
+
+    def __init__(self, renderer, height: int, width: int, rank: int, world: int, device, ring: int = 2, group=None):
+        self.r, self.rank, self.world, self.ring, self.group = renderer, rank, world, ring, group
+        self.height, self.width = height, width
+        self.frame_bytes = height * width * 4
+        self.own_ptr, handle = renderer.peer_frame_alloc(self.frame_bytes * ring)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, handle, group=group)
+        else:
+            handles[0] = handle
+        self.base = [self.own_ptr if k == rank else renderer.peer_frame_open(handles[k]) for k in range(world)]
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.count = 0
+
+    def destinations(self, slot: int):
+        return [b + slot * self.frame_bytes for b in self.base]
+
+    def render(self, camera, stream: int = 0) -> int:
+        """Enqueues this rank's share of the next frame; returns the ring slot it lands in."""
+        slot = self.count % self.ring
+        self.count += 1
+        self.r.set_peer_frames(self.destinations(slot))
+        self.r.render_device_rows(camera, self.width, self.height, self.world, self.rank, 0, stream=stream)
+        self.r.set_peer_frames([])
+        return slot
+
+    def fence(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.token, group=self.group)
+
+    def read(self, slot: int):
+        """This rank's copy of ring slot `slot` as a host array (call after the fence and a device synchronize)."""
+        return self.r.read_device(self.own_ptr + slot * self.frame_bytes, (self.height, self.width))
+
+    def close(self) -> None:
+        for k, b in enumerate(self.base):
+            self.r.peer_frame_release(b)
+        self.base = []

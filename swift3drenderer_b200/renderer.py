@@ -136,6 +136,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_debug_walk.argtypes = [vp, vp, vp, vp, vp, u32]
     lib.s3r_render_device_rows.argtypes = [vp, vp, u32, u32, u32, u32, u32, vp, vp]
     lib.s3r_tile_height.restype = u32
+    lib.s3r_peer_frame_alloc.argtypes = [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]
+    lib.s3r_peer_frame_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.s3r_peer_frame_release.argtypes = [vp, vp]
+    lib.s3r_set_peer_frames.argtypes = [vp, ctypes.POINTER(vp), u32]
+    lib.s3r_copy_from_device.argtypes = [vp, vp, vp, u64]
     if path is None:
         _lib = lib
     return lib
@@ -260,6 +265,31 @@ class Renderer:
         cams = np.ascontiguousarray(cameras, "<f4").reshape(-1, 12)
         self._check(self._lib.s3r_render_device_rows(self._h, cams.ctypes.data, cams.shape[0], width, height, row_stride,
                                                       row_phase, ctypes.c_void_p(dev_ptr), ctypes.c_void_p(stream)))
+
+    # ---- fused frame assembly over peer memory (include/s3r_b200.h) ------------------------------
+    def peer_frame_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a new allocation on this renderer's GPU."""
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        self._check(self._lib.s3r_peer_frame_alloc(self._h, nbytes, ctypes.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def peer_frame_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.s3r_peer_frame_open(self._h, handle, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_frame_release(self, ptr: int) -> None:
+        self._check(self._lib.s3r_peer_frame_release(self._h, ctypes.c_void_p(ptr)))
+
+    def set_peer_frames(self, ptrs) -> None:
+        """Destinations of the following render_device(_rows) calls ([] = back to the call's own output)."""
+        arr = (ctypes.c_void_p * max(len(ptrs), 1))(*[ctypes.c_void_p(p) for p in ptrs])
+        self._check(self._lib.s3r_set_peer_frames(self._h, arr, len(ptrs)))
+
+    def read_device(self, ptr: int, shape, dtype=np.uint32) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        self._check(self._lib.s3r_copy_from_device(self._h, out.ctypes.data, ctypes.c_void_p(ptr), out.nbytes))
+        return out
 
     def finish(self) -> bool:
         """Waits for enqueued work; True means a capacity overflowed and the last call must be repeated."""

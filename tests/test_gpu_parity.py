@@ -416,3 +416,34 @@ def test_general_path_bands_rows_and_batches(which, gpu_renderer, renderer_lib):
     batch = gpu_renderer.render(mats[3:9], W, H)
     for k in range(6):
         assert_same(batch[k], gpu_renderer.render(mats[3 + k], W, H)[0], f"{name}: view {k} of a batch")
+
+
+def test_fused_assembly_writes_rows_to_every_destination(gpu_renderer, renderer_lib):
+    """The shading kernel's fused frame assembly (s3r_set_peer_frames): the ranks' interleaved tile rows, stored
+    straight into full-size destination frames, add up to the whole frame in every destination.  (One GPU here, two
+    local destinations; across processes the destinations are CUDA-IPC mappings — tests/test_multigpu_peer.py.)"""
+    sc = S.clip_stress_scene(3000)
+    gpu_renderer.load_scene(sc)
+    m = renderer_lib.camera_path(S.input_script("spin", 12))[9]
+    W, H = 800, 450
+    whole = gpu_renderer.render(m, W, H)[0]
+    a, _ = gpu_renderer.peer_frame_alloc(W * H * 4)
+    b, _ = gpu_renderer.peer_frame_alloc(W * H * 4)
+    try:
+        for world in (1, 3):
+            for phase in range(world):
+                gpu_renderer.set_peer_frames([a, b])
+                gpu_renderer.render_device_rows(m, W, H, world, phase, 0)
+                assert gpu_renderer.finish() is False
+            gpu_renderer.set_peer_frames([])
+            for ptr in (a, b):
+                assert_same(gpu_renderer.read_device(ptr, (H, W)), whole, f"fused assembly over {world}")
+        # small scenes (tile-kernel path) refuse destinations instead of silently ignoring them
+        gpu_renderer.load_scene(S.shipped_scene(1))
+        gpu_renderer.set_peer_frames([a])
+        with pytest.raises(RuntimeError):
+            gpu_renderer.render_device_rows(m, W, H, 1, 0, 0)
+    finally:
+        gpu_renderer.set_peer_frames([])
+        gpu_renderer.peer_frame_release(a)
+        gpu_renderer.peer_frame_release(b)

@@ -47,8 +47,10 @@ def main():
     ap.add_argument("--c3-solids", type=int, default=1_000_000)
     ap.add_argument("--c4-solids", type=int, default=50_000)
     ap.add_argument("--c5-views", type=int, default=4096)
-    ap.add_argument("--partition", default="rows", choices=["rows", "bands"],
-                    help="multi-GPU split of a frame: interleaved tile rows (load balanced) or contiguous bands")
+    ap.add_argument("--partition", default="fused", choices=["fused", "rows", "bands"],
+                    help="multi-GPU split of a frame: interleaved tile rows stored straight into every rank's frame over "
+                         "NVLink peer memory (fused, general-path scenes), interleaved tile rows + all-gather (rows), or "
+                         "contiguous bands + all-gather (bands)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -112,7 +114,20 @@ def main():
         else:  # screen bands + all-gather of the assembled frame on every rank
             y0, y1 = multigpu.band_edges(H, world)[rank]
             full = [None]
-            if args.partition == "rows" and world > 1:  # interleaved tile rows: compacted buffer, gather, de-interleave
+            if args.partition == "fused" and world > 1:  # no pixel collective: rows go straight into every rank's frame
+                pf = multigpu.PeerFrames(r, H, W, rank, world, dev, ring=2)
+                last = [0]
+
+                def step():
+                    for f in range(n):
+                        last[0] = pf.render(mats[f], stream=stream.cuda_stream)
+                        pf.fence()
+
+                def read_own_slot():   # the assembled frame of the last pose, from this rank's own ring slot
+                    torch.cuda.synchronize(dev)
+                    return pf.read(last[0])
+                full[0] = read_own_slot
+            elif args.partition in ("rows", "fused") and world > 1:  # interleaved tile rows: compacted buffer, gather, de-interleave
                 asm = multigpu.InterleavedAssembler(H, W, rank, world, dev, R.tile_height())
 
                 def step():
@@ -136,9 +151,9 @@ def main():
                         full[0] = multigpu.assemble_bands(band, H, rank, world)
             frames_done = n
 
-        for _ in range(2):  # warm-up incl. capacity regrowth
+        for _ in range(2):  # warm-up incl. capacity regrowth (decided together: step() may contain a collective)
             step()
-            while r.finish():
+            while max_over_ranks(1.0 if r.finish() else 0.0) > 0:
                 step()
         r.set_option("timing", 1)
         r.timing(reset=True)
@@ -151,6 +166,8 @@ def main():
         e1.record(stream)
         barrier()
         assert not r.finish()
+        if mode != "frames" and args.partition == "fused" and world > 1:
+            line["assembly"] = "shading kernel stores rows into every rank's frame (CUDA IPC peer memory) + 1-element all-reduce per frame"
         ms = max_over_ranks(e0.elapsed_time(e1)) / reps
         tm = r.timing(reset=True)
         r.set_option("timing", 0)
@@ -184,7 +201,8 @@ def main():
         if mode == "bands":
             # every rank: the assembled frame of the last pose equals a single-GPU whole-frame render
             whole = r.render(mats[n - 1], W, H)[0]
-            same = bool(np.array_equal(full[0].cpu().numpy().view(np.uint32), whole))
+            assembled = full[0]() if callable(full[0]) else full[0].cpu().numpy().view(np.uint32)
+            same = bool(np.array_equal(assembled, whole))
             line["banded_equals_whole"] = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
         if not args.no_cpu and rank == 0 and cpu_frames:
             from oracle import port
