@@ -252,6 +252,32 @@ __device__ __forceinline__ uint32_t owned_rows_in(const Frame &f, uint32_t a0, u
     return first > a1 ? 0u : div_stride(f, a1 - first) + 1u;
 }
 
+// Pixel rows of [ylo, yhi] this submission owns, as a count and an index -> row map (flat walk work items).
+// Interleaved ownership: the first owned tile row may be cut by ylo, the last by yhi, the ones between are whole.
+struct OwnedRows { uint32_t count, first_y, first_n, next_a; };
+
+__device__ __forceinline__ OwnedRows owned_pixel_rows(const Frame &f, uint32_t ylo, uint32_t yhi) {
+    OwnedRows o;
+    if (f.row_stride == 1u) { o.count = yhi - ylo + 1u; o.first_y = ylo; o.first_n = o.count; o.next_a = 0; return o; }
+    const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
+    const uint32_t af = a0 + mod_stride(f, f.row_phase + f.row_stride - mod_stride(f, a0));   // first owned tile row >= a0
+    if (af > a1) { o.count = 0; o.first_y = 0; o.first_n = 0; o.next_a = 0; return o; }
+    o.first_y = max(ylo, af * TILE_H);
+    o.first_n = min(yhi, af * TILE_H + TILE_H - 1u) - o.first_y + 1u;
+    o.next_a = af + f.row_stride;
+    o.count = o.first_n;
+    if (o.next_a <= a1) {
+        const uint32_t more = div_stride(f, a1 - o.next_a) + 1u, last = o.next_a + (more - 1u) * f.row_stride;   // owned tile rows after the first
+        o.count += (more - 1u) * TILE_H + (min(yhi, last * TILE_H + TILE_H - 1u) - last * TILE_H + 1u);
+    }
+    return o;
+}
+__device__ __forceinline__ uint32_t owned_row_at(const Frame &f, const OwnedRows &o, uint32_t i) {
+    if (i < o.first_n) { return o.first_y + i; }
+    const uint32_t j = i - o.first_n;
+    return (o.next_a + (j / TILE_H) * f.row_stride) * TILE_H + j % TILE_H;
+}
+
 struct TileRange { uint32_t tx0, tx1, a0, a1; bool empty; };   // tile columns and ABSOLUTE tile rows, clamped to the band
 
 __device__ __forceinline__ TileRange tile_range(const Frame &f, uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax) {
@@ -1238,7 +1264,7 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
             const uint4 head = f.head[(size_t)view * f.setup_cap + g0 + tid];
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
-            if (is_flat_bbox(f, xmin, xmax, ymin, ymax) && ylo <= yhi) { rows = yhi - ylo + 1u; }
+            if (is_flat_bbox(f, xmin, xmax, ymin, ymax) && ylo <= yhi) { rows = owned_pixel_rows(f, ylo, yhi).count; }
         }
         uint32_t incl = rows;   // block-wide inclusive scan
 #pragma unroll
@@ -1257,9 +1283,8 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
             while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_pref[mid] <= i) { lo = mid; } else { hi = mid; } }
             const uint32_t slot = g0 + lo;
             const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
-            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu;
-            const uint32_t y = max(ymin, f.y0) + (i - s_pref[lo]), a = y / TILE_H;
-            if (!owns_row(f, a)) { continue; }
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+            const uint32_t y = owned_row_at(f, owned_pixel_rows(f, max(ymin, f.y0), min(ymax, f.y1 - 1u)), i - s_pref[lo]), a = y / TILE_H;
             const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
             const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
             const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
