@@ -345,7 +345,7 @@ def main():
     }
 
     cpu_baseline = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # reported baseline: rank 0 at N = 1 only
         cores = affinity_cores()
         sample = min(F, args.cpu_sample or max(24, 3 * cores))
         c = cpu_reference_fps(data_bin, W, H, F, sample, cores)
