@@ -1,12 +1,22 @@
-// kernels.cu — hand-written sm_100a kernels of the frame pipeline.
+// kernels.cu — hand-written sm_100a kernels of the frame pipeline (DESIGN.md section 5).
 //
-//   vertex_stage       K1  model/view/projection over planar float4 position streams   (render.cpp:285-289)
-//   triangle_setup     K2  gather, near reject, near-plane clip (0/1/2 out), cull, setup,
-//                          warp-ballot + block-scan compaction                          (render.cpp:297-359, 212-262)
-//   (setup) + bin_big  K3  sort-middle binning, single pass into fixed-capacity tile lists (no reference counterpart)
-//   tile_raster        K4  per-tile exact barycentric walk + depth test in registers, deferred
-//                          perspective-correct shading + rip-map fetch, colour tile in shared
-//                          memory, cp.async.bulk (TMA) write-out                        (render.cpp:360-382, 124-132)
+// Small scenes (2T <= 4096), two launches per frame:
+//   geometry_small     one CTA per view: vertex stage, classify, clip, setup            (render.cpp:285-359, 212-262)
+//   tile_raster        per 64x32 tile: exact barycentric walk + depth in registers, deferred perspective-correct
+//                      shading + rip-map fetch, colour tile in shared memory, cp.async.bulk (TMA) write-out
+//                                                                                        (render.cpp:360-382, 124-132)
+// General path (visibility buffer of 64-bit depth|order keys), six launches per frame:
+//   vertex_stage       K1   model/view/projection over planar float4 position streams   (render.cpp:285-289)
+//   triangle_classify  K2a  near reject / straddle / cull with warp-ballot compaction; unclipped triangles under 16x16
+//                           pixels are walked right here, record-free                    (render.cpp:297-317, 360-382)
+//   triangle_setup     K2b  gather, near-plane clip (0/1/2 out), setup records, block-scan compaction, inline binning
+//                                                                                        (render.cpp:297-359, 212-262)
+//   post_setup         K3   cooperative binning of the largest triangles, flat row walk of recorded triangles under
+//                           128x128, tile work queue + overflow record (no reference counterpart)
+//   tile_raster_queue  K4   tile kernel over (tile, chunk) items for triangles over 128 pixels
+//   shade_tiles        K5   visibility buffer -> colour: per 32x32 block, distinct triangles set up once, one covered
+//                           pixel per lane; clears the keys; optional fused frame assembly into peer frames
+//                                                                                        (render.cpp:363-372, 339-359, 124-132)
 //
 // PARITY RULES: this translation unit is compiled with -fmad=false -prec-div=true
 // -prec-sqrt=true -ftz=false; every expression is written in the reference's evaluation order so

@@ -71,6 +71,7 @@ EXPORTS = [
     "s3r_render_device", "s3r_finish", "s3r_render_host", "s3r_get_stats", "s3r_dump_raster_vertices",
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_render_device_rows", "s3r_tile_height",
+    "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
 ]
 
 
