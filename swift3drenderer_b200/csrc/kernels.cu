@@ -983,6 +983,11 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         list = f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap + e0;
     }
 
+    if (DIRECT && n == 0u) {
+        // nothing reaches this tile: it is background (render.cpp:282) — straight to the write-out
+#pragma unroll
+        for (int j = 0; j < SEG; j++) { sh.k.colour[row][seg * SEG + j] = kBackground; }
+    } else {
     float depth[SEG], bw0[SEG], bw1[SEG], bw2[SEG];
     uint32_t win[SEG];
 #pragma unroll
@@ -1157,6 +1162,7 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         }
         sh.k.colour[pr][pc] = rgb;
     }
+    }   // tile with triangles
 
     // ---- write-out -------------------------------------------------------------------------
     const uint32_t cols = min((uint32_t)TILE_W, f.W - tx0);
