@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <string>
 #include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/render.h"
@@ -426,7 +427,7 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
 static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uint32_t W, uint32_t H, uint32_t y0,
                         uint32_t y1, uint32_t *dev_out, cudaStream_t s, int raster_bands = 1,
                         uint32_t *band_rows = nullptr, bool packed24 = false, uint32_t row_stride = 1,
-                        uint32_t row_phase = 0) {
+                        uint32_t row_phase = 0, const std::function<int(int)> *after_band = nullptr) {
     Frame f;
     memset(&f, 0, sizeof(f));
     f.tiles_x = (W + TILE_W - 1) / TILE_W;
@@ -522,6 +523,9 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
                 const uint32_t end_row = (f.tile_row0 + f.raster_row0 + f.raster_rows) * TILE_H;
                 band_rows[b] = std::min(y1, std::max(y0, end_row)) - y0;
             }
+            // the host path enqueues band b's device->host copy right here, before the next band's launch call,
+            // so that the link starts as early as the GPU allows
+            if (after_band) { int rc2 = (*after_band)(b); if (rc2) { return rc2; } }
         }
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t2[slot], s)); r->slot_timed[slot] = true; }
@@ -684,32 +688,34 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
         if (!pinned) { int rc = ensure_staging(r, chunk_bytes + 64); if (rc) { return rc; } }
         for (int attempt = 0; attempt < 8; attempt++) {
             // ---- enqueue: geometry, banded raster, one D2H per band/slice on the copy stream -----
-            uint32_t band_rows[S3RRenderer::MAX_SLICES];
+            uint32_t band_rows[S3RRenderer::MAX_SLICES] = {};
             // band-pipelined raster/copy for the tile-kernel path only (see render_chunk)
             const int bands = nv == 1 && uses_direct_bin(r) ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
-            int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream, bands, band_rows, packed);
-            if (rc) { return rc; }
-            r->last_views = nv; r->last_W = W; r->last_H = H;
             std::vector<CopySlice> slices;
             uint8_t *target = pinned ? reinterpret_cast<uint8_t *>(dst) : r->staging;
             if (pinned) { plant_sentinels(dst, view_px * nv); }
             int n_ev = 0;
-            if (nv == 1) {
-                const int nb = std::max(1, std::min<int>(bands, (int)((y1 - 1) / TILE_H - y0 / TILE_H + 1)));
-                uint32_t row = 0;
-                for (int b = 0; b < nb; b++) {
-                    const size_t pa = (size_t)row * W, pe = (size_t)band_rows[b] * W;
-                    const size_t a = pa * bpp, e = pe * bpp;
-                    row = band_rows[b];
-                    CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[b], 0));
-                    if (e > a) {
-                        CUDA_TRY(cudaMemcpyAsync(target + a, reinterpret_cast<uint8_t *>(r->frame.p) + a, e - a,
-                                                 cudaMemcpyDeviceToHost, r->copy_stream));
-                        CUDA_TRY(cudaEventRecord(r->ev_copy[n_ev], r->copy_stream));
-                        slices.push_back(CopySlice{r->staging + a, reinterpret_cast<uint8_t *>(dst) + pa * 4, pe - pa});
-                        n_ev++;
-                    }
+            uint32_t row = 0;
+            const std::function<int(int)> copy_band = [&](int b) -> int {   // one view: band b's copy follows its raster launch
+                const size_t pa = (size_t)row * W, pe = (size_t)band_rows[b] * W;
+                const size_t a = pa * bpp, e = pe * bpp;
+                row = band_rows[b];
+                CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[b], 0));
+                if (e > a) {
+                    CUDA_TRY(cudaMemcpyAsync(target + a, reinterpret_cast<uint8_t *>(r->frame.p) + a, e - a,
+                                             cudaMemcpyDeviceToHost, r->copy_stream));
+                    CUDA_TRY(cudaEventRecord(r->ev_copy[n_ev], r->copy_stream));
+                    slices.push_back(CopySlice{r->staging + a, reinterpret_cast<uint8_t *>(dst) + pa * 4, pe - pa});
+                    n_ev++;
                 }
+                return S3R_OK;
+            };
+            int rc = render_chunk(r, cams + 12 * (size_t)v0, nv, W, H, y0, y1, r->frame.p, r->stream, bands, band_rows, packed, 1, 0,
+                                  nv == 1 ? &copy_band : nullptr);
+            if (rc) { return rc; }
+            r->last_views = nv; r->last_W = W; r->last_H = H;
+            if (nv == 1) {
+                // (copies already enqueued band by band)
             } else {
                 CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[0], 0));
                 const size_t total_px = view_px * nv;
