@@ -817,7 +817,6 @@ struct RasterShared {
     union {                                               // 32 KB
         struct {
             float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];   // big triangles: exact weights at each 8-pixel segment start
-            float rowstart[BATCH][TILE_H][3];                 // ... and at the start of each of their rows (x = xmin)
             SetupVis batch[BATCH];
         } big;
         uint4 state[TILE_W * TILE_H];                     // later: per-pixel winners (w0, w1, w2, slot) for shading
@@ -1019,37 +1018,21 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                     reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.bigq[base + b])[q];
             }
             __syncthreads();
-            // stage A1: the row-start weights (render.cpp:378-379) of every batch triangle for this tile's rows.  One
-            // thread per (triangle, component): a single exact jump from the triangle's own ymin to its first row in
-            // the tile, then true additions row by row — rows are consecutive, so only the first one needs a jump.
-            if (tid < nb * 3u) {
-                const uint32_t b = tid / 3u, c = tid % 3u;
-                const SetupVis &v = sh.u.big.batch[b];
-                const uint32_t y_first = max(ty0, (uint32_t)v.ymin), y_last = min(ty0 + TILE_H - 1u, (uint32_t)v.ymax);
-                if (y_first <= y_last) {
-                    const float d = v.dy[c];
-                    float w = walk_near(v.wstart[c], d, y_first - v.ymin);
-                    for (uint32_t yy = y_first; ; yy++) {
-                        sh.u.big.rowstart[b][yy - ty0][c] = w;
-                        if (yy == y_last) { break; }
-                        w = add_rn(w, d);
-                    }
-                }
-            }
-            __syncthreads();
-            // stage A2: exact weights at the first walked pixel of every (triangle, row, segment).  One work item per
-            // (triangle, row, component): from the row start, get to the tile's first column (true steps when it is
-            // near, the exact jump otherwise — render.cpp:374), then true steps through the tile, dropping the value
-            // at every 8-pixel segment boundary.
+            // stage A: exact weights at the first walked pixel of every (triangle, row, segment).  One work item per
+            // (triangle, component, row), a warp holding the 32 rows of one (triangle, component) — neighbouring rows take
+            // nearly the same path through the exact jump, so a warp does not serialise over components.  Each item goes
+            // from the triangle's wstart down to its row (render.cpp:378-379), then along the row to the tile's first
+            // column (render.cpp:374) — true steps when the target is near, the exact jump otherwise — and then takes
+            // true steps through the tile, dropping the value at every 8-pixel segment boundary.
             for (uint32_t item = tid; item < nb * (TILE_H * 3u); item += RASTER_THREADS) {
-                const uint32_t b = item / (TILE_H * 3u), rc = item % (TILE_H * 3u), r = rc / 3u, c = rc % 3u;
+                const uint32_t b = item / (TILE_H * 3u), rc = item % (TILE_H * 3u), c = rc / TILE_H, r = rc % TILE_H;
                 const SetupVis &v = sh.u.big.batch[b];
                 const uint32_t yy = ty0 + r;
                 if (yy < v.ymin || yy > v.ymax) { continue; }
                 const uint32_t xs = max(tx0, (uint32_t)v.xmin), xe = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
                 if (xs > xe) { continue; }
                 const float d = v.dx[c];
-                float w = walk_near(sh.u.big.rowstart[b][r][c], d, xs - v.xmin);
+                float w = walk_near(walk_near(v.wstart[c], v.dy[c], yy - v.ymin), d, xs - v.xmin);
                 uint32_t x = xs, k = (xs - tx0) / SEG;
                 while (true) {
                     sh.u.big.segstart[b][r][k][c] = w;
