@@ -182,7 +182,8 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--frames", type=int, default=600, help="frames per step (the recorded fly-through)")
-    ap.add_argument("--views-per-launch", type=int, default=1, help="camera poses rendered per kernel launch set")
+    ap.add_argument("--views-per-launch", type=int, default=8,
+                    help="consecutive poses of the recorded path rendered per launch set (multi-view batch, s3r_render_device)")
     ap.add_argument("--ring", type=int, default=8, help="device-resident output frames kept (ring > L2)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 3 per core, >= 24)")
     ap.add_argument("--no-e2e", action="store_true")

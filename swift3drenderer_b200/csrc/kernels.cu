@@ -1038,7 +1038,13 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                     sh.u.big.segstart[b][r][k][c] = w;
                     const uint32_t next = tx0 + (k + 1u) * SEG;
                     if (next > xe) { break; }
-                    for (; x < next; x++) { w = add_rn(w, d); }
+                    if (next - x == (uint32_t)SEG) {   // a whole segment: eight dependent additions, no loop control
+#pragma unroll
+                        for (int j = 0; j < SEG; j++) { w = add_rn(w, d); }
+                        x = next;
+                    } else {
+                        for (; x < next; x++) { w = add_rn(w, d); }
+                    }
                     k++;
                 }
             }
@@ -1149,6 +1155,8 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
 
     // ---- write-out -------------------------------------------------------------------------
     const uint32_t cols = min((uint32_t)TILE_W, f.W - tx0);
+    constexpr uint32_t ROWS_PER_WARP = TILE_H / (RASTER_THREADS / 32);
+    static_assert(ROWS_PER_WARP * (RASTER_THREADS / 32) == TILE_H, "tile rows split evenly over the warps");
     if (f.out_packed24) {
         // host transport format: 3 bytes per pixel.  Pack each row of 64 pixels into 48 words
         // (reusing the dead per-pixel state), then bulk-copy 192-byte rows.
@@ -1167,11 +1175,14 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         if (f.use_tma) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            if (tid < TILE_H) {
-                const uint32_t yy = ty0 + tid;
+            // the bulk copy takes uniform operands, so a warp issues its lanes' copies one after the other: four rows per
+            // warp on all eight warps instead of 32 rows on one
+            const uint32_t srow = (tid >> 5) * ROWS_PER_WARP + (tid & 31u);
+            if ((tid & 31u) < ROWS_PER_WARP) {
+                const uint32_t yy = ty0 + srow;
                 if (yy >= f.y0 && yy < f.y1) {
                     uint8_t *dst = out8 + (out_row(f, yy, tile_a) * f.W + tx0) * 3u;
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + tid * PW);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + srow * PW);
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(dst), "r"(src), "r"(cols * 3u) : "memory");
                 }
@@ -1195,11 +1206,12 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         // make the generic-proxy writes to the colour tile visible to the async (TMA) proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tid < TILE_H) {
-            const uint32_t yy = ty0 + tid;
+        const uint32_t srow = (tid >> 5) * ROWS_PER_WARP + (tid & 31u);   // four rows per warp, see above
+        if ((tid & 31u) < ROWS_PER_WARP) {
+            const uint32_t yy = ty0 + srow;
             if (yy >= f.y0 && yy < f.y1) {
                 uint32_t *dst = out + out_row(f, yy, tile_a) * f.W + tx0;
-                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.k.colour[tid][0]);
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sh.k.colour[srow][0]);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"(cols * 4u) : "memory");
             }

@@ -10,10 +10,11 @@
 //
 // walk_jump(s, d, n) returns exactly the result of n sequential adds in O(#binades crossed):
 // while s stays inside one binade (same sign and exponent field) every add moves it by a constant
-// whole number of ulps once one rounding has happened inside that binade (round-to-nearest-even
-// settles the tie case after a single step), so the remaining steps inside the binade collapse
-// into one integer multiply-add on the bit pattern.  Steps that cross a binade boundary, zero or
-// the sign are taken as true additions.  Fixed points (|d| below half an ulp) end the walk early.
+// whole number of ulps, known from d's bits and the binade's exponent alone (round-to-nearest-even
+// needs an even mantissa first in the one binade where d ends in exactly half an ulp), so the steps
+// inside the binade collapse into one integer multiply-add on the bit pattern.  Steps that cross a
+// binade boundary, zero or the sign are taken as true additions.  Fixed points (d absorbed) end the
+// walk early.
 //
 // Host + device: the same inline function is compiled by g++ for the CPU unit test
 // (tests/test_walk_jump.py) and by nvcc for the kernels.
@@ -73,33 +74,48 @@ S3R_HD uint32_t div_small(uint32_t a, uint32_t b) {
 }
 
 // n sequential adds of d onto s, bit-exact.
+//
+// One loop iteration = one true addition (which also performs every binade, zero or sign crossing) followed by
+// a jump over all the steps that stay inside the binade the addition landed in.  Inside a binade with ulp u the
+// current value is M*u with an integer M, and the exact sum is (M + t)*u with t = |d| / u, the same for every M —
+// so each add moves M by q = nearest integer to t, whatever M is.  t comes from d's own bits (|d| = Md * 2^x, so
+// t = Md / 2^sh with sh = the exponent distance), hence no second and third probing addition.  Only the binade in
+// which t ends in exactly one half is special: round-to-nearest-even sends an odd M to the even neighbour first and
+// from an even M every step is the even one of the two candidates, q = k + (k & 1) with k = floor(t); an odd M there
+// just takes one more true addition.  The landing value stays strictly inside the binade (mantissa field >= 1
+// downwards: an exact sum just below 2^e is rounded on the finer grid underneath, so the floor itself may only be
+// reached by a true addition; <= 0x7FFFFF upwards), which also keeps every skipped intermediate inside it.
 S3R_HD float walk_jump(float s, float d, uint32_t n) {
-    if (n == 0) { return s; }
-    float prev = s;
-    float cur = add_rn(s, d);
-    --n;
+    const uint32_t bd = f2u(d);
+    const uint32_t ed = (bd >> 23) & 0xFFu;
+    const uint32_t md = (bd & 0x7FFFFFu) | (ed ? 0x800000u : 0u);   // |d| = md * 2^(max(ed, 1) - 150)
+    const int32_t edp = (int32_t)(ed ? ed : 1u);
+    float cur = s;
     while (n > 0) {
         const float nxt = add_rn(cur, d);
         --n;
-        const uint32_t bp = f2u(prev), bc = f2u(cur), bn = f2u(nxt);
-        if ((((bp ^ bc) | (bc ^ bn)) >> 23) == 0) { // prev, cur, nxt: same sign, same binade
-            const int32_t q = (int32_t)(bn - bc);    // settled increment in ulps (of the magnitude)
-            if (q == 0) { return nxt; }              // fixed point: every further add is absorbed
-            const uint32_t mant = bn & 0x7FFFFFu;
-            // Stay inside the binade.  Downwards the landing mantissa must remain >= 1: an exact sum
-            // just below 2^e is rounded on the finer grid of the binade underneath, so the bottom
-            // value itself may only be reached by a true addition.
-            const uint32_t room = q > 0 ? div_small(0x7FFFFFu - mant, (uint32_t)q)
-                                        : (mant ? div_small(mant - 1u, (uint32_t)(-q)) : 0u);
-            const uint32_t k = room < n ? room : n;
-            const uint32_t landed = bn + k * (uint32_t)q;
-            n -= k;
-            prev = u2f(landed - (uint32_t)q);
-            cur = u2f(landed);
-        } else {
-            prev = cur;
-            cur = nxt;
+        uint32_t bn = f2u(nxt);
+        if (bn == f2u(cur)) { return nxt; }       // absorbed: the state repeats, so does every further add
+        cur = nxt;
+        const uint32_t e = (bn >> 23) & 0xFFu;
+        const int32_t sh = (int32_t)(e ? e : 1u) - edp;   // ulp(cur) = 2^sh * ulp(d)
+        // sh <= 0: |d| spans the binade, true steps only.  sh >= 25: |d| is below half an ulp, the next addition is
+        // absorbed (or leaves the binade through its floor).  e == 255: inf / NaN, the next addition repeats it.
+        if (n == 0 || sh <= 0 || sh >= 25 || e == 255u) { continue; }
+        const uint32_t k0 = md >> sh, rem = md & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        uint32_t q = k0 + (rem > half ? 1u : 0u);
+        if (rem == half) {
+            if (bn & 1u) { continue; }            // tie binade, odd mantissa: one more true addition settles it
+            q = k0 + (k0 & 1u);
         }
+        if (q == 0) { continue; }
+        const uint32_t mant = bn & 0x7FFFFFu;
+        const bool up = ((bn ^ bd) >> 31) == 0u;  // same sign: the magnitude grows
+        const uint32_t room = up ? div_small(0x7FFFFFu - mant, q) : (mant ? div_small(mant - 1u, q) : 0u);
+        const uint32_t k = room < n ? room : n;
+        bn = up ? bn + k * q : bn - k * q;
+        n -= k;
+        cur = u2f(bn);
     }
     return cur;
 }

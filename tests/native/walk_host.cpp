@@ -20,7 +20,7 @@ static uint32_t rnd() {
 }
 
 // mode 0: barycentric-like (s in [-2,2], |d| ~ 1/extent); mode 1: random bit patterns with nearby
-// exponents; mode 2: ties (d = (k + 1/2) ulp(s)); mode 3: subnormal / tiny; returns mismatches.
+// exponents; mode 2: ties (d = (k + 1/2) ulp(s)); mode 3: subnormal / tiny; mode 4: binade edges with sparse deltas; returns mismatches.
 uint64_t walk_fuzz(uint32_t mode, uint64_t trials, uint32_t max_n, uint64_t seed, float *bad) {
     rng_state = seed * 0x9E3779B97F4A7C15ull + 12345;
     uint64_t mism = 0;
@@ -45,6 +45,16 @@ uint64_t walk_fuzz(uint32_t mode, uint64_t trials, uint32_t max_n, uint64_t seed
             float k = (float)(rnd() % 9);
             d = (k + 0.5f) * ulp * ((rnd() & 1) ? 1.f : -1.f);
             if (rnd() & 1) { d *= 0.5f; }
+        } else if (mode == 4) {
+            // binade edges and sparse deltas: s within a few ulps of a power of two (either side, either sign), d with
+            // few significant bits at every exponent distance down to full absorption (ties in every binade)
+            uint32_t e = 90 + rnd() % 60;
+            uint32_t edge = (rnd() & 1) ? (rnd() % 5) : (0x7FFFFFu - rnd() % 5);
+            uint32_t bs = (rnd() & 0x80000000u) | (e << 23) | edge;
+            uint32_t keep = 1 + rnd() % 4;
+            uint32_t mask = ~((1u << (23 - keep)) - 1u) & 0x7FFFFFu;
+            uint32_t bd = (rnd() & 0x80000000u) | ((e - rnd() % 30) << 23) | (rnd() & mask);
+            s = s3r::u2f(bs); d = s3r::u2f(bd);
         } else {
             uint32_t bs = (rnd() & 0x80FFFFFFu) & 0x81FFFFFFu;
             uint32_t bd = (rnd() & 0x807FFFFFu) | ((rnd() % 3) << 23);

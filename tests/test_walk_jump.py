@@ -24,7 +24,7 @@ def walk_lib(tmp_path_factory):
     return lib
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("max_n", [8, 64, 4096])
 def test_fuzz_against_sequential_adds(walk_lib, mode, max_n):
     bad = np.zeros(5, np.float32)
