@@ -124,7 +124,7 @@ S3R_API uint32_t s3r_tile_height(void);
  *   s3r_set_peer_frames    the destinations of the following s3r_render_device / _rows calls (n = 0
  *                          switches back to `dev_out`, which may be NULL while destinations are set).
  * The caller orders frames across ranks (a barrier / tiny all-reduce per frame, or a ring of frames).
- * General path only (scenes over 2048 triangles); other scenes return S3R_E_ARG while destinations are set. */
+ * General path only (scenes over 1920 triangles); other scenes return S3R_E_ARG while destinations are set. */
 S3R_API int s3r_peer_frame_alloc(S3RRenderer *r, uint64_t bytes, void **dev_ptr, unsigned char ipc_handle_out[64]);
 S3R_API int s3r_peer_frame_open(S3RRenderer *r, const unsigned char ipc_handle[64], void **dev_ptr);
 S3R_API int s3r_peer_frame_release(S3RRenderer *r, void *dev_ptr);   /* frees (own) or unmaps (opened) */
@@ -150,7 +150,7 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *          "pin_host" (1 = cudaHostRegister the caller's frame buffers; default 0 — only for callers that
  *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
  *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
- *          "fused_small" (1 = one fused geometry CTA per view for scenes of <= 4096 triangles, default),
+ *          "fused_small" (1 = one fused geometry CTA per view for scenes of at most 1920 triangles, default),
  *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/
  *          copy pipeline depth of host renders, default 8), "copy_threads" (staging -> caller copy workers),
  *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */

@@ -21,6 +21,7 @@
 // PARITY RULES: this translation unit is compiled with -fmad=false -prec-div=true
 // -prec-sqrt=true -ftz=false; every expression is written in the reference's evaluation order so
 // that each binary32 intermediate equals the CPU's.  Do not "simplify" arithmetic here.
+#include <type_traits>
 #include "pipeline.cuh"
 #include "walk.cuh"
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ float walk_near(float s, float d, uint32_t n) {
     return s;
 }
 
-constexpr uint32_t WON = 0x80000000u;   // mark: this small triangle passed a depth pre-check in pass 1
+// mark on a tile-list entry: this small triangle passed a depth pre-check in pass 1 (top bit of the entry type)
 constexpr uint32_t SMALL_MAX = 16;      // triangles whose whole bbox is narrower and lower than this take the per-triangle path
 
 // ------------------------------------------------------------------------------------------------
@@ -818,6 +819,7 @@ struct RasterShared {
         struct {
             float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];   // big triangles: exact weights at each 8-pixel segment start
             SetupVis batch[BATCH];
+            uint32_t bigq[RASTER_THREADS];                    // big triangles found in the current 256-entry chunk
         } big;
         uint4 state[TILE_W * TILE_H];                     // later: per-pixel winners (w0, w1, w2, slot) for shading
     } u;
@@ -825,10 +827,12 @@ struct RasterShared {
         unsigned long long keys[TILE_W * TILE_H];         // small triangles: depth << 32 | ~order, atomicMax
         uint32_t colour[TILE_H][TILE_W];                  // later: the colour tile, source of the bulk write-out
     } k;
-    uint32_t slots[SORT_CAP];                             // 16 KB: this tile's triangles when collected in-kernel (direct_bin)
-    uint32_t bigq[RASTER_THREADS];                        // big triangles found in the current 256-entry chunk
+    uint16_t slots[SORT_CAP];                             // 7.5 KB: this tile's triangles when collected in-kernel (direct_bin)
     uint32_t n_list, n_big, any_small;
 };
+// four tile_raster CTAs per SM: 4 x (dynamic + 1 KB reserved) must fit the 228 KB of an SM
+static_assert(sizeof(RasterShared) <= 56 * 1024, "RasterShared must leave room for four CTAs per SM");
+static_assert(SORT_CAP < 0x8000, "list entries are 15-bit slots plus the WON flag");
 
 __device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115-122
     i--; i |= i >> 1; i |= i >> 2; i |= i >> 4;
@@ -960,7 +964,9 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
     }
     __syncthreads();
     uint32_t n;
-    uint32_t *list;
+    using Entry = typename std::conditional<DIRECT, uint16_t, uint32_t>::type;   // in-kernel list (shared) / bin list (global)
+    constexpr Entry WON = DIRECT ? (Entry)0x8000u : (Entry)0x80000000u;
+    Entry *list;
     if (DIRECT) {
         // small scene: collect straight from the survivors' heads (bbox overlap clamped to the band, plus the
         // conservative outside test); at most SORT_CAP survivors exist by construction of this mode
@@ -970,16 +976,16 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             if (xmax >= tx0 && xmin < tx0 + TILE_W && ymax >= ylo_t && ymin < yhi_t) {
                 if (!tile_outside_triangle(f.vis[(size_t)view * f.setup_cap + slot], tx0, ylo_t, yhi_t)) {
-                    sh.slots[atomicAdd(&sh.n_list, 1u)] = slot;
+                    sh.slots[atomicAdd(&sh.n_list, 1u)] = (uint16_t)slot;
                 }
             }
         }
         __syncthreads();
         n = sh.n_list;
-        list = sh.slots;
+        list = reinterpret_cast<Entry *>(sh.slots);
     } else {
         n = e1 - e0;
-        list = f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap + e0;
+        list = reinterpret_cast<Entry *>(f.entries + ((size_t)view * f.tile_stride + tile) * f.tile_cap + e0);
     }
 
     if (DIRECT && n == 0u) {
@@ -1003,9 +1009,9 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
             const uint32_t bwid = (head.x >> 16) - (head.x & 0xFFFFu), bhgt = (head.y >> 16) - (head.y & 0xFFFFu);
             if (bwid < SMALL_MAX && bhgt < SMALL_MAX) {
                 sh.any_small = 1u;
-                if (walk_small<1>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh)) { list[i] = slot | WON; }
+                if (walk_small<1>(f, view, slot, head, tx0, ty0, ylo_t, yhi_t, sh)) { list[i] = (Entry)(slot | WON); }
             } else {
-                sh.bigq[atomicAdd(&sh.n_big, 1u)] = slot;
+                sh.u.big.bigq[atomicAdd(&sh.n_big, 1u)] = slot;
             }
         }
         __syncthreads();
@@ -1015,7 +1021,7 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
             if (tid < nb * 4u) {   // stage the batch's coverage records
                 const uint32_t b = tid >> 2, q = tid & 3u;
                 reinterpret_cast<uint4 *>(&sh.u.big.batch[b])[q] =
-                    reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.bigq[base + b])[q];
+                    reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.u.big.bigq[base + b])[q];
             }
             __syncthreads();
             // stage A: exact weights at the first walked pixel of every (triangle, row, segment).  One work item per
@@ -1059,7 +1065,7 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 float w0 = sh.u.big.segstart[b][row][seg][0], w1 = sh.u.big.segstart[b][row][seg][1],
                       w2 = sh.u.big.segstart[b][row][seg][2];
                 const float rz0 = v.rvz[0], rz1 = v.rvz[1], rz2 = v.rvz[2];
-                const uint32_t slot = sh.bigq[base + b], order = v.order;
+                const uint32_t slot = sh.u.big.bigq[base + b], order = v.order;
 #pragma unroll
                 for (int j = 0; j < SEG; j++) {
                     const uint32_t x = sx0 + j;
@@ -1115,7 +1121,7 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         for (uint32_t i = tid; i < n; i += RASTER_THREADS) {   // small triangles that ever led a pixel drop their weights where they won
             const uint32_t e = list[i];
             if (e & WON) {
-                const uint32_t slot = e & ~WON;
+                const uint32_t slot = e & (uint32_t)(Entry)~WON;
                 walk_small<2>(f, view, slot, f.head[(size_t)view * f.setup_cap + slot], tx0, ty0, ylo_t, yhi_t, sh);
             }
         }
@@ -1227,14 +1233,17 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster(const __grid_constant__ Frame f) {
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS) tile_raster(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     raster_one_tile<true>(f, *reinterpret_cast<RasterShared *>(smem_raw), blockIdx.z, blockIdx.x, blockIdx.y + f.raster_row0, 0u, 0u);
 }
 
 // General path: persistent CTAs pop (tile, chunk of its bin list) items from the queue post_setup built.  A tile with
 // a long list is shared by as many CTAs as it has chunks, so the busiest tile no longer sets the kernel's duration.
-__global__ void __launch_bounds__(RASTER_THREADS, 3) tile_raster_queue(const __grid_constant__ Frame f) {
+#ifndef S3R_QUEUE_CTAS
+#define S3R_QUEUE_CTAS 3
+#endif
+__global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_queue(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
     const uint32_t view = blockIdx.y;
@@ -1341,7 +1350,11 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
 constexpr uint32_t SHADE_B = 32;          // block edge in pixels
 constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_B;
 constexpr uint32_t SHADE_TAB = 2048;      // hash slots (load factor <= 0.5)
-constexpr uint32_t SHADE_TRIS = 256;      // triangle setups staged per pass (one per thread)
+#ifndef S3R_SHADE_CTAS
+#define S3R_SHADE_CTAS 3
+#endif
+constexpr int SHADE_CTAS = S3R_SHADE_CTAS;                  // shade_tiles CTAs per SM the launch bounds ask for
+constexpr uint32_t SHADE_TRIS = SHADE_CTAS >= 4 ? 192 : 256; // triangle setups staged per pass (one per thread; 192 keeps four CTAs within an SM's shared memory)
 constexpr uint32_t SHADE_WORDS = 47;      // words per staged setup (odd: distinct triangles fall into distinct banks)
 constexpr uint32_t SHADE_EMPTY = 0xFFFFFFFFu;
 
@@ -1355,7 +1368,7 @@ struct ShadeShared {
     uint32_t count, n_tri;
 };
 
-__global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+__global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ShadeShared &sh = *reinterpret_cast<ShadeShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tid = threadIdx.x, lane = lane_id();
@@ -1422,7 +1435,7 @@ __global__ void __launch_bounds__(256, 3) shade_tiles(const __grid_constant__ Fr
 #pragma unroll 1
         for (uint32_t tb = 0; tb < n_tri; tb += SHADE_TRIS) {
             // ---- 2. setups of this pass's triangles ------------------------------------------------
-            if (tb + tid < n_tri) {
+            if (tid < SHADE_TRIS && tb + tid < n_tri) {
                 const uint32_t order = sh.tri_order[tb + tid];
                 uint32_t *dst = sh.setup[tid];
                 bool direct = false;
@@ -1596,7 +1609,7 @@ int launch_raster(const Frame &f, cudaStream_t s) {
         return 1;
     }
     // general path (always one raster launch per frame): the queue holds every non-empty tile of the submission
-    tile_raster_queue<<<dim3((uint32_t)g_sm_count * 3u, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+    tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
     // general path: the tile kernel only resolved the big triangles; shade the rows it covered
     uint32_t row0, nrows;
     if (f.row_stride == 1u) {

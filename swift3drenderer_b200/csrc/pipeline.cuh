@@ -36,7 +36,14 @@ constexpr int SEG = 8;                      // pixels per thread in the visibili
 constexpr int SEGS_PER_ROW = TILE_W / SEG;
 static_assert(SEGS_PER_ROW * TILE_H == RASTER_THREADS, "one thread per 8-pixel segment");
 constexpr int BATCH = 8;                    // triangles staged per visibility batch
-constexpr int SORT_CAP = 4096;              // survivors a small scene may have (in-kernel per-tile collection)
+#ifndef S3R_SORT_CAP
+#define S3R_SORT_CAP 3840
+#endif
+#ifndef S3R_RASTER_CTAS
+#define S3R_RASTER_CTAS 4
+#endif
+constexpr int SORT_CAP = S3R_SORT_CAP;      // survivors a small scene may have (in-kernel per-tile collection)
+constexpr int RASTER_CTAS = S3R_RASTER_CTAS; // tile_raster CTAs per SM the launch bounds ask for
 constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are binned cooperatively
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
 constexpr int MAX_PEERS = 16;              // destinations of the fused frame assembly (ranks of one NVSwitch domain)

@@ -503,7 +503,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
     f.direct_bin = uses_direct_bin(r) ? 1 : 0;
-    if (f.n_peers && (f.direct_bin || packed24)) { return fail(S3R_E_ARG, "peer frames need the general path (scene over 2048 triangles) and device output"); }
+    if (f.n_peers && (f.direct_bin || packed24)) { return fail(S3R_E_ARG, "peer frames need the general path (scene over 1920 triangles) and device output"); }
     f.direct_small = !f.direct_bin && r->opt_direct_small ? 1 : 0;
     f.flat_max = (uint32_t)r->opt_flat_max;
     f.rs_magic = row_stride > 1 ? (uint32_t)((1ull << 32) / row_stride) + 1u : 0u;

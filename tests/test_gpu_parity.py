@@ -360,7 +360,7 @@ def test_interleaved_tile_rows_reassemble_to_the_whole_frame(gpu_renderer, rende
 
 
 def _general_scenes():
-    """Scenes that take the general (visibility-buffer) path: > 2048 triangles."""
+    """Scenes that take the general (visibility-buffer) path: > 1920 triangles."""
     return (("clip", lambda: S.clip_stress_scene(3000), "spin", 9),          # straddlers, spawned, big and mid-size triangles
             ("dense", lambda: S.icosahedron_field(20000, seed=9, extent=40, r_range=(0.3, 1.0)), "spin", 5))  # tiny triangles
 
