@@ -1241,7 +1241,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS) tile_raster(const
 // General path: persistent CTAs pop (tile, chunk of its bin list) items from the queue post_setup built.  A tile with
 // a long list is shared by as many CTAs as it has chunks, so the busiest tile no longer sets the kernel's duration.
 #ifndef S3R_QUEUE_CTAS
-#define S3R_QUEUE_CTAS 3
+#define S3R_QUEUE_CTAS 4
 #endif
 __global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_queue(const __grid_constant__ Frame f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1351,7 +1351,7 @@ constexpr uint32_t SHADE_B = 32;          // block edge in pixels
 constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_B;
 constexpr uint32_t SHADE_TAB = 2048;      // hash slots (load factor <= 0.5)
 #ifndef S3R_SHADE_CTAS
-#define S3R_SHADE_CTAS 3
+#define S3R_SHADE_CTAS 4
 #endif
 constexpr int SHADE_CTAS = S3R_SHADE_CTAS;                  // shade_tiles CTAs per SM the launch bounds ask for
 constexpr uint32_t SHADE_TRIS = SHADE_CTAS >= 4 ? 192 : 256; // triangle setups staged per pass (one per thread; 192 keeps four CTAs within an SM's shared memory)
