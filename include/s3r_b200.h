@@ -151,6 +151,8 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
  *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
  *          "fused_small" (1 = one fused geometry CTA per view for scenes of at most 1920 triangles, default),
+ *          "spans" (1 = small scenes, whole-frame launches: the row walks of the largest survivors are done once per
+ *          frame by span_walk instead of by exact jumps in every tile, default),
  *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/
  *          copy pipeline depth of host renders, default 8), "copy_threads" (staging -> caller copy workers),
  *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */

@@ -808,6 +808,60 @@ __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Fr
         if (c[C_OVERFLOW]) { atomicOr(f.sticky + 0, c[C_OVERFLOW]); }
         atomicMax(f.sticky + 1, c[C_SETUPS]);
     }
+    if (f.coltab && tid < 32u) {
+        // the first SPAN_MAX survivors (in slot order) with a box of SPAN_MIN pixels or more get a checkpoint table
+        const uint32_t n = f.counters[view * C_COUNT + C_OVERFLOW] ? 0u
+                         : min(f.counters[view * C_COUNT + C_SETUPS], min(f.setup_cap, (uint32_t)SORT_CAP));
+        uint32_t count = 0;
+        for (uint32_t base = 0; base < n && count < SPAN_MAX; base += 32u) {
+            const uint32_t slot = base + tid;
+            bool q = false;
+            if (slot < n) {
+                const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+                q = (head.x >> 16) - (head.x & 0xFFFFu) >= SPAN_MIN || (head.y >> 16) - (head.y & 0xFFFFu) >= SPAN_MIN;
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, q);
+            const uint32_t idx = count + __popc(m & ((1u << tid) - 1u));
+            if (q && idx < SPAN_MAX) { f.span_slots[view * SPAN_MAX + idx] = slot; }
+            count += __popc(m);
+        }
+        if (tid == 0) { f.counters[view * C_COUNT + C_SPANS] = min(count, SPAN_MAX); }
+    }
+}
+
+// Small scenes, once per frame: the checkpoint tables of the (at most SPAN_MAX) largest survivors.  One thread per
+// (span, component, pixel row): the row's start weight by the exact jump from the triangle's wstart (render.cpp:378-379),
+// then the reference's own walk along the row (render.cpp:374) — true additions from xmin to xmax — dropping the
+// weight at the first walked pixel of every tile column.  Every tile's stage A then loads what it would otherwise
+// reach with two exact jumps per (row, component); the values are the same bits.  Threads of a warp are consecutive
+// rows, so every store (and every later load) is one coalesced line.
+__global__ void __launch_bounds__(128) span_walk(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.z, k = blockIdx.y / 3u, c = blockIdx.y % 3u, y = blockIdx.x * 128u + threadIdx.x;
+    if (k >= f.counters[view * C_COUNT + C_SPANS] || y >= f.H) { return; }
+    const uint32_t a = y / TILE_H;   // rows of tile rows this submission does not rasterise are never read
+    if (!owns_row(f, a) || a * TILE_H >= f.y1 || (a + 1u) * TILE_H <= f.y0) { return; }
+    const uint32_t slot = f.span_slots[view * SPAN_MAX + k];
+    const SetupVis *v = f.vis + (size_t)view * f.setup_cap + slot;
+    const uint32_t xmin = v->xmin, xmax = v->xmax, ymin = v->ymin, ymax = v->ymax;
+    if (y < ymin || y > ymax) { return; }
+    const float d = v->dx[c];
+    float w = walk_near(v->wstart[c], v->dy[c], y - ymin);
+    const uint32_t t0 = xmin / TILE_W, t1 = xmax / TILE_W;
+    float *tab = f.coltab + ((((size_t)view * SPAN_MAX + k) * f.tiles_x + t0) * 3u + c) * f.span_h + y;
+    uint32_t x = xmin;
+    for (uint32_t t = t0; ; t++) {
+        *tab = w;
+        if (t == t1) { break; }
+        const uint32_t next = (t + 1u) * TILE_W;
+        if (next - x == (uint32_t)TILE_W) {
+#pragma unroll 16
+            for (int j = 0; j < TILE_W; j++) { w = add_rn(w, d); }
+        } else {
+            for (uint32_t j = x; j < next; j++) { w = add_rn(w, d); }
+        }
+        x = next;
+        tab += 3u * f.span_h;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -820,6 +874,7 @@ struct RasterShared {
             float segstart[BATCH][TILE_H][SEGS_PER_ROW][3];   // big triangles: exact weights at each 8-pixel segment start
             SetupVis batch[BATCH];
             uint32_t bigq[RASTER_THREADS];                    // big triangles found in the current 256-entry chunk
+            uint32_t span[BATCH];                             // the batch triangles' checkpoint tables (span_walk), NO_TRI = none
         } big;
         uint4 state[TILE_W * TILE_H];                     // later: per-pixel winners (w0, w1, w2, slot) for shading
     } u;
@@ -1022,6 +1077,13 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 const uint32_t b = tid >> 2, q = tid & 3u;
                 reinterpret_cast<uint4 *>(&sh.u.big.batch[b])[q] =
                     reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.u.big.bigq[base + b])[q];
+            } else if (tid >= 32u && tid < 32u + nb) {   // ... and find their checkpoint tables, if they have one
+                uint32_t span = NO_TRI;
+                if (DIRECT && f.coltab) {
+                    const uint32_t n_span = f.counters[view * C_COUNT + C_SPANS], slot = sh.u.big.bigq[base + tid - 32u];
+                    for (uint32_t k = 0; k < n_span; k++) { if (f.span_slots[view * SPAN_MAX + k] == slot) { span = k; } }
+                }
+                sh.u.big.span[tid - 32u] = span;
             }
             __syncthreads();
             // stage A: exact weights at the first walked pixel of every (triangle, row, segment).  One work item per
@@ -1038,7 +1100,10 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 const uint32_t xs = max(tx0, (uint32_t)v.xmin), xe = min(tx0 + TILE_W - 1u, (uint32_t)v.xmax);
                 if (xs > xe) { continue; }
                 const float d = v.dx[c];
-                float w = walk_near(walk_near(v.wstart[c], v.dy[c], yy - v.ymin), d, xs - v.xmin);
+                const uint32_t span = sh.u.big.span[b];
+                float w = span != NO_TRI   // walked once for the whole frame by span_walk: the same bits, one load
+                    ? f.coltab[((((size_t)view * SPAN_MAX + span) * f.tiles_x + tile_x) * 3u + c) * f.span_h + yy]
+                    : walk_near(walk_near(v.wstart[c], v.dy[c], yy - v.ymin), d, xs - v.xmin);
                 uint32_t x = xs, k = (xs - tx0) / SEG;
                 while (true) {
                     sh.u.big.segstart[b][r][k][c] = w;
@@ -1627,7 +1692,9 @@ int launch_raster(const Frame &f, cudaStream_t s) {
 
 int launch_geometry_small(const Frame &f, cudaStream_t s) {
     geometry_small<<<f.n_views, 256, 0, s>>>(f);
-    return 1;
+    if (!f.coltab) { return 1; }
+    span_walk<<<dim3(ceil_div(f.H, 128u), SPAN_MAX * 3u, f.n_views), 128, 0, s>>>(f);
+    return 2;
 }
 
 // test hook: the device build of walk_jump on arrays (tests compare it with sequential adds)

@@ -48,6 +48,8 @@ constexpr uint32_t BIG_TILES = 16;          // triangles over more tiles are bin
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu;
 constexpr int MAX_PEERS = 16;              // destinations of the fused frame assembly (ranks of one NVSwitch domain)
 constexpr uint32_t RASTER_CHUNK = 64;       // bin-list entries one tile-kernel work item resolves (general path)
+constexpr uint32_t SPAN_MAX = 8;            // small scenes: survivors whose tile-column checkpoints are walked once per frame (span_walk)
+constexpr uint32_t SPAN_MIN = 128;          // ... those whose box is at least this wide or high
 
 constexpr float kNear = 0.1f;                   // render-cpp/render.cpp:89
 constexpr float kScale = 0x1.0a2c9ap-5f;        // near * tanf(fov / 2), render.cpp:92 (binary32 value of the reference build)
@@ -59,6 +61,7 @@ enum Counter : uint32_t {
     C_QHEAD = 12,    // ... and how many of them have been taken
     C_DONE = 10,     // CTAs of post_setup that have finished (the last one closes the frame's geometry)
     C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
+    C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
     C_COUNT = 16
 };
 
@@ -134,12 +137,17 @@ struct Frame {
     int direct_small;   // 1 (general path): small unclipped survivors are walked by the classify kernel and shaded from the raw scene
     int direct_bin;     // 1: no bin arrays — every raster CTA collects its triangles from the setup list itself
     int out_packed24;   // 1: `out` is a byte buffer with 3 bytes per pixel (B, G, R), used for host transport
+    // small scenes, whole-frame launches: exact weights of the largest survivors at the first walked pixel of every
+    // (tile column, pixel row), written once per frame by span_walk and read by every tile's stage A
+    float *coltab;          // [views][SPAN_MAX][tiles_x][3][span_h], null = every tile takes the exact jump itself
+    uint32_t *span_slots;   // [views][SPAN_MAX] survivor slots that have a table (counters[C_SPANS] of them)
+    uint32_t span_h;        // H rounded up to a multiple of 32
 };
 
 // Launchers (kernels.cu).  Each returns the number of kernels it enqueued.
 int launch_geometry(const Frame &f, cudaStream_t s);   // reset, vertex stage, clip/cull/setup, binning
 int launch_raster(const Frame &f, cudaStream_t s);     // per-tile visibility + shading + write-out
-int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry
+int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
 cudaError_t configure_kernels();
 void launch_walk_jump(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count, cudaStream_t st);
 

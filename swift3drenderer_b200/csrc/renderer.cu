@@ -87,6 +87,8 @@ struct S3RRenderer {
     DevBuf<uint32_t> entries;
     DevBuf<float> cams;
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
+    DevBuf<float> coltab;     // small scenes: tile-column checkpoints of the largest survivors (span_walk)
+    DevBuf<uint32_t> span_slots;
     // submission ring: pinned camera staging + events, so the host can run RING chunks ahead
     static constexpr int RING = 16;
     float *cams_pinned = nullptr;     // RING x views_cap x 12
@@ -109,7 +111,7 @@ struct S3RRenderer {
     uint8_t *staging = nullptr;
     size_t staging_bytes = 0;
     HostCopier *copier = nullptr;
-    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1;
+    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1, opt_spans = 1;
     std::vector<HostPin> pins;
     // fused frame assembly
     std::vector<void *> own_frames, opened_frames;
@@ -170,6 +172,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
+    r->coltab.release(); r->span_slots.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
     delete r->copier;
     if (r->sticky_host) { cudaFreeHost(r->sticky_host); }
@@ -507,6 +510,17 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.direct_small = !f.direct_bin && r->opt_direct_small ? 1 : 0;
     f.flat_max = (uint32_t)r->opt_flat_max;
     f.rs_magic = row_stride > 1 ? (uint32_t)((1ull << 32) / row_stride) + 1u : 0u;
+    if (f.direct_bin && r->opt_spans && raster_bands <= 1) {
+        // whole-frame launches of a small scene: the largest survivors' row walks are done once per frame (span_walk)
+        // instead of by exact jumps in every tile.  The banded host path keeps the jumps: its first band must not wait.
+        f.span_h = (H + 31u) & ~31u;
+        const size_t per_view = (size_t)SPAN_MAX * f.tiles_x * 3u * f.span_h;
+        if (per_view * r->views_cap * sizeof(float) <= (size_t)1 << 30) {
+            CUDA_TRY(r->coltab.ensure(per_view * r->views_cap));
+            CUDA_TRY(r->span_slots.ensure((size_t)SPAN_MAX * r->views_cap));
+            f.coltab = r->coltab.p; f.span_slots = r->span_slots.p;
+        }
+    }
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
@@ -924,6 +938,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "tma_store")) { r->opt_tma = value != 0; return S3R_OK; }
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
+    if (!strcmp(name, "spans")) { r->opt_spans = value != 0; return S3R_OK; }
     if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
         if (value < 16 || value > 65536) { return fail(S3R_E_ARG, "flat_max out of range"); }
         r->opt_flat_max = (int)value; return S3R_OK;

@@ -447,3 +447,49 @@ def test_fused_assembly_writes_rows_to_every_destination(gpu_renderer, renderer_
         gpu_renderer.set_peer_frames([])
         gpu_renderer.peer_frame_release(a)
         gpu_renderer.peer_frame_release(b)
+
+
+def test_span_tables_equal_in_tile_jumps_and_the_oracle(renderer_lib, oracle_port):
+    """Small scenes, device path: the checkpoint tables of the largest survivors (span_walk, one row walk per frame)
+    must give every tile exactly the weights its own exact jumps give — whole frames, bands, interleaved tile rows and
+    view batches, with more than SPAN_MAX large survivors in some frames (the rest keep jumping)."""
+    import torch
+    th = renderer_lib.tile_height()
+    r = renderer_lib.Renderer(0)
+    cases = ((S.shipped_scene(1), (0, 110, 150, 230, 345, 350, 500, 550), (1920, 1080)),
+             (S.shipped_scene(2, regular_floor=True), (40, 150), (1283, 721)),
+             (S.icosahedron_field(60, seed=12, extent=12, r_range=(2.0, 5.0)), (3, 9), (1920, 1080)))
+    for sc, frames, (W, H) in cases:
+        r.load_scene(sc)
+        osc = oracle_port.OracleScene(sc)
+        mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+        out = torch.zeros((len(frames), H, W), dtype=torch.int32, device="cuda:0")
+
+        def dev(views, **kw):
+            r.render_device(views, W, H, out.data_ptr(), **kw)
+            assert r.finish() is False
+            return out.cpu().numpy().view(np.uint32)
+
+        want = np.stack([osc.render(mats[f], W, H)["pixels"] for f in frames])
+        for spans in (1, 0):
+            r.set_option("spans", spans)
+            before = r.kernel_launches
+            got = dev(mats[list(frames)])                       # one batch of views
+            assert r.kernel_launches - before == (3 if spans else 2)
+            for i, f in enumerate(frames):
+                assert_same(got[i], want[i], f"spans={spans} batch frame {f} {W}x{H}")
+        r.set_option("spans", 1)
+        for f, w in zip(frames[:2], want[:2]):
+            assert_same(dev(mats[f])[0], w, f"single view frame {f}")
+            y0, y1 = H // 3 + 5, (2 * H) // 3 + 1               # a band that cuts tile rows
+            band = dev(mats[f], y0=y0, y1=y1)
+            assert_same(band.reshape(-1)[: (y1 - y0) * W].reshape(y1 - y0, W), w[y0:y1], f"band frame {f}")
+            frame = np.zeros((H, W), np.uint32)
+            for phase in range(3):
+                rows, frame_rows, buf_rows = renderer_lib.rows_layout(H, 3, phase, th)
+                buf = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
+                r.render_device_rows(mats[f], W, H, 3, phase, buf.data_ptr())
+                assert r.finish() is False
+                frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
+            assert_same(frame, w, f"interleaved rows frame {f}")
+    r.close()
