@@ -162,6 +162,13 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
 S3R_API int s3r_debug_walk(S3RRenderer *r, const float *start, const float *delta, const uint32_t *steps,
                            float *out, uint32_t count);
 
+/* Test hook: compares the shading chain's hand-scheduled IEEE division / reciprocal square root (csrc/exact_math.cuh)
+ * with the compiler's operators on the device.  mode 0: every binary32 bit pattern first .. first + count - 1 through
+ * 1/sqrt; mode 1: `count` seeded pseudo-random operand sets through the divisions.  result[0] = mismatches,
+ * result[1..4] = operands and values of the first one (bit patterns). */
+S3R_API int s3r_debug_exact_math(S3RRenderer *r, uint32_t mode, uint64_t first, uint64_t count, uint32_t seed,
+                                 uint64_t result[5]);
+
 /* Harness-only: resets the camera owned by updateAndRender (include/render.h) to the reference's
  * initial state so that the same Input script can be replayed; scene and buffers stay loaded. */
 S3R_API void s3r_dropin_reset(void);

@@ -24,6 +24,7 @@
 #include <type_traits>
 #include "pipeline.cuh"
 #include "walk.cuh"
+#include "exact_math.cuh"
 
 namespace s3r {
 
@@ -57,7 +58,7 @@ __device__ __forceinline__ float3 scale3(float3 a, float s) { return make_float3
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 // simd_fast_normalize as pinned by the oracle shim: v * (1 / sqrt(dot(v, v)))
 // (1.0f / x is the correctly rounded reciprocal, and so is __frcp_rn(x): same bits, fewer instructions)
-__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, __frcp_rn(__fsqrt_rn(dot3(a, a)))); }
+__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, inv_sqrt_rn(dot3(a, a))); }   // == __frcp_rn(__fsqrt_rn(.)), exact_math.cuh
 // EDGE_FUNCTION(a, b, c), render.cpp:9
 __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by, float cx, float cy) {
     return (cx - ax) * (ay - by) + (cy - ay) * (bx - ax);
@@ -898,7 +899,8 @@ __device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115
 __device__ __forceinline__ uint32_t shade_math(const Frame &f, float rz0, float rz1, float rz2, const SetupShade &s,
                                                float w0, float w1, float w2) {
     const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;
-    const float b0 = w0 / ooz, b1 = w1 / ooz, b2 = w2 / ooz;
+    float b0, b1, b2;
+    div3_rn(w0, w1, w2, ooz, b0, b1, b2);   // w / ooz (render.cpp:365), one reciprocal refinement for the three
     const float3 c0 = make_float3(s.cv[0], s.cv[1], s.cv[2]), c1 = make_float3(s.cv[3], s.cv[4], s.cv[5]),
                  c2 = make_float3(s.cv[6], s.cv[7], s.cv[8]);
     const float3 n0 = make_float3(s.n[0], s.n[1], s.n[2]), n1 = make_float3(s.n[3], s.n[4], s.n[5]),
@@ -1701,6 +1703,51 @@ int launch_geometry_small(const Frame &f, cudaStream_t s) {
 __global__ void walk_jump_kernel(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) { out[i] = walk_jump(s[i], d[i], n[i]); }
+}
+
+// test hook: exact_math.cuh against the compiler's IEEE operators.  mode 0: inv_sqrt_rn over every binary32 bit pattern
+// in [lo_bits, hi_bits]; mode 1: div3_rn over `count` pseudo-random operand sets (seeded), a quarter of them
+// with extreme mantissas.  result[0] = mismatches, result[1..4] = the first mismatch's operands / values (bit patterns).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void exact_math_kernel(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed,
+                                  unsigned long long *result) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (mode == 0) {
+            const float x = __uint_as_float((uint32_t)(lo + i));
+            const uint32_t got = __float_as_uint(inv_sqrt_rn(x)), want = __float_as_uint(__frcp_rn(__fsqrt_rn(x)));
+            if (got != want && !(got > 0x7f800000u && want > 0x7f800000u)) {
+                if (atomicAdd(result, 1ull) == 0ull) { result[1] = __float_as_uint(x); result[2] = got; result[3] = want; }
+            }
+        } else {
+            uint32_t h = mix32((uint32_t)i ^ seed) , g = mix32((uint32_t)(i >> 32) + h + 0x9e3779b9u);
+            uint32_t op[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                g = mix32(g + 0x85ebca6bu * (k + 1)); h = mix32(h ^ g);
+                uint32_t mant = g & 0x7FFFFFu;
+                const uint32_t sel = (h >> 8) & 15u;
+                if (sel == 0) { mant = 0x7FFFFFu; } else if (sel == 1) { mant = 0u; } else if (sel == 2) { mant = 0x7FFFFEu; } else if (sel == 3) { mant = 1u; }
+                const uint32_t e = 127u - 62u + (h >> 24) % 124u;   // a little beyond the guarded range on both sides
+                op[k] = (e << 23) | mant;
+            }
+            if (((h >> 3) & 63u) == 0u) { op[(h >> 12) & 3u] = 0u; }     // zeros take the fallback
+            const float a0 = __uint_as_float(op[0]), a1 = __uint_as_float(op[1]), a2 = __uint_as_float(op[2]), b = __uint_as_float(op[3]);
+            float q0, q1, q2;
+            div3_rn(a0, a1, a2, b, q0, q1, q2);
+            const float w0 = a0 / b, w1 = a1 / b, w2 = a2 / b;
+            const bool ok = __float_as_uint(q0) == __float_as_uint(w0) && __float_as_uint(q1) == __float_as_uint(w1) &&
+                            __float_as_uint(q2) == __float_as_uint(w2);
+            if (!ok && !(b == 0.f)) {
+                if (atomicAdd(result, 1ull) == 0ull) { result[1] = op[0]; result[2] = op[3]; result[3] = __float_as_uint(q0); result[4] = __float_as_uint(w0); }
+            }
+        }
+    }
+}
+
+void launch_exact_math(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed, unsigned long long *result,
+                       cudaStream_t st) {
+    exact_math_kernel<<<(uint32_t)g_sm_count * 8u, 256, 0, st>>>(mode, lo, count, seed, result);
 }
 
 void launch_walk_jump(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count, cudaStream_t st) {

@@ -149,6 +149,8 @@ int launch_geometry(const Frame &f, cudaStream_t s);   // reset, vertex stage, c
 int launch_raster(const Frame &f, cudaStream_t s);     // per-tile visibility + shading + write-out
 int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
 cudaError_t configure_kernels();
+void launch_exact_math(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed, unsigned long long *result,
+                       cudaStream_t st);
 void launch_walk_jump(const float *s, const float *d, const uint32_t *n, float *out, uint32_t count, cudaStream_t st);
 
 }  // namespace s3r

@@ -911,6 +911,20 @@ extern "C" int s3r_debug_walk(S3RRenderer *r, const float *start, const float *d
     return S3R_OK;
 }
 
+extern "C" int s3r_debug_exact_math(S3RRenderer *r, uint32_t mode, uint64_t first, uint64_t count, uint32_t seed, uint64_t result[5]) {
+    if (!r || !result) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    DevBuf<unsigned long long> res;
+    CUDA_TRY(res.ensure(5));
+    CUDA_TRY(cudaMemset(res.p, 0, 5 * sizeof(unsigned long long)));
+    launch_exact_math(mode, first, count, seed, res.p, r->stream);
+    r->launches++;
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    CUDA_TRY(cudaMemcpy(result, res.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    res.release();
+    return S3R_OK;
+}
+
 extern "C" uint64_t s3r_kernel_launches(const S3RRenderer *r) { return r ? r->launches : 0; }
 
 extern "C" int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raster_ms, uint64_t *chunks, int reset) {

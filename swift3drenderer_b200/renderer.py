@@ -70,7 +70,7 @@ EXPORTS = [
     "s3r_load_scene_arrays", "s3r_scene_counts", "s3r_camera_reset", "s3r_camera_update", "s3r_factor",
     "s3r_render_device", "s3r_finish", "s3r_render_host", "s3r_get_stats", "s3r_dump_raster_vertices",
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
-    "s3r_dropin_reset", "s3r_debug_walk", "s3r_render_device_rows", "s3r_tile_height",
+    "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
 ]
 
@@ -135,6 +135,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(u64), ctypes.c_int]
     lib.s3r_debug_walk.argtypes = [vp, vp, vp, vp, vp, u32]
+    lib.s3r_debug_exact_math.argtypes = [vp, u32, u64, u64, u32, ctypes.POINTER(u64)]
     lib.s3r_render_device_rows.argtypes = [vp, vp, u32, u32, u32, u32, u32, vp, vp]
     lib.s3r_tile_height.restype = u32
     lib.s3r_peer_frame_alloc.argtypes = [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]

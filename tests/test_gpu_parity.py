@@ -493,3 +493,19 @@ def test_span_tables_equal_in_tile_jumps_and_the_oracle(renderer_lib, oracle_por
                 frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
             assert_same(frame, w, f"interleaved rows frame {f}")
     r.close()
+
+
+def test_exact_math_equals_ieee_operators(gpu_renderer):
+    """csrc/exact_math.cuh: the shading chain's hand-scheduled 1/sqrt and shared-reciprocal divisions must be the
+    compiler's correctly rounded operators bit for bit — EVERY positive binary32 (and the negative/NaN fallbacks) for
+    1/sqrt, 2^33 seeded operand sets incl. extreme mantissas and out-of-range operands for the division."""
+    import ctypes
+    lib, h = gpu_renderer._lib, gpu_renderer._h
+    lib.s3r_debug_exact_math.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                         ctypes.POINTER(ctypes.c_uint64)]
+    res = (ctypes.c_uint64 * 5)()
+    assert lib.s3r_debug_exact_math(h, 0, 0, 1 << 32, 0, res) == 0          # all 2^32 bit patterns
+    assert res[0] == 0, f"1/sqrt: {res[0]} mismatches, first x={res[1]:08x} got={res[2]:08x} want={res[3]:08x}"
+    for seed in (1, 2):
+        assert lib.s3r_debug_exact_math(h, 1, 0, 1 << 32, seed, res) == 0
+        assert res[0] == 0, f"div: {res[0]} mismatches, first a={res[1]:08x} b={res[2]:08x} got={res[3]:08x} want={res[4]:08x}"
