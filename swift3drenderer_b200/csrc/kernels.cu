@@ -890,9 +890,9 @@ struct RasterShared {
 static_assert(sizeof(RasterShared) <= 56 * 1024, "RasterShared must leave room for four CTAs per SM");
 static_assert(SORT_CAP < 0x8000, "list entries are 15-bit slots plus the WON flag");
 
-__device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115-122
-    i--; i |= i >> 1; i |= i >> 2; i |= i >> 4;
-    return i + 1;
+__device__ __forceinline__ uint32_t next_pow2_8(uint32_t i) {  // render.cpp:115-122 for its domain 1 <= i <= 256
+    // i--; i |= i >> 1; i |= i >> 2; i |= i >> 4; return i + 1;  ==  one past the smeared top bit of i - 1
+    return 1u << (32 - __clz((int)(i - 1u)));
 }
 
 // render.cpp:363-372 + getColor (:339-359) + getTextureColor (:124-132) for one winning pixel
@@ -926,7 +926,9 @@ __device__ __forceinline__ uint32_t shade_math(const Frame &f, float rz0, float 
         const uint32_t x = (uint32_t)((u - truncf(u)) * (float)lx) + (511u & ~(2u * lx - 1u));
         const uint32_t y = (uint32_t)((v - truncf(v)) * (float)ly) + (511u & ~(2u * ly - 1u));
         const uint32_t idx = (x + (y << 9)) & 0x3FFFFu;  // stays inside the atlas even for hostile uv
-        const uint32_t rgb = __ldg(f.texels + ((size_t)(s.texture % f.n_tex) << 18) + idx);
+        uint32_t tex = s.texture;
+        if (tex >= f.n_tex) { tex %= f.n_tex; }   // (a hostile index stays inside the atlases; valid scenes never divide)
+        const uint32_t rgb = __ldg(f.texels + ((size_t)tex << 18) + idx);
         base = make_float3((float)(rgb >> 16), (float)((rgb >> 8) & 255u), (float)(rgb & 255u));
     }
     const uint32_t r = (uint32_t)(int)(shade * base.x) & 255u, g = (uint32_t)(int)(shade * base.y) & 255u,

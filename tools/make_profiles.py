@@ -85,7 +85,10 @@ def main():
     rep = os.path.join(OUT, f"{tag}_c2_tile_raster.ncu-rep")
     if os.path.exists(rep):
         out, hdr, units, data = kernel_table(rep, "C2 (bench workload): `tile_raster`, 3840x2160, data.bin scene")
-        out = [f"# {tag}: tile_raster on the bench workload", ""] + out + stall_table(rep, "tile_raster") + lines_table(rep, "tile_raster")
+        seg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_segments.py"), rep, "tile_raster"],
+                             capture_output=True, text=True).stdout
+        out = [f"# {tag}: tile_raster on the bench workload (one launch = 8 poses)", ""] + out + stall_table(rep, "tile_raster") + \
+            ["", "Warp time barrier to barrier (tools/ncu_segments.py):", "", "```", seg.rstrip(), "```"] + lines_table(rep, "tile_raster", 30)
         open(os.path.join(PROF, f"{tag}_c2_tile_raster.md"), "w").write("\n".join(out) + "\n")
         ix = {h: i for i, h in enumerate(hdr)}
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -117,9 +120,18 @@ def main():
             doc += stall_table(rep, k) + lines_table(rep, k, 12)
         open(os.path.join(PROF, f"{tag}_c4_kernels.md"), "w").write("\n".join(doc) + "\n")
     for src, dst in (("l_w1.csv", f"{tag}_launches_c3_whole_frame.csv"), ("l_w8.csv", f"{tag}_launches_c3_one_of_8.csv"),
-                     ("l_c4.csv", f"{tag}_launches_c4.csv"), (f"launches_c2_{tag}.csv", f"{tag}_launches_bench_c2_24frames.csv")):
+                     ("l_c4.csv", f"{tag}_launches_c4.csv"), (f"launches_c2_{tag}.csv", f"{tag}_launches_bench_c2_48frames.csv")):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
+    par = os.path.join(OUT, f"parity_{tag}")
+    if os.path.isdir(par):
+        shutil.rmtree(os.path.join(PROF, f"parity_{tag}"), ignore_errors=True)
+        shutil.copytree(par, os.path.join(PROF, f"parity_{tag}"))
+    if os.path.exists(os.path.join(OUT, "configs.jsonl")):
+        lines = [l for l in open(os.path.join(OUT, "configs.jsonl")) if l.strip()]
+        one = [l for l in lines if '"gpus": 1' in l][-5:]
+        if one:
+            open(os.path.join(PROF, f"{tag}_configs_1gpu.jsonl"), "w").writelines(one)
     for src in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, src))

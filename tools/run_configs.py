@@ -101,8 +101,8 @@ def main():
 
         if mode == "frames":  # frame-parallel: this rank renders its share of the poses, several per launch
             mine = list(multigpu.frame_shard(n, rank, world))
-            vpl = 64 if W * H <= 1024 * 1024 else 1
-            out = torch.empty((8 if vpl == 1 else 2, vpl, H, W), dtype=torch.int32, device=dev)
+            vpl = 64 if W * H <= 1024 * 1024 else 8   # poses per launch set (bench.py renders C2 the same way)
+            out = torch.empty((2, vpl, H, W), dtype=torch.int32, device=dev)
 
             def step():
                 k = 0
