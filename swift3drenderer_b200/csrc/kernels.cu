@@ -202,7 +202,7 @@ __device__ __forceinline__ bool make_setup(const Corner &d0, const Corner &d1, c
             s.pay[3 * k + 2] = __uint_as_float(d[k]->pay.z) * v.rvz[k];
         }
     } else {
-        s.texture = d0.pay.x;
+        s.texture = d0.pay.x % f.n_tex;   // valid scenes: unchanged (checked at load); a mixed-kind triangle's reinterpreted payload stays inside the atlases
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             s.pay[2 * k] = __uint_as_float(d[k]->pay.z) * v.rvz[k];
@@ -926,9 +926,7 @@ __device__ __forceinline__ uint32_t shade_math(const Frame &f, float rz0, float 
         const uint32_t x = (uint32_t)((u - truncf(u)) * (float)lx) + (511u & ~(2u * lx - 1u));
         const uint32_t y = (uint32_t)((v - truncf(v)) * (float)ly) + (511u & ~(2u * ly - 1u));
         const uint32_t idx = (x + (y << 9)) & 0x3FFFFu;  // stays inside the atlas even for hostile uv
-        uint32_t tex = s.texture;
-        if (tex >= f.n_tex) { tex %= f.n_tex; }   // (a hostile index stays inside the atlases; valid scenes never divide)
-        const uint32_t rgb = __ldg(f.texels + ((size_t)tex << 18) + idx);
+        const uint32_t rgb = __ldg(f.texels + ((size_t)s.texture << 18) + idx);   // s.texture < n_tex (make_setup)
         base = make_float3((float)(rgb >> 16), (float)((rgb >> 8) & 255u), (float)(rgb & 255u));
     }
     const uint32_t r = (uint32_t)(int)(shade * base.x) & 255u, g = (uint32_t)(int)(shade * base.y) & 255u,
