@@ -66,6 +66,13 @@ __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by,
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// fire-and-forget 64-bit max on a visibility key: always the reduction form (REDG.E.MAX.64).  atomicMax() with an unused
+// result is sometimes compiled to the returning ATOMG form instead, and a walk loop then waits for each atomic to
+// come back before it may reuse the address registers (45 % of post_setup's warp time on the clipping-stress scene).
+__device__ __forceinline__ void red_max_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 // n sequential additions of d onto s (render.cpp:374-379): true steps when the target is near, the exact
 // jump (walk.cuh) otherwise.  Both give the same bits; the loop is cheaper for short distances.
 __device__ __forceinline__ float walk_near(float s, float d, uint32_t n) {
@@ -692,7 +699,7 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
                 const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
@@ -1336,19 +1343,32 @@ __global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_qu
 // with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame f) {
-    __shared__ uint32_t s_sum, s_max, s_last, s_warp[8], s_pref[257];
+    constexpr uint32_t FLAT_ROUND = 64, FLAT_CK = 16;   // survivors per round; row-start checkpoints per survivor, one every 8 rows
+    __shared__ uint32_t s_sum, s_max, s_last, s_round, s_warp[8], s_pref[257];
+    __shared__ float s_ck[FLAT_ROUND][FLAT_CK][3];
+    __shared__ uint4 s_head[FLAT_ROUND], s_rec[FLAT_ROUND][4];   // the round's survivors, staged once (the items are latency-bound otherwise)
     const uint32_t view = blockIdx.y;
     bin_big_body(f, view);   // K3 for the triangles the setup kernel left to a whole CTA
-    // Flat walk of the recorded triangles under flat_max x flat_max pixels: 256 survivors per CTA and round, one work
-    // item per (triangle, box row) found by binary search in the prefix sums of the rows, so that every lane walks one
-    // row whatever the mix of box sizes.  Exactly the reference's own additions (render.cpp:374-379).
+    // Flat walk of the recorded triangles under flat_max x flat_max pixels: FLAT_ROUND survivors per CTA and round, one
+    // work item per (triangle, box row) found by binary search in the prefix sums of the rows, so that every lane walks
+    // one row whatever the mix of box sizes.  Exactly the reference's own additions (render.cpp:374-379).  Rounds are
+    // small and handed out by an atomic counter: their cost varies by orders of magnitude with the box sizes, and a
+    // static deal of 256-survivor rounds left two thirds of the CTAs without work on the clipping-stress scene.
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    for (uint32_t g0 = blockIdx.x * 256u; g0 < n; g0 += gridDim.x * 256u) {
+    while (true) {
+        if (tid == 0) { s_round = atomicAdd(f.counters + view * C_COUNT + C_FLATQ, 1u); }
+        __syncthreads();
+        const uint32_t g0 = s_round * FLAT_ROUND;
+        if (g0 >= n) { break; }
         uint32_t rows = 0;
-        if (g0 + tid < n) {
+        if (g0 + (tid >> 2) < n) {   // 64-byte coverage records of the round: one coalesced 4 KB read
+            s_rec[tid >> 2][tid & 3u] = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + g0 + (tid >> 2))[tid & 3u];
+        }
+        if (tid < FLAT_ROUND && g0 + tid < n) {
             const uint4 head = f.head[(size_t)view * f.setup_cap + g0 + tid];
+            s_head[tid] = head;
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
             if (is_flat_bbox(f, xmin, xmax, ymin, ymax) && ylo <= yhi) { rows = owned_pixel_rows(f, ylo, yhi).count; }
@@ -1365,31 +1385,46 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
         if (tid == 0) { s_pref[0] = 0; }
         __syncthreads();
         const uint32_t total = s_pref[256];
+        // row starts (render.cpp:378-379) by true additions, once per (survivor, component): every 8th one is kept, an
+        // item then needs at most 7 more additions instead of an exact jump per component
+        for (uint32_t idx = tid; idx < FLAT_ROUND * 3u; idx += 256u) {
+            const uint32_t sv = idx / 3u, c = idx % 3u;
+            if (s_pref[sv + 1u] == s_pref[sv]) { continue; }
+            const SetupVis *v = reinterpret_cast<const SetupVis *>(&s_rec[sv][0]);
+            const uint32_t last = min(min((uint32_t)v->ymax, f.y1 - 1u) - v->ymin, FLAT_CK * 8u - 1u);
+            const float d = v->dy[c];
+            float w = v->wstart[c];
+            for (uint32_t r = 0; ; r++) {
+                if ((r & 7u) == 0u) { s_ck[sv][r >> 3][c] = w; }
+                if (r == last) { break; }
+                w = add_rn(w, d);
+            }
+        }
+        __syncthreads();
         for (uint32_t i = tid; i < total; i += 256u) {
             uint32_t lo = 0, hi = 256;   // largest j with s_pref[j] <= i
             while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_pref[mid] <= i) { lo = mid; } else { hi = mid; } }
-            const uint32_t slot = g0 + lo;
-            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+            const uint4 head = s_head[lo];
             const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
             const uint32_t y = owned_row_at(f, owned_pixel_rows(f, max(ymin, f.y0), min(ymax, f.y1 - 1u)), i - s_pref[lo]), a = y / TILE_H;
-            const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
-            const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+            const uint4 q1 = s_rec[lo][1], q2 = s_rec[lo][2], q3 = s_rec[lo][3];
             const float dx0 = __uint_as_float(q1.w), dx1 = __uint_as_float(q2.x), dx2 = __uint_as_float(q2.y);
             const float rz0 = __uint_as_float(q3.y), rz1 = __uint_as_float(q3.z), rz2 = __uint_as_float(q3.w);
-            float w0 = walk_near(__uint_as_float(q1.x), __uint_as_float(q2.z), y - ymin);   // render.cpp:378
-            float w1 = walk_near(__uint_as_float(q1.y), __uint_as_float(q2.w), y - ymin);
-            float w2 = walk_near(__uint_as_float(q1.z), __uint_as_float(q3.x), y - ymin);
+            const uint32_t ck = min((y - ymin) >> 3, FLAT_CK - 1u), more = y - ymin - 8u * ck;   // more <= 7 for boxes under 128 rows
+            float w0 = walk_near(s_ck[lo][ck][0], __uint_as_float(q2.z), more);   // render.cpp:378
+            float w1 = walk_near(s_ck[lo][ck][1], __uint_as_float(q2.w), more);
+            float w2 = walk_near(s_ck[lo][ck][2], __uint_as_float(q3.x), more);
             const unsigned long long key_lo = (unsigned long long)(~head.z);
             unsigned long long *krow = keys + out_row(f, y, a) * f.W;
             for (uint32_t x = xmin; x <= xmax; x++) {
                 const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (inside && ooz > 0.f) { atomicMax(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
-        __syncthreads();   // s_pref is rewritten by the next round
+        __syncthreads();   // s_pref and s_round are rewritten by the next round
     }
     // the last CTA of the view to get here closes the frame's geometry (tile statistics, overflow record)
     if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }

@@ -61,6 +61,7 @@ enum Counter : uint32_t {
     C_QHEAD = 12,    // ... and how many of them have been taken
     C_DONE = 10,     // CTAs of post_setup that have finished (the last one closes the frame's geometry)
     C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
+    C_FLATQ = 14,    // general path: rounds of the flat walk handed out so far (post_setup)
     C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
     C_COUNT = 16
 };
