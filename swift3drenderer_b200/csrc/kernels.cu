@@ -1087,10 +1087,13 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 reinterpret_cast<uint4 *>(&sh.u.big.batch[b])[q] =
                     reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + sh.u.big.bigq[base + b])[q];
             } else if (tid >= 32u && tid < 32u + nb) {   // ... and find their checkpoint tables, if they have one
-                uint32_t span = NO_TRI;
+                uint32_t span = NO_TRI;   // DIRECT: index of the triangle's checkpoint table; queue path: offset of its row-start block
+                const uint32_t slot = sh.u.big.bigq[base + tid - 32u];
                 if (DIRECT && f.coltab) {
-                    const uint32_t n_span = f.counters[view * C_COUNT + C_SPANS], slot = sh.u.big.bigq[base + tid - 32u];
+                    const uint32_t n_span = f.counters[view * C_COUNT + C_SPANS];
                     for (uint32_t k = 0; k < n_span; k++) { if (f.span_slots[view * SPAN_MAX + k] == slot) { span = k; } }
+                } else if (!DIRECT && f.rowtab) {
+                    span = f.rowbase[(size_t)view * f.setup_cap + slot];
                 }
                 sh.u.big.span[tid - 32u] = span;
             }
@@ -1110,9 +1113,15 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 if (xs > xe) { continue; }
                 const float d = v.dx[c];
                 const uint32_t span = sh.u.big.span[b];
-                float w = span != NO_TRI   // walked once for the whole frame by span_walk: the same bits, one load
-                    ? f.coltab[((((size_t)view * SPAN_MAX + span) * f.tiles_x + tile_x) * 3u + c) * f.span_h + yy]
-                    : walk_near(walk_near(v.wstart[c], v.dy[c], yy - v.ymin), d, xs - v.xmin);
+                float w;
+                if (span == NO_TRI) {
+                    w = walk_near(walk_near(v.wstart[c], v.dy[c], yy - v.ymin), d, xs - v.xmin);
+                } else if (DIRECT) {   // walked once for the whole frame by span_walk: the same bits, one load
+                    w = f.coltab[((((size_t)view * SPAN_MAX + span) * f.tiles_x + tile_x) * 3u + c) * f.span_h + yy];
+                } else {               // row start walked once by post_setup, then along the row
+                    const uint32_t h = (uint32_t)v.ymax - v.ymin + 1u;
+                    w = walk_near(f.rowtab[(size_t)view * f.rowtab_cap + span + c * h + (yy - v.ymin)], d, xs - v.xmin);
+                }
                 uint32_t x = xs, k = (xs - tx0) / SEG;
                 while (true) {
                     sh.u.big.segstart[b][r][k][c] = w;
@@ -1349,6 +1358,34 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
     __shared__ uint4 s_head[FLAT_ROUND], s_rec[FLAT_ROUND][4];   // the round's survivors, staged once (the items are latency-bound otherwise)
     const uint32_t view = blockIdx.y;
     bin_big_body(f, view);   // K3 for the triangles the setup kernel left to a whole CTA
+    if (f.rowtab) {
+        // row starts of the tile-path triangles: one thread per triangle takes a block of the table and walks its own
+        // rows with true additions (three independent chains).  Every (tile, triangle) pair of the tile kernel would
+        // otherwise pay an exact jump per (row, component) for the same values.
+        const uint32_t n_all = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
+        for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_all; slot += gridDim.x * blockDim.x) {
+            const uint4 head = f.head[(size_t)view * f.setup_cap + slot];
+            const uint32_t xmin = head.x & 0xFFFFu, xmax = head.x >> 16, ymin = head.y & 0xFFFFu, ymax = head.y >> 16;
+            uint32_t base = NO_TRI;
+            if (!is_flat_bbox(f, xmin, xmax, ymin, ymax)) {
+                const uint32_t h = ymax - ymin + 1u;
+                base = atomicAdd(f.counters + view * C_COUNT + C_ROWTAB, 3u * h);
+                if (base > f.rowtab_cap || 3u * h > f.rowtab_cap - base) { base = NO_TRI; }   // table full: this one keeps jumping
+            }
+            f.rowbase[(size_t)view * f.setup_cap + slot] = base;
+            if (base == NO_TRI) { continue; }
+            const uint4 *rec = reinterpret_cast<const uint4 *>(f.vis + (size_t)view * f.setup_cap + slot);
+            const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+            const float dy0 = __uint_as_float(q2.z), dy1 = __uint_as_float(q2.w), dy2 = __uint_as_float(q3.x);
+            float w0 = __uint_as_float(q1.x), w1 = __uint_as_float(q1.y), w2 = __uint_as_float(q1.z);
+            const uint32_t h = ymax - ymin + 1u;
+            float *t = f.rowtab + (size_t)view * f.rowtab_cap + base;
+            for (uint32_t r = 0; r < h; r++) {
+                t[r] = w0; t[h + r] = w1; t[2u * h + r] = w2;
+                w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2);
+            }
+        }
+    }
     // Flat walk of the recorded triangles under flat_max x flat_max pixels: FLAT_ROUND survivors per CTA and round, one
     // work item per (triangle, box row) found by binary search in the prefix sums of the rows, so that every lane walks
     // one row whatever the mix of box sizes.  Exactly the reference's own additions (render.cpp:374-379).  Rounds are

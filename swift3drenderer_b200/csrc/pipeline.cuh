@@ -61,6 +61,7 @@ enum Counter : uint32_t {
     C_QHEAD = 12,    // ... and how many of them have been taken
     C_DONE = 10,     // CTAs of post_setup that have finished (the last one closes the frame's geometry)
     C_DIRECT = 9,    // small unclipped survivors walked straight from the classify kernel (no setup record)
+    C_ROWTAB = 15,   // general path: floats of row-start tables allocated so far (post_setup)
     C_FLATQ = 14,    // general path: rounds of the flat walk handed out so far (post_setup)
     C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
     C_COUNT = 16
@@ -143,6 +144,11 @@ struct Frame {
     float *coltab;          // [views][SPAN_MAX][tiles_x][3][span_h], null = every tile takes the exact jump itself
     uint32_t *span_slots;   // [views][SPAN_MAX] survivor slots that have a table (counters[C_SPANS] of them)
     uint32_t span_h;        // H rounded up to a multiple of 32
+    // general path: row-start weights (render.cpp:378-379) of the tile-path triangles, walked once per frame by
+    // post_setup; the tile kernel's stage A then needs only the jump along the row
+    float *rowtab;          // [views][rowtab_cap]: per triangle a block [component][box row]
+    uint32_t *rowbase;      // [views][setup_cap] block offset per survivor slot, NO_TRI = none (flat-walked, or the table was full)
+    uint32_t rowtab_cap;
 };
 
 // Launchers (kernels.cu).  Each returns the number of kernels it enqueued.

@@ -89,6 +89,8 @@ struct S3RRenderer {
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
     DevBuf<float> coltab;     // small scenes: tile-column checkpoints of the largest survivors (span_walk)
     DevBuf<uint32_t> span_slots;
+    DevBuf<float> rowtab;     // general path: row-start blocks of the tile-path triangles (post_setup)
+    DevBuf<uint32_t> rowbase;
     // submission ring: pinned camera staging + events, so the host can run RING chunks ahead
     static constexpr int RING = 16;
     float *cams_pinned = nullptr;     // RING x views_cap x 12
@@ -172,7 +174,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
-    r->coltab.release(); r->span_slots.release();
+    r->coltab.release(); r->span_slots.release(); r->rowtab.release(); r->rowbase.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
     delete r->copier;
     if (r->sticky_host) { cudaFreeHost(r->sticky_host); }
@@ -247,7 +249,7 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
     r->V = V; r->Vpad = px.size(); r->I = I; r->T = T; r->A = A; r->n_texels = n_texels;
     r->has_scene = true;
     r->views_cap = 0;  // scratch is re-sized on the next render
-    r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+    r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release(); r->rowbase.release();
     return S3R_OK;
 }
 
@@ -521,6 +523,13 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
             f.coltab = r->coltab.p; f.span_slots = r->span_slots.p;
         }
     }
+    if (!f.direct_bin && r->opt_spans) {
+        // general path: 8 M floats of row-start blocks per view; a triangle that does not fit keeps its exact jumps
+        f.rowtab_cap = (uint32_t)std::min<size_t>(8u << 20, ((size_t)256 << 20) / std::max<size_t>(r->views_cap, 1));   // <= 1 GB in all
+        CUDA_TRY(r->rowtab.ensure((size_t)f.rowtab_cap * r->views_cap));
+        CUDA_TRY(r->rowbase.ensure((size_t)r->setup_cap * r->views_cap));
+        f.rowtab = r->rowtab.p; f.rowbase = r->rowbase.p;
+    }
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
@@ -610,7 +619,7 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
         r->setup_cap = (uint32_t)std::min<uint64_t>(2ull * r->T + 16, (uint64_t)need_setups + need_setups / 2 + 1024);
         r->big_cap = std::max(r->big_cap, r->setup_cap / 16u);
         // vis/shade are view-strided by setup_cap: force reallocation
-        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release(); r->rowbase.release();
     }
     if (overflow & 2u) { r->tile_cap = std::max(r->tile_cap, need_entries + need_entries / 2 + 64); r->entries.release(); }
     if (overflow & 4u) { r->big_cap = std::max(r->big_cap, need_big + need_big / 2 + 64); r->big_list.release(); }
@@ -976,7 +985,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
         if (value < 1) { return fail(S3R_E_ARG, "setup_capacity < 1"); }
         cudaStreamSynchronize(r->stream);
         r->setup_cap = (uint32_t)value; r->tile_cap = 4; r->big_cap = 4;
-        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release();
+        r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release(); r->rowbase.release();
         return S3R_OK;
     }
     return fail(S3R_E_ARG, std::string("unknown option ") + name);
