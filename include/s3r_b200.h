@@ -162,6 +162,18 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
 S3R_API int s3r_debug_walk(S3RRenderer *r, const float *start, const float *delta, const uint32_t *steps,
                            float *out, uint32_t count);
 
+/* Frame sink (replaces the reference shell's CoreImage -> Metal blit, main.swift:124-140, for
+ * headless use): appends device-resident frames — 0x00RRGGBB words, i.e. bytes B, G, R, 0, the shell's .BGRA8 — to a
+ * file without passing through a caller's host buffer.  format 0: raw BGR0 frames back to back; format 1: YUV4MPEG2
+ * 4:2:0 (BT.601 limited range), converted on the GPU (1.5 bytes per pixel over PCIe).  s3r_sink_submit is asynchronous
+ * and stream-ordered: enqueue it on the stream the frame was rendered on (null = the renderer's own stream, like
+ * s3r_render_device); the frame may be overwritten by work enqueued after it.  At most four frames are in flight; s3r_sink_close drains them and reports how many reached the file. */
+typedef struct S3RSink S3RSink;
+S3R_API int s3r_sink_open(S3RRenderer *r, const char *path, uint32_t width, uint32_t height, uint32_t fps_num,
+                          uint32_t fps_den, int format, S3RSink **out);
+S3R_API int s3r_sink_submit(S3RSink *sink, const uint32_t *dev_frame, void *stream);
+S3R_API int s3r_sink_close(S3RSink *sink, uint64_t *frames_written);
+
 /* Test hook: compares the shading chain's hand-scheduled IEEE division / reciprocal square root (csrc/exact_math.cuh)
  * with the compiler's operators on the device.  mode 0: every binary32 bit pattern first .. first + count - 1 through
  * 1/sqrt; mode 1: `count` seeded pseudo-random operand sets through the divisions.  result[0] = mismatches,

@@ -1057,3 +1057,160 @@ extern "C" __attribute__((visibility("default"))) void updateAndRender(const Pix
         exit(70);
     }
 }
+
+// --------------------------------------------------------------------------------------------------
+// Frame sink: consumes device-resident frames — the memory layout the reference's shell
+// hands to CoreImage as .BGRA8 (main.swift:124-128: bytes B, G, R, 0) — without a synchronous trip through the
+// caller's host buffer.  Two containers: raw BGR0 frames, or YUV4MPEG2 4:2:0 (any player / encoder reads it), with
+// the colour conversion done on the GPU so that 1.5 instead of 4 bytes per pixel cross PCIe.  Submission is
+// asynchronous: conversion kernel and device->host copy on the caller's stream into a ring of pinned buffers, a
+// writer thread waits for each copy's event and appends the frame to the file.
+// --------------------------------------------------------------------------------------------------
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+
+namespace {
+
+// BT.601 limited range, the usual integer form; chroma from the rounded mean of the 2x2 block (edge blocks repeat
+// their last column / row).  One thread per 2x2 block.
+__global__ void __launch_bounds__(256) bgr0_to_i420(const uint32_t *frame, uint32_t W, uint32_t H, uint8_t *yp, uint8_t *up, uint8_t *vp) {
+    const uint32_t cw = (W + 1u) / 2u, ch = (H + 1u) / 2u;
+    const uint32_t bx = blockIdx.x * 16u + (threadIdx.x & 15u), by = blockIdx.y * 16u + (threadIdx.x >> 4);
+    if (bx >= cw || by >= ch) { return; }
+    uint32_t sr = 0, sg = 0, sb = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+        const uint32_t x = min(2u * bx + (k & 1u), W - 1u), y = min(2u * by + (k >> 1), H - 1u);
+        const uint32_t p = frame[(size_t)y * W + x], r = (p >> 16) & 255u, g = (p >> 8) & 255u, b = p & 255u;
+        sr += r; sg += g; sb += b;
+        if (2u * bx + (k & 1u) < W && 2u * by + (k >> 1) < H) {
+            yp[(size_t)y * W + x] = (uint8_t)(((66u * r + 129u * g + 25u * b + 128u) >> 8) + 16u);
+        }
+    }
+    const int r = (int)((sr + 2u) >> 2), g = (int)((sg + 2u) >> 2), b = (int)((sb + 2u) >> 2);
+    up[(size_t)by * cw + bx] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+    vp[(size_t)by * cw + bx] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+}
+
+}  // namespace
+
+struct S3RSink {
+    static const int RING = 4;
+    int device = 0, format = 0;
+    cudaStream_t default_stream = nullptr;   // the renderer's own stream (what s3r_render_device uses for stream = null)
+    uint32_t W = 0, H = 0;
+    size_t frame_bytes = 0;
+    FILE *file = nullptr;
+    uint8_t *dev_yuv = nullptr;          // format 1: conversion target (one frame; the copy that follows is stream-ordered)
+    uint8_t *host[RING] = {};
+    cudaEvent_t copied[RING] = {};
+    bool busy[RING] = {};
+    uint64_t submitted = 0, written = 0;
+    bool closing = false, io_error = false;
+    std::deque<int> jobs;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread writer;
+};
+
+static void sink_writer(S3RSink *k) {
+    cudaSetDevice(k->device);
+    while (true) {
+        int slot;
+        {
+            std::unique_lock<std::mutex> lock(k->mu);
+            k->cv.wait(lock, [&] { return !k->jobs.empty() || k->closing; });
+            if (k->jobs.empty()) { return; }
+            slot = k->jobs.front();
+            k->jobs.pop_front();
+        }
+        const bool ok = cudaEventSynchronize(k->copied[slot]) == cudaSuccess &&
+                        (k->format == 0 || fwrite("FRAME\n", 1, 6, k->file) == 6) &&
+                        fwrite(k->host[slot], 1, k->frame_bytes, k->file) == k->frame_bytes;
+        {
+            std::lock_guard<std::mutex> lock(k->mu);
+            if (ok) { k->written++; } else { k->io_error = true; }
+            k->busy[slot] = false;
+        }
+        k->cv.notify_all();
+    }
+}
+
+extern "C" int s3r_sink_open(S3RRenderer *r, const char *path, uint32_t width, uint32_t height, uint32_t fps_num,
+                             uint32_t fps_den, int format, S3RSink **out) {
+    if (!r || !path || !out) { return fail(S3R_E_ARG, "null argument"); }
+    if (width == 0 || height == 0 || width > 65535 || height > 65535 || fps_num == 0 || fps_den == 0 || format < 0 || format > 1) {
+        return fail(S3R_E_ARG, "bad sink geometry, rate or format");
+    }
+    CUDA_TRY(cudaSetDevice(r->device));
+    S3RSink *k = new S3RSink();
+    k->device = r->device; k->format = format; k->W = width; k->H = height; k->default_stream = r->stream;
+    const size_t cw = (width + 1u) / 2u, ch = (height + 1u) / 2u;
+    k->frame_bytes = format == 0 ? (size_t)width * height * 4u : (size_t)width * height + 2u * cw * ch;
+    k->file = fopen(path, "wb");
+    if (!k->file) { delete k; return fail(S3R_E_IO, std::string("cannot create ") + path); }
+    if (format == 1) {
+        fprintf(k->file, "YUV4MPEG2 W%u H%u F%u:%u Ip A1:1 C420jpeg XCOLORRANGE=LIMITED\n", width, height, fps_num, fps_den);
+        if (cudaMalloc(&k->dev_yuv, k->frame_bytes) != cudaSuccess) { fclose(k->file); delete k; return fail(S3R_E_CUDA, "sink: cudaMalloc"); }
+    }
+    for (int i = 0; i < S3RSink::RING; i++) {
+        if (cudaMallocHost(reinterpret_cast<void **>(&k->host[i]), k->frame_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&k->copied[i], cudaEventDisableTiming) != cudaSuccess) {
+            return fail(S3R_E_CUDA, "sink: pinned ring allocation failed");
+        }
+    }
+    k->writer = std::thread(sink_writer, k);
+    *out = k;
+    return S3R_OK;
+}
+
+extern "C" int s3r_sink_submit(S3RSink *k, const uint32_t *dev_frame, void *stream) {
+    if (!k || !dev_frame) { return fail(S3R_E_ARG, "null argument"); }
+    CUDA_TRY(cudaSetDevice(k->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : k->default_stream;
+    const int slot = (int)(k->submitted % S3RSink::RING);
+    {
+        std::unique_lock<std::mutex> lock(k->mu);   // back-pressure: at most RING frames between the GPU and the file
+        k->cv.wait(lock, [&] { return !k->busy[slot]; });
+        if (k->io_error) { return fail(S3R_E_IO, "sink: write failed"); }
+        k->busy[slot] = true;
+    }
+    if (k->format == 1) {
+        const size_t cw = (k->W + 1u) / 2u, ch = (k->H + 1u) / 2u;
+        uint8_t *yp = k->dev_yuv, *up = yp + (size_t)k->W * k->H, *vp = up + cw * ch;
+        bgr0_to_i420<<<dim3((unsigned)((cw + 15u) / 16u), (unsigned)((ch + 15u) / 16u)), 256, 0, s>>>(dev_frame, k->W, k->H, yp, up, vp);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(k->host[slot], k->dev_yuv, k->frame_bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(k->host[slot], dev_frame, k->frame_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaEventRecord(k->copied[slot], s));
+    k->submitted++;
+    {
+        std::lock_guard<std::mutex> lock(k->mu);
+        k->jobs.push_back(slot);
+    }
+    k->cv.notify_all();
+    return S3R_OK;
+}
+
+extern "C" int s3r_sink_close(S3RSink *k, uint64_t *frames_written) {
+    if (!k) { return fail(S3R_E_ARG, "sink is null"); }
+    {
+        std::lock_guard<std::mutex> lock(k->mu);
+        k->closing = true;
+    }
+    k->cv.notify_all();
+    if (k->writer.joinable()) { k->writer.join(); }   // drains the queue first
+    cudaSetDevice(k->device);
+    const bool bad = k->io_error || fclose(k->file) != 0;
+    if (frames_written) { *frames_written = k->written; }
+    for (int i = 0; i < S3RSink::RING; i++) {
+        if (k->host[i]) { cudaFreeHost(k->host[i]); }
+        if (k->copied[i]) { cudaEventDestroy(k->copied[i]); }
+    }
+    if (k->dev_yuv) { cudaFree(k->dev_yuv); }
+    delete k;
+    return bad ? fail(S3R_E_IO, "sink: write failed") : S3R_OK;
+}

@@ -72,6 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close",
 ]
 
 
@@ -143,6 +144,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_peer_frame_release.argtypes = [vp, vp]
     lib.s3r_set_peer_frames.argtypes = [vp, ctypes.POINTER(vp), u32]
     lib.s3r_copy_from_device.argtypes = [vp, vp, vp, u64]
+    lib.s3r_sink_open.argtypes = [vp, ctypes.c_char_p, u32, u32, u32, u32, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.s3r_sink_submit.argtypes = [vp, vp, vp]
+    lib.s3r_sink_close.argtypes = [vp, ctypes.POINTER(u64)]
     if path is None:
         _lib = lib
     return lib
@@ -332,6 +336,23 @@ class Renderer:
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.s3r_kernel_launches(self._h))
+
+
+class Sink:
+    """Frame sink (``s3r_sink_*``): device-resident frames -> raw BGR0 (``fmt=0``) or YUV4MPEG2 4:2:0 (``fmt=1``) file."""
+
+    def __init__(self, renderer: "Renderer", path: str, width: int, height: int, fps=(60, 1), fmt: int = 1):
+        self._r, self._h = renderer, ctypes.c_void_p()
+        renderer._check(renderer._lib.s3r_sink_open(renderer._h, path.encode(), width, height, fps[0], fps[1], fmt, ctypes.byref(self._h)))
+
+    def submit(self, dev_ptr: int, stream: int = 0) -> None:
+        self._r._check(self._r._lib.s3r_sink_submit(self._h, ctypes.c_void_p(dev_ptr), ctypes.c_void_p(stream)))
+
+    def close(self) -> int:
+        n = ctypes.c_uint64()
+        h, self._h = self._h, ctypes.c_void_p()
+        self._r._check(self._r._lib.s3r_sink_close(h, ctypes.byref(n)))
+        return int(n.value)
 
 
 class DropIn:

@@ -509,3 +509,49 @@ def test_exact_math_equals_ieee_operators(gpu_renderer):
     for seed in (1, 2):
         assert lib.s3r_debug_exact_math(h, 1, 0, 1 << 32, seed, res) == 0
         assert res[0] == 0, f"div: {res[0]} mismatches, first a={res[1]:08x} b={res[2]:08x} got={res[3]:08x} want={res[4]:08x}"
+
+
+def _i420_reference(px):
+    """numpy restatement of the sink's BT.601 limited-range conversion (csrc/renderer.cu: bgr0_to_i420)."""
+    H, W = px.shape
+    r, g, b = ((px >> 16) & 255).astype(np.int64), ((px >> 8) & 255).astype(np.int64), (px & 255).astype(np.int64)
+    y = ((66 * r + 129 * g + 25 * b + 128) >> 8) + 16
+    ys, xs = np.minimum(np.arange(0, H + (H & 1)), H - 1), np.minimum(np.arange(0, W + (W & 1)), W - 1)
+    mean = lambda c: (c[np.ix_(ys, xs)].reshape(len(ys) // 2, 2, len(xs) // 2, 2).sum(axis=(1, 3)) + 2) >> 2
+    r2, g2, b2 = mean(r), mean(g), mean(b)
+    u = ((-38 * r2 - 74 * g2 + 112 * b2 + 128) >> 8) + 128
+    v = ((112 * r2 - 94 * g2 - 18 * b2 + 128) >> 8) + 128
+    return np.concatenate([y.astype(np.uint8).ravel(), u.astype(np.uint8).ravel(), v.astype(np.uint8).ravel()])
+
+
+def test_frame_sink_writes_device_frames(gpu_renderer, renderer_lib, tmp_path):
+    """s3r_sink_*: device-resident frames go to a raw BGR0 file unchanged and to a YUV4MPEG2 file through the GPU colour
+    conversion — more frames than the pinned ring holds, odd frame size, frames overwritten right after submission."""
+    import torch
+    sc = S.shipped_scene(1)
+    gpu_renderer.load_scene(sc)
+    mats = renderer_lib.camera_path(S.input_script("flythrough", 600))
+    W, H, frames = 1283, 721, (0, 110, 150, 230, 330, 450, 599)
+    want = [gpu_renderer.render(mats[f], W, H)[0] for f in frames]
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda:0")
+    raw_path, y4m_path = str(tmp_path / "frames.bgr0"), str(tmp_path / "frames.y4m")
+    raw = renderer_lib.Sink(gpu_renderer, raw_path, W, H, fmt=0)
+    y4m = renderer_lib.Sink(gpu_renderer, y4m_path, W, H, fps=(30, 1), fmt=1)
+    for f in frames:                                   # one frame buffer, reused: the sinks are stream-ordered
+        gpu_renderer.render_device(mats[f], W, H, out.data_ptr())
+        raw.submit(out.data_ptr())
+        y4m.submit(out.data_ptr())
+    assert raw.close() == len(frames) and y4m.close() == len(frames)
+    assert gpu_renderer.finish() is False
+    got = np.fromfile(raw_path, np.uint32).reshape(len(frames), H, W)
+    for i, f in enumerate(frames):
+        assert_same(got[i], want[i], f"raw sink frame {f}")
+    blob = open(y4m_path, "rb").read()
+    head, _, body = blob.partition(b"\n")
+    assert head.split()[:4] == [b"YUV4MPEG2", b"W%d" % W, b"H%d" % H, b"F30:1"] and b"C420jpeg" in head
+    n = W * H + 2 * ((W + 1) // 2) * ((H + 1) // 2)
+    assert len(body) == len(frames) * (6 + n)
+    for i, f in enumerate(frames):
+        rec = body[i * (6 + n):(i + 1) * (6 + n)]
+        assert rec[:6] == b"FRAME\n"
+        assert np.array_equal(np.frombuffer(rec[6:], np.uint8), _i420_reference(want[i])), f"y4m frame {f}"
