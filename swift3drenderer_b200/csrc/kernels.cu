@@ -1,9 +1,12 @@
 // kernels.cu — hand-written sm_100a kernels of the frame pipeline.
 //
-// Small scenes (2T <= 4096), two launches per frame:
-//   geometry_small     one CTA per view: vertex stage, classify, clip, setup            (render.cpp:285-359, 212-262)
-//   tile_raster        per 64x32 tile: exact barycentric walk + depth in registers, deferred perspective-correct
-//                      shading + rip-map fetch, colour tile in shared memory, cp.async.bulk (TMA) write-out
+// Small scenes (2T <= 3840), three launches per batch of views:
+//   geometry_small     one CTA per view: vertex stage, classify, clip, setup; picks the largest survivors for span_walk
+//                                                                                        (render.cpp:285-359, 212-262)
+//   span_walk          once per frame: the reference's own row walk of the (<= 8) largest survivors, dropping the
+//                      weights at every tile column (whole-frame launches only)          (render.cpp:374-379)
+//   tile_raster        per 64x32 tile, 4 CTAs/SM: exact barycentric walk + depth in registers, deferred perspective-
+//                      correct shading + rip-map fetch, colour tile in shared memory, cp.async.bulk (TMA) write-out
 //                                                                                        (render.cpp:360-382, 124-132)
 // General path (visibility buffer of 64-bit depth|order keys), six launches per frame:
 //   vertex_stage       K1   model/view/projection over planar float4 position streams   (render.cpp:285-289)
@@ -11,8 +14,8 @@
 //                           pixels are walked right here, record-free                    (render.cpp:297-317, 360-382)
 //   triangle_setup     K2b  gather, near-plane clip (0/1/2 out), setup records, block-scan compaction, inline binning
 //                                                                                        (render.cpp:297-359, 212-262)
-//   post_setup         K3   cooperative binning of the largest triangles, flat row walk of recorded triangles under
-//                           128x128, tile work queue + overflow record (no reference counterpart)
+//   post_setup         K3   cooperative binning of the largest triangles, their row-start blocks, flat row walk of
+//                           recorded triangles under 128x128, tile work queue + overflow record
 //   tile_raster_queue  K4   tile kernel over (tile, chunk) items for triangles over 128 pixels
 //   shade_tiles        K5   visibility buffer -> colour: per 32x32 block, distinct triangles set up once, one covered
 //                           pixel per lane; clears the keys; optional fused frame assembly into peer frames
@@ -20,7 +23,8 @@
 //
 // PARITY RULES: this translation unit is compiled with -fmad=false -prec-div=true
 // -prec-sqrt=true -ftz=false; every expression is written in the reference's evaluation order so
-// that each binary32 intermediate equals the CPU's.  Do not "simplify" arithmetic here.
+// that each binary32 intermediate equals the CPU's.  Do not "simplify" arithmetic here.  The only
+// hand-scheduled operators are in exact_math.cuh (device-checked against the compiler's, bit for bit).
 #include <type_traits>
 #include "pipeline.cuh"
 #include "walk.cuh"
