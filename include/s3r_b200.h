@@ -151,6 +151,7 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
  *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
  *          "fused_small" (1 = one fused geometry CTA per view for scenes of at most 1920 triangles, default),
+ *          "tensor_store" (1 = tile_raster writes each tile with one TMA tensor store instead of 32 bulk row copies, default),
  *          "spans" (1 = small scenes, whole-frame launches: the row walks of the largest survivors are done once per
  *          frame by span_walk instead of by exact jumps in every tile, default),
  *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/

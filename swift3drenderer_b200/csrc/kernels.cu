@@ -961,6 +961,26 @@ __device__ __forceinline__ uint32_t swizzled(uint32_t row, uint32_t seg, uint32_
     return row * TILE_W + seg * SEG + (j ^ (seg & 7u));  // spreads a thread's 8-pixel run over the 16-byte bank groups
 }
 
+// Output row (inside the submission's output, signed: a band may start inside a tile) of a tile's first pixel row.
+__device__ __forceinline__ int32_t tile_first_out_row(const Frame &f, uint32_t ty0, uint32_t tile_a) {
+    return f.row_stride == 1u ? (int32_t)ty0 - (int32_t)f.y0 : (int32_t)(div_stride(f, tile_a) * TILE_H);
+}
+
+// One TMA tensor store for a whole tile: the box (TILE_W pixels x TILE_H rows, contiguous in shared memory) goes to
+// {x, row, view} of the output tensor; whatever lies outside the tensor (band edges, a partial last tile) is clipped
+// by the copy engine.  Called by all threads after the tile is complete in shared memory; one thread issues it.
+__device__ __forceinline__ void tensor_store_tile(const Frame &f, const void *tile_smem, int32_t x, int32_t row, int32_t view) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile_smem);
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                     :: "l"(reinterpret_cast<unsigned long long>(&f.out_map)), "r"(x), "r"(row), "r"(view), "r"(src) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 // Per-triangle walk of a small triangle inside one tile, exactly as the reference walks it
 // (render.cpp:360-382): rows from the triangle's own ymin, pixels from its own xmin, true additions only.
 // PASS 1 publishes depth keys with atomicMax; PASS 2 (after every key is final) lets the winner of each
@@ -1265,7 +1285,9 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
             o[2] = (p.z >> 16) | (p.w << 8);
         }
         uint8_t *out8 = reinterpret_cast<uint8_t *>(f.out) + (size_t)view * f.out_view_stride * 3u;
-        if (f.use_tma) {
+        if (f.use_tmap) {
+            tensor_store_tile(f, packed, (int32_t)(tx0 * 3u), tile_first_out_row(f, ty0, tile_a), (int32_t)view);
+        } else if (f.use_tma) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             // the bulk copy takes uniform operands, so a warp issues its lanes' copies one after the other: four rows per
@@ -1295,7 +1317,9 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         return;
     }
     uint32_t *out = f.out + (size_t)view * f.out_view_stride;
-    if (f.use_tma) {
+    if (f.use_tmap) {
+        tensor_store_tile(f, &sh.k.colour[0][0], (int32_t)tx0, tile_first_out_row(f, ty0, tile_a), (int32_t)view);
+    } else if (f.use_tma) {
         // make the generic-proxy writes to the colour tile visible to the async (TMA) proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();

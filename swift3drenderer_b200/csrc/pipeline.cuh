@@ -20,6 +20,7 @@
 // Screen tiles are TILE_W x TILE_H pixels, aligned to the full frame's origin (so a band-partitioned
 // render bins and rasterises exactly the tiles the whole-frame render would).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -149,6 +150,10 @@ struct Frame {
     float *rowtab;          // [views][rowtab_cap]: per triangle a block [component][box row]
     uint32_t *rowbase;      // [views][setup_cap] block offset per survivor slot, NO_TRI = none (flat-walked, or the table was full)
     uint32_t rowtab_cap;
+    // tile_raster write-out as ONE 3-D TMA tensor store per tile (box 64 x 32 x 1 of {x, output row, view}; rows and
+    // columns outside the output are clipped by the hardware) instead of 32 bulk row copies
+    int use_tmap;
+    CUtensorMap out_map;    // 64-byte aligned member of a __grid_constant__ parameter
 };
 
 // Launchers (kernels.cu).  Each returns the number of kernels it enqueued.

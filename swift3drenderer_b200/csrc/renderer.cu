@@ -113,7 +113,7 @@ struct S3RRenderer {
     uint8_t *staging = nullptr;
     size_t staging_bytes = 0;
     HostCopier *copier = nullptr;
-    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1, opt_spans = 1;
+    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1, opt_spans = 1, opt_tmap = 1;
     std::vector<HostPin> pins;
     // fused frame assembly
     std::vector<void *> own_frames, opened_frames;
@@ -426,6 +426,34 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     return S3R_OK;
 }
 
+// Tensor map of a submission's output for tile_raster's one-store-per-tile write-out: {x, output row, view}, 32-bit
+// pixels or (packed host transport) bytes with 3 per pixel.  cuTensorMapEncodeTiled comes from the driver through the
+// runtime's entry-point query, so the library does not link libcuda.  false = use the bulk row copies.
+static bool encode_out_map(CUtensorMap *map, void *base, uint32_t W, uint64_t rows, uint32_t views, uint64_t view_stride_px, bool packed24) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode || rows == 0) { return false; }
+    const uint64_t bpp = packed24 ? 3 : 4;
+    const cuuint64_t dims[3] = {packed24 ? (cuuint64_t)W * 3u : (cuuint64_t)W, rows, views};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * bpp, view_stride_px * bpp};   // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {packed24 ? (cuuint32_t)TILE_W * 3u : (cuuint32_t)TILE_W, (cuuint32_t)TILE_H, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (strides[0] % 16u || strides[1] % 16u) { return false; }
+    return encode(map, packed24 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // raster_bands > 1: the tile rows are rasterised in that many launches, with r->ev_raster[b] recorded
 // after band b (used by the staged host path to start the D2H of a band while the next one renders);
 // band_rows[b] receives the first pixel row (relative to y0) after band b.
@@ -504,6 +532,11 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     }
     f.out_packed24 = packed24 ? 1 : 0;
     f.use_tma = r->opt_tma && (W % (packed24 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(dev_out) & 15u) == 0);
+    // (interleaved tile rows keep the row copies: rows past H stay unwritten; so do bands that start inside a tile row —
+    // the store's start coordinate must not be negative)
+    if (f.use_tma && r->opt_tmap && uses_direct_bin(r) && dev_out && row_stride == 1 && y0 % TILE_H == 0) {
+        f.use_tmap = encode_out_map(&f.out_map, dev_out, W, (uint64_t)(f.out_view_stride / W), n_views, f.out_view_stride, packed24) ? 1 : 0;
+    }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t0[slot], s)); }
     // small scenes are launch-latency bound: one fused CTA per view and no bin arrays instead of eight
     // launches; 2T <= SORT_CAP guarantees every raster CTA can hold the whole survivor list
@@ -962,6 +995,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "spans")) { r->opt_spans = value != 0; return S3R_OK; }
+    if (!strcmp(name, "tensor_store")) { r->opt_tmap = value != 0; return S3R_OK; }
     if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
         if (value < 16 || value > 65536) { return fail(S3R_E_ARG, "flat_max out of range"); }
         r->opt_flat_max = (int)value; return S3R_OK;

@@ -130,15 +130,36 @@ def test_batched_views_equal_single_views(gpu_renderer, renderer_lib):
 
 
 def test_tma_and_plain_write_out_agree(gpu_renderer, renderer_lib):
+    """tile_raster's three write-outs — one TMA tensor store per tile, bulk row copies, plain stores — on the host path
+    (24-bit packed transport, banded launches) and the device path (32-bit, whole frame and a band that cuts tile rows),
+    with widths that are and are not multiples of the tile width."""
+    import torch
     sc = S.shipped_scene(1)
     gpu_renderer.load_scene(sc)
     m = renderer_lib.camera_path(S.input_script("flythrough", 120))[110]
-    a = gpu_renderer.render(m, 1280, 720)[0]
-    gpu_renderer.set_option("tma_store", 0)
-    b = gpu_renderer.render(m, 1280, 720)[0]
-    gpu_renderer.set_option("tma_store", 1)
-    assert len(np.unique(a)) > 100, len(np.unique(a))
-    assert_same(b, a, 'plain vs TMA write-out')
+    variants = ((1, 1), (1, 0), (0, 0))   # (tma_store, tensor_store)
+    for W, H in ((1280, 720), (1936, 1000), (1284, 722)):
+        frames = []
+        for tma, tmap in variants:
+            gpu_renderer.set_option("tma_store", tma)
+            gpu_renderer.set_option("tensor_store", tmap)
+            host = gpu_renderer.render(m, W, H)[0]
+            out = torch.zeros((H, W), dtype=torch.int32, device="cuda:0")
+            gpu_renderer.render_device(m, W, H, out.data_ptr())
+            assert gpu_renderer.finish() is False
+            y0, y1 = H // 3 + 7, (2 * H) // 3 + 5
+            band = torch.zeros((y1 - y0, W), dtype=torch.int32, device="cuda:0")
+            gpu_renderer.render_device(m, W, H, band.data_ptr(), y0=y0, y1=y1)
+            assert gpu_renderer.finish() is False
+            frames.append((host, out.cpu().numpy().view(np.uint32), band.cpu().numpy().view(np.uint32), y0, y1))
+        gpu_renderer.set_option("tma_store", 1)
+        gpu_renderer.set_option("tensor_store", 1)
+        ref = frames[-1][0]
+        assert len(np.unique(ref)) > 100, len(np.unique(ref))
+        for (tma, tmap), (host, dev, band, y0, y1) in zip(variants, frames):
+            assert_same(host, ref, f"{W}x{H} host path, tma={tma} tensor={tmap}")
+            assert_same(dev, ref, f"{W}x{H} device path, tma={tma} tensor={tmap}")
+            assert_same(band, ref[y0:y1], f"{W}x{H} band, tma={tma} tensor={tmap}")
 
 
 @pytest.mark.parametrize("direct_small", [1, 0])

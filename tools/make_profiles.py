@@ -128,10 +128,12 @@ def main():
         shutil.rmtree(os.path.join(PROF, f"parity_{tag}"), ignore_errors=True)
         shutil.copytree(par, os.path.join(PROF, f"parity_{tag}"))
     if os.path.exists(os.path.join(OUT, "configs.jsonl")):
-        lines = [l for l in open(os.path.join(OUT, "configs.jsonl")) if l.strip()]
-        one = [l for l in lines if '"gpus": 1' in l][-5:]
-        if one:
-            open(os.path.join(PROF, f"{tag}_configs_1gpu.jsonl"), "w").writelines(one)
+        latest = {}   # the most recent single-GPU line of every configuration (C1..C5)
+        for l in open(os.path.join(OUT, "configs.jsonl")):
+            if l.strip() and '"gpus": 1' in l:
+                latest[json.loads(l)["config"][:2]] = l
+        if latest:
+            open(os.path.join(PROF, f"{tag}_configs_1gpu.jsonl"), "w").writelines(latest[k] for k in sorted(latest))
     for src in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, src))
