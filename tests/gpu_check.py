@@ -1,4 +1,4 @@
-"""tools/gpu_check.py — quick CUDA-vs-oracle parity sweep (development aid; the tests in tests/ are
+"""tests/gpu_check.py — quick CUDA-vs-oracle parity sweep (development aid; the tests in tests/ are
 the real gate).  Uses oracle/ only as the checker."""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

@@ -1,4 +1,4 @@
-"""tools/parity_report.py [--out profiles/parity_r01] — the parity measurement of SURVEY.md 8(d), with diff images.
+"""tests/parity_report.py [--out profiles/parity_r01] — the parity measurement of SURVEY.md 8(d), with diff images.
 
 For a fixed subset of frames of every configuration (C2: every 50th frame of the 600-frame fly-through at
 3840x2160; C1; reduced C3/C4 fields; a C5 pose batch) the frame rendered by render.so on cuda:0 is compared with
@@ -14,7 +14,8 @@ the CPU checker (oracle/, the C restatement pinned bit-identical to the unmodifi
 north_star's bar is: identical coverage/depth decisions off-edge and >= 99.9 % of pixels within +-1 LSB.
 Writes <out>/report.json and PNGs (zlib only, no imaging library): <cfg>_fNNNN_diff.png — full resolution, 8-bit,
 64 x the largest channel difference (black = identical) — and <cfg>_fNNNN_gpu.png, the GPU frame box-filtered down
-to at most 640 pixels wide.  Needs a GPU; the checker is used as checker only."""
+to at most 640 pixels wide.  Needs a GPU; the checker is used as checker only.
+(Lives under tests/: the oracle is test infrastructure.)"""
 from __future__ import annotations
 
 import argparse
@@ -107,7 +108,7 @@ def compare(got: np.ndarray, want: np.ndarray, mask):
 
 
 def drift(n: int) -> np.ndarray:
-    """tools/run_configs.py's C3 path: creep forward, pan a little."""
+    """tests/run_configs.py's C3 path: creep forward, pan a little."""
     inp = np.zeros(n, S.INPUT_DTYPE)
     for f in range(n):
         inp[f]["up"] = 1.0

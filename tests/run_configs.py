@@ -1,14 +1,15 @@
-"""tools/run_configs.py — runs BASELINE.json's five configurations (C1..C5) on 1..8 GPUs.
+"""tests/run_configs.py — runs BASELINE.json's five configurations (C1..C5) on 1..8 GPUs.
 
-    python tools/run_configs.py --config c1,c3            # one GPU
+    python tests/run_configs.py --config c1,c3            # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/run_configs.py --config c3,c4,c5            # one rank per GPU
+        tests/run_configs.py --config c3,c4,c5            # one rank per GPU
 
 Per configuration: device-resident frames/s (CUDA events, max over ranks), Mpixels/s, Mtriangles/s (input
 triangles), per-stage time, fraction of the HBM roofline for B_alg = 12V + 28A + 8I + 4WH, a parity check
 of sample frames against the oracle (checker only), and — rank 0, bounded sample — the CPU reference.
 C2/C5 are frame-parallel across ranks; C3/C4 are screen-band partitioned with an NCCL all-gather per frame.
-One JSON line per configuration (also appended to gpurun_out/configs.jsonl)."""
+One JSON line per configuration (also appended to gpurun_out/configs.jsonl).
+(Lives under tests/: it uses the oracle as the checker of its sample frames.)"""
 from __future__ import annotations
 
 import argparse

@@ -17,6 +17,6 @@ for w in 1 8; do
 done
 ncu --metrics $M --clock-control none --launch-skip 72 -c 6 --csv --log-file $O/l_c4.csv python tools/c4_probe.py > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"triangle_setup|post_setup|tile_raster_queue|shade_tiles" --launch-skip 48 -c 4 -f -o $O/${TAG}_c4 python tools/c4_probe.py > /dev/null 2>&1
-python tools/run_configs.py --config c1,c2,c3,c4,c5 2>&1 | grep "^{" | cut -c1-260
-python tools/parity_report.py --out $O/parity_$TAG 2>&1 | tail -7
+python tests/run_configs.py --config c1,c2,c3,c4,c5 2>&1 | grep "^{" | cut -c1-260
+python tests/parity_report.py --out $O/parity_$TAG 2>&1 | tail -7
 ls -la $O/*.ncu-rep
