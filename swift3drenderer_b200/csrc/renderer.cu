@@ -1171,6 +1171,16 @@ static void sink_writer(S3RSink *k) {
     }
 }
 
+static void sink_free(S3RSink *k) {   // everything but the writer thread
+    if (k->file) { fclose(k->file); }
+    for (int i = 0; i < S3RSink::RING; i++) {
+        if (k->host[i]) { cudaFreeHost(k->host[i]); }
+        if (k->copied[i]) { cudaEventDestroy(k->copied[i]); }
+    }
+    if (k->dev_yuv) { cudaFree(k->dev_yuv); }
+    delete k;
+}
+
 extern "C" int s3r_sink_open(S3RRenderer *r, const char *path, uint32_t width, uint32_t height, uint32_t fps_num,
                              uint32_t fps_den, int format, S3RSink **out) {
     if (!r || !path || !out) { return fail(S3R_E_ARG, "null argument"); }
@@ -1183,14 +1193,15 @@ extern "C" int s3r_sink_open(S3RRenderer *r, const char *path, uint32_t width, u
     const size_t cw = (width + 1u) / 2u, ch = (height + 1u) / 2u;
     k->frame_bytes = format == 0 ? (size_t)width * height * 4u : (size_t)width * height + 2u * cw * ch;
     k->file = fopen(path, "wb");
-    if (!k->file) { delete k; return fail(S3R_E_IO, std::string("cannot create ") + path); }
+    if (!k->file) { sink_free(k); return fail(S3R_E_IO, std::string("cannot create ") + path); }
     if (format == 1) {
         fprintf(k->file, "YUV4MPEG2 W%u H%u F%u:%u Ip A1:1 C420jpeg XCOLORRANGE=LIMITED\n", width, height, fps_num, fps_den);
-        if (cudaMalloc(&k->dev_yuv, k->frame_bytes) != cudaSuccess) { fclose(k->file); delete k; return fail(S3R_E_CUDA, "sink: cudaMalloc"); }
+        if (cudaMalloc(&k->dev_yuv, k->frame_bytes) != cudaSuccess) { sink_free(k); return fail(S3R_E_CUDA, "sink: cudaMalloc"); }
     }
     for (int i = 0; i < S3RSink::RING; i++) {
         if (cudaMallocHost(reinterpret_cast<void **>(&k->host[i]), k->frame_bytes) != cudaSuccess ||
             cudaEventCreateWithFlags(&k->copied[i], cudaEventDisableTiming) != cudaSuccess) {
+            sink_free(k);
             return fail(S3R_E_CUDA, "sink: pinned ring allocation failed");
         }
     }
@@ -1238,13 +1249,8 @@ extern "C" int s3r_sink_close(S3RSink *k, uint64_t *frames_written) {
     k->cv.notify_all();
     if (k->writer.joinable()) { k->writer.join(); }   // drains the queue first
     cudaSetDevice(k->device);
-    const bool bad = k->io_error || fclose(k->file) != 0;
+    const bool bad = k->io_error || fflush(k->file) != 0;
     if (frames_written) { *frames_written = k->written; }
-    for (int i = 0; i < S3RSink::RING; i++) {
-        if (k->host[i]) { cudaFreeHost(k->host[i]); }
-        if (k->copied[i]) { cudaEventDestroy(k->copied[i]); }
-    }
-    if (k->dev_yuv) { cudaFree(k->dev_yuv); }
-    delete k;
+    sink_free(k);
     return bad ? fail(S3R_E_IO, "sink: write failed") : S3R_OK;
 }
