@@ -87,16 +87,18 @@ def main():
         out, hdr, units, data = kernel_table(rep, "C2 (bench workload): `tile_raster`, 3840x2160, data.bin scene")
         seg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_segments.py"), rep, "tile_raster"],
                              capture_output=True, text=True).stdout
-        out = [f"# {tag}: tile_raster on the bench workload (one launch = 8 poses)", ""] + out + stall_table(rep, "tile_raster") + \
+        out = [f"# {tag}: tile_raster on the bench workload (one launch = 8 poses: the capture passes `--views-per-launch 8`)", ""] + out + stall_table(rep, "tile_raster") + \
             ["", "Warp time barrier to barrier (tools/ncu_segments.py):", "", "```", seg.rstrip(), "```"] + lines_table(rep, "tile_raster", 30)
         open(os.path.join(PROF, f"{tag}_c2_tile_raster.md"), "w").write("\n".join(out) + "\n")
         ix = {h: i for i, h in enumerate(hdr)}
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd = float(data[0][ix["dram__bytes_read.sum"]]) * scale[units[ix["dram__bytes_read.sum"]]]
         wr = float(data[0][ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]]
+        grid = float(data[0][ix["launch__grid_size"]]) if "launch__grid_size" in ix else 4080.0
         json.dump({"tile_raster_dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
-                   "source": f"profiles/{tag}_c2_tile_raster.md (ncu --set full, one launch; the 33 MB frame stays in the 126 MB L2 "
-                             "during the capture, so DRAM writes are far below the algorithmic bytes)"},
+                   "poses_per_launch": int(round(grid / 4080.0)),   # 60 x 68 tiles per 3840x2160 pose
+                   "source": f"profiles/{tag}_c2_tile_raster.md (ncu --set full, one launch of `poses_per_launch` poses: the DRAM writes are "
+                             "the frames themselves, 33 MB each, minus what is still in the 126 MB L2 when the launch ends)"},
                   open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
     doc = [f"# {tag}: general-path kernels on C3 (1 M icosahedrons, 20 M triangles, 4K)", ""]
     for w, title in (("w1", "whole frame on one GPU"), ("w8", "one rank's share of 8 (interleaved tile rows)")):
