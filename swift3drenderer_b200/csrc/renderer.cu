@@ -113,7 +113,7 @@ struct S3RRenderer {
     uint8_t *staging = nullptr;
     size_t staging_bytes = 0;
     HostCopier *copier = nullptr;
-    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1, opt_spans = 1, opt_tmap = 1;
+    int opt_copy_threads = 0, opt_host_bands = 12, opt_pack24 = 1, opt_fused_small = 1, opt_direct_small = 1, opt_spans = 1, opt_tmap = 1, opt_band_taper = 1;
     std::vector<HostPin> pins;
     // fused frame assembly
     std::vector<void *> own_frames, opened_frames;
@@ -151,6 +151,7 @@ extern "C" int s3r_create(S3RRenderer **out, int device) {
     }
     if (const char *env = getenv("S3R_COPY_THREADS")) { r->opt_copy_threads = atoi(env); }
     if (const char *env = getenv("S3R_HOST_BANDS")) { r->opt_host_bands = std::max(1, atoi(env)); }
+    if (const char *env = getenv("S3R_BAND_TAPER")) { r->opt_band_taper = atoi(env) != 0; }
     if (const char *env = getenv("S3R_PACK24")) { r->opt_pack24 = atoi(env) != 0; }
     CUDA_TRY(configure_kernels());
     *out = r;
@@ -569,9 +570,25 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
     const int nb = f.direct_bin ? std::max(1, std::min<int>(raster_bands, (int)f.tiles_y)) : 1;   // the general path's tile queue spans the frame
-    for (int b = 0; b < nb; b++) {
-        f.raster_row0 = (uint32_t)((uint64_t)f.tiles_y * b / nb);
-        f.raster_rows = (uint32_t)((uint64_t)f.tiles_y * (b + 1) / nb) - f.raster_row0;
+    // band edges in tile rows: uniform — the copy workers expand 24-bit pixels about as fast as the link delivers
+    // them, so any larger band builds a backlog — except that the host path's last band is tapered (1/2, 1/4, 1/4):
+    // what is left to expand when the link goes idle is a quarter band instead of a whole one
+    uint32_t edge[S3RRenderer::MAX_SLICES + 1];
+    int n_edges = 0;
+    for (int b = 0; b <= nb; b++) { edge[n_edges++] = (uint32_t)((uint64_t)f.tiles_y * b / nb); }
+    if (r->opt_band_taper && after_band && nb >= 3 && n_edges + 2 <= S3RRenderer::MAX_SLICES) {
+        const uint32_t lo = edge[nb - 1], rows = f.tiles_y - lo;
+        if (rows >= 2) {   // strictly increasing edges: 2 rows -> 1 + 1, 3 -> 2 + 1, 4 -> 2 + 1 + 1, 6 -> 3 + 1 + 2, ...
+            const uint32_t a = lo + (rows + 1) / 2, b2 = a + (f.tiles_y - a) / 2;
+            n_edges = nb;
+            edge[n_edges++] = a;
+            if (b2 > a && b2 < f.tiles_y) { edge[n_edges++] = b2; }
+            edge[n_edges++] = f.tiles_y;
+        }
+    }
+    for (int b = 0; b + 1 < n_edges; b++) {
+        f.raster_row0 = edge[b];
+        f.raster_rows = edge[b + 1] - edge[b];
         r->launches += (uint64_t)launch_raster(f, s);
         if (raster_bands > 1 || band_rows) {
             CUDA_TRY(cudaEventRecord(r->ev_raster[b], s));
