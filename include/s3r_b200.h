@@ -182,6 +182,11 @@ S3R_API int s3r_sink_close(S3RSink *sink, uint64_t *frames_written);
 S3R_API int s3r_debug_exact_math(S3RRenderer *r, uint32_t mode, uint64_t first, uint64_t count, uint32_t seed,
                                  uint64_t result[5]);
 
+/* Test hook, callable without a GPU: the tile-row band edges of a host render (s3r_render_host pipelines raster launches
+ * with device-to-host copies band by band; the last band is tapered).  Returns the number of edges written (bands + 1),
+ * edges_out needs room for 65. */
+S3R_API int s3r_debug_band_edges(uint32_t tiles_y, int bands, int taper, uint32_t *edges_out, int capacity);
+
 /* Harness-only: resets the camera owned by updateAndRender (include/render.h) to the reference's
  * initial state so that the same Input script can be replayed; scene and buffers stay loaded. */
 S3R_API void s3r_dropin_reset(void);

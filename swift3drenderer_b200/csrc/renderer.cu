@@ -455,6 +455,33 @@ static bool encode_out_map(CUtensorMap *map, void *base, uint32_t W, uint64_t ro
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Band edges in tile rows for `nb` <= tiles_y raster launches: uniform — the copy workers expand 24-bit pixels about as
+// fast as the link delivers them, so any larger band builds a backlog — except that (taper, host path) the last band
+// is split 1/2, 1/4, 1/4: what is left to expand when the link goes idle is a quarter band instead of a whole one.
+// Returns the number of edges (bands + 1); every band has at least one tile row.
+static int band_edges(uint32_t tiles_y, int nb, bool taper, uint32_t *edge) {
+    int n_edges = 0;
+    for (int b = 0; b <= nb; b++) { edge[n_edges++] = (uint32_t)((uint64_t)tiles_y * b / nb); }
+    if (taper && nb >= 3 && n_edges + 2 <= S3RRenderer::MAX_SLICES) {
+        const uint32_t lo = edge[nb - 1], rows = tiles_y - lo;
+        if (rows >= 2) {   // strictly increasing edges: 2 rows -> 1 + 1, 3 -> 2 + 1, 4 -> 2 + 1 + 1, 6 -> 3 + 1 + 2, ...
+            const uint32_t a = lo + (rows + 1) / 2, b2 = a + (tiles_y - a) / 2;
+            n_edges = nb;
+            edge[n_edges++] = a;
+            if (b2 > a && b2 < tiles_y) { edge[n_edges++] = b2; }
+            edge[n_edges++] = tiles_y;
+        }
+    }
+    return n_edges;
+}
+
+// Test hook (CPU-callable): the band edges s3r_render_host uses for `tiles_y` tile rows and `bands` requested bands.
+extern "C" int s3r_debug_band_edges(uint32_t tiles_y, int bands, int taper, uint32_t *edges_out, int capacity) {
+    if (!edges_out || tiles_y == 0 || bands < 1 || capacity < S3RRenderer::MAX_SLICES + 1) { return fail(S3R_E_ARG, "bad band request"); }
+    const int nb = std::max(1, std::min<int>(std::min(bands, (int)S3RRenderer::MAX_SLICES - 2), (int)tiles_y));
+    return band_edges(tiles_y, nb, taper != 0, edges_out);
+}
+
 // raster_bands > 1: the tile rows are rasterised in that many launches, with r->ev_raster[b] recorded
 // after band b (used by the staged host path to start the D2H of a band while the next one renders);
 // band_rows[b] receives the first pixel row (relative to y0) after band b.
@@ -570,22 +597,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
     const int nb = f.direct_bin ? std::max(1, std::min<int>(raster_bands, (int)f.tiles_y)) : 1;   // the general path's tile queue spans the frame
-    // band edges in tile rows: uniform — the copy workers expand 24-bit pixels about as fast as the link delivers
-    // them, so any larger band builds a backlog — except that the host path's last band is tapered (1/2, 1/4, 1/4):
-    // what is left to expand when the link goes idle is a quarter band instead of a whole one
     uint32_t edge[S3RRenderer::MAX_SLICES + 1];
-    int n_edges = 0;
-    for (int b = 0; b <= nb; b++) { edge[n_edges++] = (uint32_t)((uint64_t)f.tiles_y * b / nb); }
-    if (r->opt_band_taper && after_band && nb >= 3 && n_edges + 2 <= S3RRenderer::MAX_SLICES) {
-        const uint32_t lo = edge[nb - 1], rows = f.tiles_y - lo;
-        if (rows >= 2) {   // strictly increasing edges: 2 rows -> 1 + 1, 3 -> 2 + 1, 4 -> 2 + 1 + 1, 6 -> 3 + 1 + 2, ...
-            const uint32_t a = lo + (rows + 1) / 2, b2 = a + (f.tiles_y - a) / 2;
-            n_edges = nb;
-            edge[n_edges++] = a;
-            if (b2 > a && b2 < f.tiles_y) { edge[n_edges++] = b2; }
-            edge[n_edges++] = f.tiles_y;
-        }
-    }
+    const int n_edges = band_edges(f.tiles_y, nb, r->opt_band_taper && after_band, edge);
     for (int b = 0; b + 1 < n_edges; b++) {
         f.raster_row0 = edge[b];
         f.raster_rows = edge[b + 1] - edge[b];

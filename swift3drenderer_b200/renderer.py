@@ -72,7 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
-    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges",
 ]
 
 
@@ -147,6 +147,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_sink_open.argtypes = [vp, ctypes.c_char_p, u32, u32, u32, u32, ctypes.c_int, ctypes.POINTER(vp)]
     lib.s3r_sink_submit.argtypes = [vp, vp, vp]
     lib.s3r_sink_close.argtypes = [vp, ctypes.POINTER(u64)]
+    lib.s3r_debug_band_edges.argtypes = [u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u32), ctypes.c_int]
     if path is None:
         _lib = lib
     return lib

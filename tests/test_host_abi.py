@@ -93,3 +93,21 @@ def test_product_never_references_the_oracle():
                     text = open(os.path.join(d, f)).read()
                     code = "\n".join(l for l in text.splitlines() if "import" in l or "#include" in l or "dlopen" in l or "CDLL" in l)
                     assert "oracle" not in code, f"{f} pulls in oracle/: {code}"
+
+
+def test_host_band_edges_cover_every_tile_row_once(renderer_lib):
+    """s3r_render_host pipelines raster launches with device-to-host copies band by band; its band edges (uniform, last band
+    tapered) must start at 0, end at tiles_y and grow strictly — an empty band would be an invalid launch."""
+    import ctypes
+    lib = renderer_lib.load_library()
+    out = (ctypes.c_uint32 * 65)()
+    for tiles_y in list(range(1, 140)) + [2048]:
+        for bands in (1, 2, 3, 4, 7, 8, 12, 16, 24, 62, 64, 1000):
+            for taper in (0, 1):
+                n = lib.s3r_debug_band_edges(tiles_y, bands, taper, out, 65)
+                e = list(out[:n])
+                assert n >= 2 and e[0] == 0 and e[-1] == tiles_y and all(b > a for a, b in zip(e, e[1:])), (tiles_y, bands, taper, e)
+                if not taper:
+                    assert n - 1 == min(bands, tiles_y, 62)
+    n = lib.s3r_debug_band_edges(68, 12, 1, out, 65)          # 4K: 68 tile rows, 12 bands, last one split 3 + 1 + 2
+    assert list(out[:n]) == [0, 5, 11, 17, 22, 28, 34, 39, 45, 51, 56, 62, 65, 66, 68]
