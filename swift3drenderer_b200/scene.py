@@ -556,6 +556,70 @@ def clip_stress_scene(n: int = 50000, seed: int = 11, textures: Optional[np.ndar
     return concat_scenes(slab, front)
 
 
+def hazard_scene(textures: Optional[np.ndarray] = None) -> Scene:
+    """A handful of triangles aimed at the reference's quirks (SURVEY.md 8 hazard list), seen from the initial camera
+    (origin, looking down -z): H2 exact depth ties (the same triangle twice with different colours, and two coplanar
+    triangles overlapping in part: the first in list order must win), H3 a fan with shared edges and a shared apex (pixels
+    on an edge belong to both neighbours), H4 slivers and dots around the `area < 10` cull, back faces, H5 kind taken from
+    corner 0, H9 vertices exactly on and just around the near plane z = -0.1 (on the plane counts as behind), H12 a textured
+    triangle with constant uv (rip-map level inf -> 256), a huge triangle running far off screen (long incremental walks),
+    triangles partly and wholly outside the frame."""
+    tx = procedural_textures(2) if textures is None else textures
+    b = _Builder()
+    n = [0.0, 0.0, 1.0]
+
+    def tri(pts, attrs):
+        v0 = b.add_vertices(pts)
+        a0 = b.add_attrs(attrs)
+        b.vi += [v0, v0 + 1, v0 + 2]
+        b.ai += [a0, a0 + 1, a0 + 2]
+
+    def col(rgb, normal=n):
+        return color_attr(normal, rgb)
+
+    # H2: identical triangles, different colours — the first must own every pixel
+    quad = [(-3.0, 1.0, -10.0), (-3.0, 3.0, -10.0), (-1.0, 1.0, -10.0)]
+    tri(quad, [col((255, 0, 0))] * 3)
+    tri(quad, [col((0, 255, 0))] * 3)
+    # H2: coplanar, partly overlapping, later one larger
+    tri([(0.0, 1.0, -10.0), (0.0, 3.0, -10.0), (2.0, 1.0, -10.0)], [col((0, 0, 255))] * 3)
+    tri([(-0.5, 0.5, -10.0), (-0.5, 3.5, -10.0), (3.0, 0.5, -10.0)], [col((255, 255, 0))] * 3)
+    # H3: a fan of six triangles around a shared apex, shared edges, smooth normals
+    import math
+    c = (3.5, -1.5, -8.0)
+    ring = [(c[0] + 1.5 * math.cos(k * math.pi / 3), c[1] + 1.5 * math.sin(k * math.pi / 3), c[2] - 0.3 * (k % 2)) for k in range(6)]
+    for k in range(6):
+        p, q = ring[(k + 1) % 6], ring[k]
+        tri([c, p, q], [col((40 * k + 30, 200 - 30 * k, 90), _normalize([0.2 * (k - 2), 0.1, 1.0]))] * 3)
+    # H4: slivers and dots around the area cull, and a back face (negative area)
+    for k in range(8):
+        x, s_ = -4.0 + 0.45 * k, 0.004 * (k + 1)
+        tri([(x, -1.0, -6.0), (x, -1.0 + 30 * s_, -6.0), (x + s_, -1.0, -6.0)], [col((250, 250, 250))] * 3)
+        tri([(x, -2.0, -6.0), (x, -2.0 + s_ * 4, -6.0), (x + s_ * 4, -2.0, -6.0)], [col((250, 120, 250))] * 3)
+    tri([(-3.0, -3.0, -9.0), (-1.0, -3.0, -9.0), (-3.0, -1.5, -9.0)], [col((10, 250, 250))] * 3)   # wound the other way
+    # H5: kind from corner 0 — a textured triangle and a coloured one whose other corners carry the other kind
+    # (the reference reads the other corners' records through the same union: a colour record's blue is a texture
+    # record's u, a texture record's index bits and u are a colour record's red and blue)
+    tri([(-1.0, -3.2, -7.0), (-1.0, -1.7, -7.0), (0.5, -3.2, -7.0)],
+        [texture_attr(n, 1, (0.0, 0.0)), col((50, 100, 2.0)), texture_attr(n, 0, (2.0, 1.5))])
+    tri([(0.7, -3.2, -7.0), (0.7, -1.7, -7.0), (2.2, -3.2, -7.0)],
+        [col((200, 100, 50)), texture_attr(n, 1, (200.0, 3.0)), col((100, 200, 50))])
+    # H9: vertices exactly on the near plane (z = -0.1: behind), one ulp in front of it, and a straddler through it
+    near = np.float32(-0.1)
+    tri([(-0.02, 0.0, near), (-0.02, 0.03, near), (0.0, 0.0, -0.3)], [col((255, 128, 0))] * 3)            # two corners on the plane
+    tri([(0.01, 0.0, np.nextafter(near, np.float32(-1))), (0.01, 0.03, -0.2), (0.03, 0.0, -0.3)], [col((128, 255, 0))] * 3)
+    tri([(-0.05, -0.04, 0.05), (-0.05, -0.01, -0.4), (-0.02, -0.04, -0.4)], [col((0, 128, 255))] * 3)     # one corner behind the eye
+    # H12: constant uv -> no texture gradient -> level = ooz / 0 = inf -> clamped to 256
+    tri([(2.5, 1.0, -9.0), (2.5, 2.5, -9.0), (4.0, 1.0, -9.0)], [texture_attr(n, 0, (0.25, 0.75))] * 3)
+    # long walks: a floor-like textured triangle running far beyond the frame on three sides
+    tri([(-400.0, -4.0, -2.0), (0.0, -4.0, -900.0), (400.0, -4.0, -2.0)],
+        [texture_attr([0.0, 1.0, 0.0], 0, (0.0, 0.0)), texture_attr([0.0, 1.0, 0.0], 0, (40.0, 90.0)), texture_attr([0.0, 1.0, 0.0], 0, (80.0, 0.0))])
+    # partly and wholly outside the frame
+    tri([(5.5, 2.0, -9.0), (5.5, 4.5, -9.0), (9.0, 2.0, -9.0)], [col((90, 90, 250))] * 3)
+    tri([(30.0, 0.0, -9.0), (30.0, 2.0, -9.0), (33.0, 0.0, -9.0)], [col((250, 90, 90))] * 3)
+    return b.scene(tx)
+
+
 def c3_scene(n: int = 1_000_000, seed: int = 7, textures: Optional[np.ndarray] = None) -> Scene:
     """C3: n textured icosahedrons (20 n triangles, shared vertices, per-corner attributes) filling the
     view frustum around z = -4000 so that ~21 % of the triangles survive the area >= 10 cull at 4K from
