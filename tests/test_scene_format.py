@@ -101,3 +101,20 @@ def test_input_scripts_are_deterministic_and_cover_ranges():
     assert np.abs(np.diff(a["mouse"], axis=0)).max() <= 12.01
     c1 = S.input_script("c1_path", 300)
     assert c1["down"][:60].all() and c1["right"][60:120].all() and (np.diff(c1["mouse"][120:, 0]) == 2).all()
+
+
+def test_hazard_scene_is_a_valid_data_bin(tmp_path):
+    """The quirk scene (scene.hazard_scene, golden cases hazards_*) must satisfy the format contract — including its
+    mixed-kind triangles, which are legal: the reference takes kind and texture index from corner 0 — and survive a
+    write/read round trip byte for byte."""
+    sc = S.hazard_scene()
+    assert S.validate(sc) == []
+    c = sc.counts()
+    assert c["T"] == 36 and c["I"] == 108 and c["V"] == 108 and c["A"] == 108
+    kinds = sc.attributes["kind"][sc.attribute_indices.reshape(-1, 3).astype(np.int64)]
+    assert int((kinds.min(axis=1) != kinds.max(axis=1)).sum()) == 2          # exactly the two mixed-kind triangles
+    path = str(tmp_path / "hazards.bin")
+    S.write_data_bin(path, sc)
+    back = S.read_data_bin(path)
+    assert np.array_equal(back.vertices, sc.vertices) and np.array_equal(back.vertex_indices, sc.vertex_indices)
+    assert back.attributes.tobytes() == sc.attributes.tobytes() and np.array_equal(back.textures, sc.textures)
