@@ -1,24 +1,25 @@
 #!/usr/bin/env python
 """bench.py — frames/s at 3840x2160 of the updateAndRender() hot path on N B200s.
 
-Workload (BASELINE.json configs[1], "C2"): the reference's data.bin demo scene (39 vertices, 51
-triangles, 2 rip-map atlases) at 3840x2160 over the 600-frame recorded fly-through
-(swift3drenderer_b200.scene.input_script("flythrough")).  One *step* = the whole 600-frame
-fly-through.  N > 1: frame-parallel, one process per GPU, every rank renders the full fly-through
-(weak scaling, no data-path collective — frames are independent once the 600 camera poses have
-been replayed on the host).
-
-  value    device-resident frames/s: camera matrices in, 24 consecutive poses of the recorded path per
-           launch set (s3r_render_device's multi-view batch), frames left in HBM (ring of 4 batches
-           = 3.2 GB > the 126 MB L2), CUDA-event timed on the launching stream, max over ranks.
-  e2e      the same 600 frames through the reference-facing plugin call
-           updateAndRender(const PixelData*, const Input*) with the caller's pageable double
-           buffer: host camera step, 48 B H2D, render, 33.2 MB D2H inside the timed region.
-  roofline HBM: algorithmic bytes per frame (12V + 28A + 8I + 4WH) / the tile
-           rasteriser's average launch time (CUDA events around every launch in the timed region).
-  cpu_baseline / --impl reference: the reference's own render.cpp (oracle/_ref, compiled unmodified;
-           falls back to the C port oracle/render_oracle.c) on the host cores, one replica process per
-           core over a bounded sample of the same frames.
+Primary workload (BASELINE.json configs[2], "C3", the configuration north_star's target is quoted on): 1 M textured
+icosahedrons (V = 12 M, T = 20 M, A = 60 M; swift3drenderer_b200.scene.c3_scene, seed 7) at 3840x2160 over an 8-pose
+drift path.  One *step* = those 8 frames, one pose per launch set.
+  N = 1   the whole frame on one GPU.
+  N > 1   STRONG scaling: the frame is partitioned by screen space (interleaved 32-pixel tile rows, rank = row mod N), one
+          process per GPU; every rank's shading kernel stores its rows straight into the full-size frame of EVERY rank over
+          NVLink peer memory (CUDA IPC) and a one-element NCCL all-reduce per frame is the ordering fence, so that every
+          rank holds the assembled frame.  `--partition rows|bands` selects the NCCL all-gather assemblies instead.
+  value    assembled frames/s, device-resident, CUDA-event timed on the launching stream, max over ranks.
+  e2e      the same poses through the reference-facing plugin call updateAndRender(const PixelData*, const Input*)
+           on a private render.so beside C3's data.bin with the caller's pageable double buffer (host camera step,
+           48 B H2D, render, D2H of the frame inside the timed region).  N > 1: one replica per rank on its own GPU.
+  roofline per kernel from CUDA events recorded after every launch of the timed region (option "timing") and for the
+           frame (B_alg = 12V + 28A + 8I + 4WH); `traffic` from the committed ncu capture.
+  cpu_baseline / --impl reference: the reference's own render.cpp (oracle/_ref, compiled unmodified; falls back to the C
+           port) on the host cores: one single-threaded replica process per core (bounded by memory: each replica maps
+           the 4 GB scene and allocates the reference's 2x scratch), one frame per replica and step.
+Secondary record (`secondary`, BASELINE.json configs[1], "C2"): the reference's data.bin demo scene, 600-frame recorded
+fly-through, frame-parallel at N > 1 — last round's headline, kept for continuity (value, e2e, roofline, cpu_baseline).
 """
 from __future__ import annotations
 
@@ -30,37 +31,182 @@ import subprocess
 import sys
 import tempfile
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "frames/s at 3840x2160 (data.bin scene, 600-frame fly-through)"
+METRIC = "frames/s at 3840x2160 (1 M textured icosahedrons = 20 M triangles, screen-partitioned over N GPUs)"
 UNIT = "frames/s"
+C2_METRIC = "frames/s at 3840x2160 (data.bin scene, 600-frame fly-through)"
+POSES = 8   # frames per step of the primary workload
+
+
+# --------------------------------------------------------------------------------------------------
+# workload definition (shared by both arms)
+# --------------------------------------------------------------------------------------------------
+def drift_inputs(n: int) -> np.ndarray:
+    """Slow drift through the field: creep forward, pan a little (keeps the field in view)."""
+    from swift3drenderer_b200 import scene as S
+    inp = np.zeros(n, S.INPUT_DTYPE)
+    for f in range(n):
+        inp[f]["up"] = 1.0
+        inp[f]["mouse"] = (0.5 * f, 0.2 * f)
+    return inp
+
+
+def c3_data_bin(solids: int, wait_s: float = 600.0) -> str:
+    """data.bin of the C3 field, generated once per box (4 GB for 1 M solids) and shared by every rank and both arms."""
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    path = os.path.join(base, f"s3r_c3_{solids}_seed7.data.bin")
+    lock = path + ".lock"
+    if os.path.exists(path):
+        return path
+    try:
+        fd = os.open(lock, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+    except FileExistsError:
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > wait_s:
+                raise SystemExit(f"bench.py: {path} did not appear within {wait_s:.0f} s (stale {lock}?)")
+            time.sleep(0.25)
+        return path
+    try:
+        from swift3drenderer_b200 import scene as S
+        tmp = path + f".tmp{os.getpid()}"
+        S.write_data_bin(tmp, S.c3_scene(solids))
+        os.rename(tmp, path)
+    finally:
+        os.close(fd)
+        os.unlink(lock)
+    return path
+
+
+def frame_digest(frame: np.ndarray) -> dict:
+    a = np.ascontiguousarray(frame, np.uint32)
+    return {"sum": int(a.sum(dtype=np.uint64)), "crc32": int(zlib.crc32(a.tobytes()))}
+
+
+def affinity_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 16.0
 
 
 # --------------------------------------------------------------------------------------------------
 # CPU reference arm (test infrastructure used as a *timed baseline*, never as the product)
 # --------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    kind, data_bin, W, H, frames, n_inputs, barrier_t = args
+def _replica_main(conn, kind, data_bin, W, H, n_inputs):
+    """One single-threaded replica of the CPU reference: loads the scene, renders pose 0 (reply: digest), then renders the
+    next pose of the drift path for every 'go' it receives (reply: seconds spent inside the render call)."""
+    sys.path.insert(0, ROOT)
+    inp = drift_inputs(n_inputs)
+    out = np.empty((H, W), np.uint32)
+    if kind == "reference":
+        from oracle import refso
+        ref = refso.RefRenderer(data_bin)
+        render = lambda f: ref.update_and_render(W, H, inp[f], out)   # noqa: E731  (camera state lives in the library)
+    else:
+        from oracle import port
+        osc = port.OracleScene(path=data_bin)
+        mats = port.camera_path(inp)
+        render = lambda f: out.__setitem__(slice(None), osc.render(mats[f], W, H)["pixels"])   # noqa: E731
+    t0 = time.perf_counter()
+    render(0)
+    conn.send(("ready", time.perf_counter() - t0, frame_digest(out)))
+    f = 1
+    while True:
+        msg = conn.recv()
+        if msg != "go":
+            break
+        t0 = time.perf_counter()
+        render(f % n_inputs)
+        conn.send(("done", time.perf_counter() - t0, f))
+        f += 1
+    conn.close()
+
+
+class CpuReplicas:
+    """`n` replica processes of the reference (memory-bounded); step() = one frame per replica, in parallel."""
+
+    def __init__(self, data_bin: str, W: int, H: int, n_inputs: int, gb_per_replica: float, cap: int = 0):
+        from oracle import refso, port
+        self.kind = "reference" if refso.available() else "port"
+        if self.kind == "port":
+            port.build()
+        n = affinity_cores()
+        n = max(1, min(n, int(mem_available_gb() * 0.7 / max(gb_per_replica, 0.05))))
+        if cap:
+            n = min(n, cap)
+        self.n = n
+        ctx = mp.get_context("spawn")
+        self.conns, self.procs = [], []
+        t0 = time.perf_counter()
+        for _ in range(n):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_replica_main, args=(b, self.kind, data_bin, W, H, n_inputs), daemon=True)
+            p.start()
+            self.conns.append(a); self.procs.append(p)
+        ready = [c.recv() for c in self.conns]
+        self.load_and_first_frame_s = time.perf_counter() - t0
+        self.frame0 = ready[0][2]
+        assert all(r[2] == self.frame0 for r in ready), "replicas disagree on pose 0"
+
+    def step(self):
+        """-> (wall seconds of the step, summed in-call seconds)."""
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send("go")
+        busy = [c.recv()[1] for c in self.conns]
+        return time.perf_counter() - t0, sum(busy)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send("stop")
+            except OSError:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+
+
+def _c2_cpu_worker(args):
+    kind, data_bin, W, H, frames, n_inputs = args
     sys.path.insert(0, ROOT)
     from swift3drenderer_b200 import scene as S
     inp = S.input_script("flythrough", n_inputs)
     want = set(frames)
     out = np.empty((H, W), np.uint32)
-    tiny = np.empty((1, 1), np.uint32)
     if kind == "reference":
         from oracle import refso
         ref = refso.RefRenderer(data_bin)
-        t0 = time.perf_counter()
-        for f in range(max(frames) + 1):  # the reference's camera is internal: replay every Input, render
-            if f in want:                  # unwanted frames at 1x1 (the triangle loop of 51 triangles is negligible)
+        # the reference's camera is internal: every Input is replayed; frames outside the sample are rendered at 16 x 9
+        # AFTER the sampled frame's time has been taken (the 51-triangle loop is negligible; the depth-buffer realloc and
+        # its page faults on the way back to 4K are part of the reference's own resize path and stay inside the sample)
+        small = np.empty((9, 16), np.uint32)
+        dt = 0.0
+        for f in range(max(frames) + 1):
+            if f in want:
+                t0 = time.perf_counter()
                 ref.update_and_render(W, H, inp[f], out)
+                dt += time.perf_counter() - t0
             else:
-                ref.update_and_render(1, 1, inp[f], tiny)
-        dt = time.perf_counter() - t0
+                ref.update_and_render(16, 9, inp[f], small)
         ref.close()
     else:
         from oracle import port
@@ -73,30 +219,22 @@ def _cpu_worker(args):
     return dt, len(frames)
 
 
-def cpu_reference_fps(data_bin: str, W: int, H: int, n_inputs: int, sample_frames: int, workers: int):
-    """frames/s of the CPU reference over `sample_frames` evenly spaced frames, `workers` replicas."""
+def c2_cpu_reference_fps(data_bin: str, W: int, H: int, n_inputs: int, sample_frames: int, workers: int):
+    """frames/s of the CPU reference over `sample_frames` evenly spaced frames of the fly-through, `workers` replicas."""
     from oracle import refso, port
     kind = "reference" if refso.available() else "port"
     if kind == "port":
         port.build()
     frames = sorted(set(np.linspace(0, n_inputs - 1, sample_frames).astype(int).tolist()))
-    shards = [frames[i::workers] for i in range(workers)]
-    shards = [s for s in shards if s]
+    shards = [s for s in (frames[i::workers] for i in range(workers)) if s]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(len(shards)) as pool:
-        res = pool.map(_cpu_worker, [(kind, data_bin, W, H, s, n_inputs, 0) for s in shards])
+        res = pool.map(_c2_cpu_worker, [(kind, data_bin, W, H, s, n_inputs) for s in shards])
     wall = time.perf_counter() - t0
-    busy = max(r[0] for r in res)  # slowest replica's render loop (excludes interpreter start-up)
+    busy = max(r[0] for r in res)
     return {"kind": kind, "cores": len(shards), "frames": len(frames), "wall_s": wall, "busy_s": busy,
             "fps": len(frames) / busy, "fps_single_core": len(frames) / sum(r[0] for r in res)}
-
-
-def affinity_cores() -> int:
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
 
 
 # --------------------------------------------------------------------------------------------------
@@ -117,7 +255,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -162,17 +300,25 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes(poses_per_launch: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per tile_raster launch from the committed ncu capture
-    (profiles/roofline_traffic.json), scaled from the capture's poses per launch to this run's, or None."""
+def ncu_traffic():
+    """Committed ncu figures (profiles/roofline_traffic.json): dram bytes per launch by workload and kernel, or {}."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(path):
-        try:
-            rec = json.load(open(path))
-            return int(rec["tile_raster_dram_bytes_per_launch"] / max(rec.get("poses_per_launch", 1), 1) * poses_per_launch)
-        except (ValueError, KeyError):
-            return None
-    return None
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
+
+
+# Algorithmic bytes per launch of the general path's kernels (DESIGN.md section 5): every logical input the kernel is
+# the first to need, read once, and the output pixels written once; together they are B_alg = 12V + 28A + 8I + 4WH.
+# Scratch (raster-space vertices, keys, work lists) is excluded, as SURVEY.md 8(d) prescribes.
+def kernel_alg_bytes(name: str, c: dict, px: int) -> int:
+    return {
+        "vertex_stage": 12 * c["V"],
+        "triangle_classify": 4 * c["I"],
+        "cluster_front": 12 * c["V"] + 4 * c["I"],
+        "shade_tiles": 4 * c["I"] + 28 * c["A"] + 4 * px,
+    }.get(name, 0)
 
 
 _RESULT_FD = None
@@ -193,76 +339,96 @@ def emit(line: dict) -> None:
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--frames", type=int, default=600, help="frames per step (the recorded fly-through)")
-    ap.add_argument("--views-per-launch", type=int, default=24,
-                    help="consecutive poses of the recorded path rendered per launch set (multi-view batch, s3r_render_device)")
-    ap.add_argument("--ring", type=int, default=4, help="device-resident output batches kept (ring > L2)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 3 per core, >= 24)")
+    ap.add_argument("--c3-solids", type=int, default=1_000_000, help="icosahedrons of the primary workload (20 triangles each)")
+    ap.add_argument("--partition", default="fused", choices=["fused", "rows", "bands"],
+                    help="N > 1: interleaved tile rows stored straight into every rank's frame over NVLink peer memory (fused), "
+                         "interleaved tile rows + NCCL all-gather (rows), contiguous bands + NCCL all-gather (bands)")
+    ap.add_argument("--ring", type=int, default=4, help="assembled frames kept per rank (ring slots)")
+    ap.add_argument("--c2-frames", type=int, default=600, help="frames per step of the secondary record (the recorded fly-through)")
+    ap.add_argument("--c2-views-per-launch", type=int, default=24)
+    ap.add_argument("--cpu-replicas", type=int, default=0, help="cap on CPU reference replicas (0 = cores, bounded by memory)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    W, H, F = args.width, args.height, args.frames
+    W, H = args.width, args.height
     assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("S3R_ALLOW_SHORT_WARMUP"), "W >= 3 warm-up steps"
-
-    from swift3drenderer_b200 import assets, scene as S
-    data_bin = assets.ensure_shipped_data_bin()
-    sc = S.read_data_bin(data_bin)
-    counts = sc.counts()
+    solids = args.c3_solids
+    counts = {"V": 12 * solids, "I": 60 * solids, "A": 60 * solids, "T": 20 * solids}
     b_alg = 12 * counts["V"] + 28 * counts["A"] + 8 * counts["I"] + 4 * W * H
     config = {
-        "workload": f"C2: reference data.bin scene (V={counts['V']}, T={counts['T']}, {counts['textures']} rip-map atlases) "
-                    f"at {W}x{H}, {F}-frame recorded fly-through; step = {F} frames",
-        "parallelism": f"frame-parallel x{world}" if world > 1 else "single GPU",
-        "frames_per_step": F, "views_per_launch": args.views_per_launch,
-        "l2": f"outputs cycle through a ring of {args.ring} batches of {args.views_per_launch} frames "
-              f"({args.ring * args.views_per_launch * 4 * W * H / 1e6:.0f} MB > 126 MB L2); "
-              "the 2.1 MB scene is L2-resident by the nature of the workload",
+        "workload": f"C3: {solids} textured icosahedrons (V={counts['V']}, T={counts['T']}, A={counts['A']}, 2 rip-map atlases), "
+                    f"seed 7, at {W}x{H}, {POSES}-pose drift path; step = {POSES} frames, one pose per launch set",
+        "parallelism": ("single GPU, whole frame" if world == 1 else
+                        {"fused": f"screen partition x{world}: interleaved 32-pixel tile rows, rows stored into every rank's frame over "
+                                  "NVLink peer memory by the shading kernel, 1-element NCCL all-reduce per frame as the fence",
+                         "rows": f"screen partition x{world}: interleaved tile rows + NCCL all-gather + de-interleave",
+                         "bands": f"screen partition x{world}: contiguous bands + NCCL all-gather"}[args.partition]),
+        "frames_per_step": POSES,
+        "l2": f"inputs larger than L2: {b_alg / 1e6:.0f} MB of scene + frame per frame against the 126 MB L2; outputs cycle "
+              f"through a ring of {args.ring} frames",
     }
 
     # ---------------------------------------------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = affinity_cores()
-        sample = args.cpu_sample or max(24, 3 * cores)
-        sample = min(sample, F)
+        t_start = time.perf_counter()
+        data_bin = c3_data_bin(solids)
+        reps = CpuReplicas(data_bin, W, H, 4096, gb_per_replica=8.0 * solids / 1e6 + 0.3, cap=args.cpu_replicas)
+        log(f"reference arm: {reps.n} replicas ({reps.kind}), load + pose 0 took {reps.load_and_first_frame_s:.1f} s")
         for _ in range(min(args.warmup, 1)):
-            cpu_reference_fps(data_bin, W, H, F, min(sample, cores), cores)
-        t0 = time.perf_counter()
-        runs = [cpu_reference_fps(data_bin, W, H, F, sample, cores) for _ in range(args.steps)]
-        fps = sum(r["frames"] for r in runs) / sum(r["busy_s"] for r in runs)
-        ms_per_step = 1e3 * sum(r["busy_s"] for r in runs) / len(runs)
+            reps.step()
+        walls, busys = [], []
+        for _ in range(args.steps):
+            w, b = reps.step()
+            walls.append(w); busys.append(b)
+        reps.close()
+        frames = reps.n * args.steps
+        fps = frames / sum(walls)
         line = {
             "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": runs[0]["cores"], "kind": runs[0]["kind"],
-                             "sample": f"{runs[0]['frames']} evenly spaced frames of the {F}-frame fly-through per step, "
-                                       f"one single-threaded replica per core ({runs[0]['cores']}), render loops only",
-                             "single_core_fps": runs[0]["fps_single_core"]},
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": reps.n, "kind": reps.kind,
+                             "sample": f"{reps.n} frames per step: one single-threaded replica per core (bounded by memory), each "
+                                       f"rendering the next pose of the drift path at {W}x{H}; scene load and pose 0 are warm-up",
+                             "single_core_fps": frames / sum(busys)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+            "gpu_launches": 0, "frame0_digest": reps.frame0, "wall_s": time.perf_counter() - t_start,
         }
+        if not args.no_secondary:
+            from swift3drenderer_b200 import assets
+            cores = affinity_cores()
+            c = c2_cpu_reference_fps(assets.ensure_shipped_data_bin(), W, H, args.c2_frames, min(args.c2_frames, max(24, 3 * cores)), cores)
+            line["secondary"] = {"metric": C2_METRIC, "value": c["fps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+                                 "sample": f"{c['frames']} evenly spaced frames of the fly-through, one replica per core",
+                                 "single_core_fps": c["fps_single_core"]}
         emit(line)
         return
 
     # ---------------------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
-    from swift3drenderer_b200 import renderer as R
+    from swift3drenderer_b200 import assets, multigpu, renderer as R, scene as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the renderer has no CPU fallback")
@@ -270,21 +436,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    R.build_library()
-    r = R.Renderer(local_rank)
-    r.load_scene_file(data_bin)
-    mats = R.camera_path(S.input_script("flythrough", F))
-    ring = torch.empty((args.ring, args.views_per_launch, H, W), dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the renderer launches on it, the events time it
-    torch.cuda.set_stream(stream)
-    vpl = args.views_per_launch
-
-    def run_step():
-        k = 0
-        for f0 in range(0, F, vpl):
-            r.render_device(mats[f0:f0 + vpl], W, H, ring[k % args.ring].data_ptr(), stream=stream.cuda_stream)
-            k += 1
+    os.environ["S3R_DEVICE"] = str(local_rank)   # the drop-in (updateAndRender) of this rank renders on this rank's GPU
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -292,10 +444,90 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    R.build_library()
+    if rank == 0:
+        t0 = time.perf_counter()
+        data_bin = c3_data_bin(solids)
+        log(f"C3 data.bin ready in {time.perf_counter() - t0:.1f} s: {data_bin}")
+    barrier()
+    data_bin = c3_data_bin(solids)
+    t0 = time.perf_counter()
+    r = R.Renderer(local_rank)
+    r.load_scene_file(data_bin)
+    log(f"rank {rank}: scene loaded in {time.perf_counter() - t0:.1f} s")
+    inputs = drift_inputs(POSES)
+    mats = R.camera_path(inputs)
+    stream = torch.cuda.Stream(dev)   # a real (non-default) stream: the renderer launches on it, the events time it
+    torch.cuda.set_stream(stream)
+
+    # ---- the step --------------------------------------------------------------------------------
+    assembled = [None]   # callable -> this rank's assembled frame of the last pose (host array)
+    pf = None
+    comm = None
+    if world == 1:
+        ring = torch.empty((args.ring, H, W), dtype=torch.int32, device=dev)
+        k = [0]
+
+        def run_step():
+            for f in range(POSES):
+                r.render_device(mats[f], W, H, ring[k[0] % args.ring].data_ptr(), stream=stream.cuda_stream)
+                k[0] += 1
+        assembled[0] = lambda: ring[(k[0] - 1) % args.ring].cpu().numpy().view(np.uint32)
+    elif args.partition == "fused":
+        pf = multigpu.PeerFrames(r, H, W, rank, world, dev, ring=args.ring)
+        last = [0]
+
+        def run_step():
+            for f in range(POSES):
+                last[0] = pf.render(mats[f], stream=stream.cuda_stream)
+                pf.fence_async()
+        assembled[0] = lambda: pf.read(last[0])
+        comm = {"kind": "peer stores (st.global.v4 over NVLink, CUDA IPC) from shade_tiles + 1-element NCCL all-reduce per frame",
+                "bytes_per_frame_per_rank_sent": int(4 * W * H / world * (world - 1)),
+                "bytes_per_frame_total": int(4 * W * H * (world - 1))}
+    elif args.partition == "rows":
+        asm = multigpu.InterleavedAssembler(H, W, rank, world, dev, R.tile_height())
+        full = [None]
+
+        def run_step():
+            for f in range(POSES):
+                r.render_device_rows(mats[f], W, H, world, rank, asm.mine.data_ptr(), stream=stream.cuda_stream)
+                full[0] = asm.gather()
+        assembled[0] = lambda: full[0].cpu().numpy().view(np.uint32)
+        comm = {"kind": "NCCL all-gather of compacted tile rows + index_select", "bytes_per_frame_total": int(4 * W * H * (world - 1))}
+    else:
+        frames = torch.zeros((args.ring, H, W), dtype=torch.int32, device=dev)
+        y0, y1 = multigpu.band_edges(H, world)[rank]
+        assert multigpu.equal_bands(H, world), "--partition bands needs H % N == 0"
+        k = [0]
+        full = [None]
+
+        def run_step():
+            for f in range(POSES):
+                fr = frames[k[0] % args.ring]
+                r.render_device(mats[f], W, H, fr[y0:y1].data_ptr(), y0=y0, y1=y1, stream=stream.cuda_stream)
+                full[0] = multigpu.gather_bands_inplace(fr, rank, world)
+                k[0] += 1
+        assembled[0] = lambda: full[0].cpu().numpy().view(np.uint32)
+        comm = {"kind": "in-place NCCL all-gather of contiguous bands", "bytes_per_frame_total": int(4 * W * H * (world - 1))}
+
+    def drain():
+        if pf is not None:
+            pf.drain()
+        torch.cuda.synchronize(dev)
+
     for _ in range(args.warmup):
         run_step()
-        while r.finish():  # capacity regrowth happens here, outside the timed region
+        drain()
+        while max_over_ranks(1.0 if r.finish() else 0.0) > 0:   # capacity regrowth happens here, outside the timed region
             run_step()
+            drain()
     r.set_option("timing", 1)
     r.timing(reset=True)
     clocks = ClockSampler(local_rank)
@@ -307,87 +539,218 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         run_step()
+    if pf is not None:
+        pf.join(stream)          # the timed region ends when the last frame's fence has completed
     e1.record(stream)
     barrier()
-    overflowed = r.finish()
-    assert not overflowed, "capacity overflow inside the timed region"
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    assert not r.finish(), "capacity overflow inside the timed region"
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = r.kernel_launches - launches0
+    kt = r.kernel_timing()
     stage = r.timing(reset=True)
     r.set_option("timing", 0)
     clock_info = clocks.stop() if rank == 0 else None
-
-    frames_total = world * args.steps * F
+    frames_total = args.steps * POSES
     value = frames_total / (ms_total / 1e3)
 
-    # ---- e2e: the reference-facing plugin call with host buffers ---------------------------------
+    # ---- checks (untimed): the assembled frame equals the whole frame; digest of pose 0 for the cross-arm comparison
+    whole_last = r.render(mats[POSES - 1], W, H)[0]
+    same = bool(np.array_equal(assembled[0](), whole_last))
+    banded_equals_whole = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
+    frame0 = frame_digest(r.render(mats[0], W, H)[0])
+    stats_last = r.stats(0)
+
+    # ---- e2e: the reference-facing plugin call with host buffers, this rank's replica on this rank's GPU -----------
     e2e = None
     if not args.no_e2e:
+        t0 = time.perf_counter()
         d = R.DropIn(data_bin)
-        inp = S.input_script("flythrough", F)
-        double = np.zeros((2, H, W), np.uint32)  # pageable, alternated per call like main.swift:117-118
-        for f in range(0, 12):  # warm: scene load, buffer registration, capacity growth
-            d.update_and_render(W, H, inp[f], out=double[f & 1])
+        double = np.zeros((2, H, W), np.uint32)   # pageable, alternated per call like main.swift:117-118
+        d.update_and_render(W, H, inputs[0], out=double[0])   # scene load
+        e2e_frame0 = frame_digest(double[0])
+        for f in range(1, 2 * POSES):   # warm: capacity growth, staging buffers, copy workers
+            d.update_and_render(W, H, inputs[f % POSES], out=double[f & 1])
+        log(f"rank {rank}: drop-in ready in {time.perf_counter() - t0:.1f} s")
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             d.reset_camera()
-            for f in range(F):
-                d.update_and_render(W, H, inp[f], out=double[f & 1])
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": frames_total / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": 48 * F,
-               "d2h_bytes_per_step": 4 * W * H * F,
-               "call": "updateAndRender(const PixelData*, const Input*) on a private render.so + data.bin, pageable "
-                       "double buffer registered once by the library; synchronous per frame"}
-        checksum = int(double[(F - 1) & 1].astype(np.uint64).sum())
+            for f in range(POSES):
+                d.update_and_render(W, H, inputs[f], out=double[f & 1])
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * frames_total / dt, "unit": UNIT, "h2d_bytes_per_step": 48 * POSES * world,
+               "d2h_bytes_per_step": 3 * W * H * POSES * world,
+               "mode": "one frame per call on one GPU" if world == 1 else
+                       f"{world} independent updateAndRender replicas, one per rank, each on its own GPU (S3R_DEVICE = LOCAL_RANK); "
+                       "the screen partition is what `value` measures",
+               "call": "updateAndRender(const PixelData*, const Input*) on a private render.so beside C3's data.bin; caller's buffer is a "
+                       "pageable double buffer (not registered: S3R_PIN_HOST unset); transport = frame shaded in row bands, each band "
+                       "copied D2H as 24-bit pixels into the library's pinned staging while the next is shaded, copy workers expand "
+                       "it into the caller's buffer; synchronous per frame",
+               "frame0_digest": e2e_frame0, "frame0_equals_device_path": e2e_frame0 == frame0}
         d.close()
-    else:
-        checksum = None
+
+    # ---- secondary record: C2 (data.bin demo scene, 600-frame fly-through), frame-parallel ------------------------
+    secondary = None
+    if not args.no_secondary:
+        secondary = run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # ---- roofline ----------------------------------------------------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    raster_s = stage["raster_ms"] / 1e3 / max(stage["chunks"], 1) / vpl  # per frame
-    achieved = b_alg / raster_s / 1e9 if raster_s > 0 else 0.0
-    roofline = {
-        "bound": "hbm", "kernel": "tile_raster", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": ncu_traffic_bytes(vpl), "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": b_alg * vpl,
-        "avg_launch_us": raster_s * vpl * 1e6,
-        "share_of_step": stage["raster_ms"] / ms_total * world if ms_total else None,
-        "geometry_us_per_frame": stage["geometry_ms"] * 1e3 / max(stage["chunks"], 1) / vpl,
-        "note": "C2 is shading-bound (IEEE div/sqrt per pixel), not HBM-bound: 33 MB per frame; see DESIGN.md",
-    }
+    traffic = ncu_traffic().get("c3", {})
+    px_rank = W * H // world
+    kernels = {}
+    for name, rec in kt.items():
+        n = max(rec["launches"], 1)
+        us = rec["ms"] * 1e3 / n
+        alg = kernel_alg_bytes(name, counts, px_rank)
+        kernels[name] = {"avg_launch_us": us, "launches": rec["launches"], "share_of_step": rec["ms"] / ms_total if ms_total else None,
+                         "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / us / 1e3 if us > 0 else None,
+                         "frac": alg / us / 1e3 / peak if us > 0 else None,
+                         "ncu_dram_bytes_per_launch": traffic.get(name if world == 1 else name + f"@{world}")}
+    dominant = max(kernels, key=lambda n: kernels[n]["avg_launch_us"]) if kernels else None
+    t_frame_s = ms_total / 1e3 / frames_total
+    b_alg_rank = 12 * counts["V"] + 28 * counts["A"] + 8 * counts["I"] + 4 * px_rank
+    roofline = None
+    if dominant:
+        dk = kernels[dominant]
+        roofline = {
+            "bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+            "traffic": dk["ncu_dram_bytes_per_launch"], "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_launch"], "avg_launch_us": dk["avg_launch_us"],
+            "share_of_step": dk["share_of_step"],
+            "frame": {"algorithmic_bytes_per_gpu": b_alg_rank, "achieved": b_alg_rank / t_frame_s / 1e9,
+                      "frac": b_alg_rank / t_frame_s / 1e9 / peak,
+                      "ncu_dram_bytes_per_frame": traffic.get("frame" if world == 1 else f"frame@{world}"),
+                      "note": "B_alg = 12V + 28A + 8I + 4WH/N per GPU (SURVEY.md 8(d)); the kernels read attributes of visible "
+                              "triangles only, so the DRAM traffic of a frame is below B_alg"},
+            "kernels": kernels,
+        }
 
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------------------
     cpu_baseline = None
-    if not args.no_cpu and world == 1:   # reported baseline: rank 0 at N = 1 only
-        cores = affinity_cores()
-        sample = min(F, args.cpu_sample or max(24, 3 * cores))
-        c = cpu_reference_fps(data_bin, W, H, F, sample, cores)
-        cpu_baseline = {"value": c["fps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
-                        "sample": f"{c['frames']} evenly spaced frames of the {F}-frame fly-through, one single-threaded "
-                                  f"replica per core ({c['cores']}), render loops only",
-                        "single_core_fps": c["fps_single_core"], "wall_s": c["wall_s"]}
+    if not args.no_cpu and world == 1:
+        reps = CpuReplicas(data_bin, W, H, 4096, gb_per_replica=8.0 * solids / 1e6 + 0.3, cap=args.cpu_replicas)
+        wall, busy = reps.step()
+        reps.close()
+        cpu_baseline = {"value": reps.n / wall, "unit": UNIT, "cores": reps.n, "kind": reps.kind,
+                        "sample": f"{reps.n} frames: one single-threaded replica per core (bounded by memory), each rendering pose 1 of "
+                                  f"the drift path at {W}x{H} once; scene load and pose 0 are warm-up ({reps.load_and_first_frame_s:.0f} s)",
+                        "single_core_fps": reps.n / busy, "frame0_digest": reps.frame0,
+                        "frame0_equals_b200": reps.frame0 == frame0}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "mpixels_per_s": value * W * H / 1e6, "mtriangles_per_s": value * counts["T"] / 1e6,
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e_last_frame_checksum": checksum,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "banded_equals_whole": banded_equals_whole, "frame0_digest": frame0, "comm": comm,
+        "stage_ms_per_frame": {"geometry": stage["geometry_ms"] / max(stage["chunks"], 1), "raster": stage["raster_ms"] / max(stage["chunks"], 1)},
+        "stats_last_pose": stats_last, "secondary": secondary,
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks):
+    """The secondary record: BASELINE.json configs[1] — the demo scene at 4K over the recorded fly-through; every rank renders
+    the full fly-through (frame-parallel replicas, no data-path collective)."""
+    import torch
+    from swift3drenderer_b200 import assets, renderer as R, scene as S
+    W, H, F, vpl = args.width, args.height, args.c2_frames, args.c2_views_per_launch
+    steps = max(1, min(args.steps, 5))
+    data_bin = assets.ensure_shipped_data_bin()
+    sc = S.read_data_bin(data_bin)
+    counts = sc.counts()
+    b_alg = 12 * counts["V"] + 28 * counts["A"] + 8 * counts["I"] + 4 * W * H
+    r2 = R.Renderer(local_rank)
+    r2.load_scene_file(data_bin)
+    inp = S.input_script("flythrough", F)
+    mats = R.camera_path(inp)
+    ring_n = 4
+    ring = torch.empty((ring_n, vpl, H, W), dtype=torch.int32, device=dev)
+
+    def run_step():
+        k = 0
+        for f0 in range(0, F, vpl):
+            r2.render_device(mats[f0:f0 + vpl], W, H, ring[k % ring_n].data_ptr(), stream=stream.cuda_stream)
+            k += 1
+
+    for _ in range(3):
+        run_step()
+        while r2.finish():
+            run_step()
+    r2.set_option("timing", 1)
+    r2.timing(reset=True)
+    barrier()
+    launches0 = r2.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        run_step()
+    e1.record(stream)
+    barrier()
+    assert not r2.finish()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = r2.kernel_launches - launches0
+    kt = r2.kernel_timing()
+    r2.timing(reset=True)
+    r2.set_option("timing", 0)
+    value = world * steps * F / (ms_total / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        d = R.DropIn(data_bin)
+        double = np.zeros((2, H, W), np.uint32)
+        for f in range(12):
+            d.update_and_render(W, H, inp[f], out=double[f & 1])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d.reset_camera()
+            for f in range(F):
+                d.update_and_render(W, H, inp[f], out=double[f & 1])
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * steps * F / dt, "unit": UNIT, "h2d_bytes_per_step": 48 * F * world,
+               "d2h_bytes_per_step": 3 * W * H * F * world,
+               "last_frame_digest": frame_digest(double[(F - 1) & 1]),
+               "call": "updateAndRender on a private render.so beside the demo data.bin, pageable double buffer (not registered), "
+                       "12 row bands rasterised and copied D2H as 24-bit pixels into pinned staging, copy workers expand into the "
+                       "caller's buffer; one replica per rank on its own GPU"}
+        d.close()
+    r2.close()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_gbs()
+    rec = kt.get("tile_raster", {"ms": 0.0, "launches": 0})
+    launch_us = rec["ms"] * 1e3 / max(rec["launches"], 1)
+    tr = ncu_traffic().get("c2", {}).get("tile_raster")
+    roofline = {"bound": "hbm", "kernel": "tile_raster", "achieved": b_alg * vpl / launch_us / 1e3 if launch_us else None, "peak": peak,
+                "unit": "GB/s", "frac": b_alg * vpl / launch_us / 1e3 / peak if launch_us else None,
+                "traffic": int(tr["dram_bytes_per_launch"] / tr["poses_per_launch"] * vpl) if tr else None,
+                "issue_slot_frac": tr.get("issue_active_frac") if tr else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_alg * vpl, "avg_launch_us": launch_us,
+                "share_of_step": rec["ms"] / ms_total if ms_total else None,
+                "note": "C2 is shading-bound (IEEE div/sqrt per pixel, issue slots), not HBM-bound: 33 MB per frame"}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cores = affinity_cores()
+        c = c2_cpu_reference_fps(data_bin, W, H, F, min(F, max(24, 3 * cores)), cores)
+        cpu = {"value": c["fps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+               "sample": f"{c['frames']} evenly spaced frames of the {F}-frame fly-through, one single-threaded replica per core",
+               "single_core_fps": c["fps_single_core"]}
+    return {"metric": C2_METRIC, "value": value, "unit": UNIT, "scaling": "weak (frame-parallel replicas)", "steps": steps,
+            "ms_per_step": ms_total / steps, "frames_per_step": F, "views_per_launch": vpl, "gpu_launches": int(launches),
+            "workload": f"C2: reference data.bin scene (V={counts['V']}, T={counts['T']}) at {W}x{H}, {F}-frame recorded fly-through",
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
 
 
 if __name__ == "__main__":

@@ -145,6 +145,10 @@ S3R_API uint64_t s3r_kernel_launches(const S3RRenderer *r);   /* kernels launche
  * geometry kernels (reset .. bin fill) and the tile rasteriser, measured on the launching stream;
  * *chunks = number of (multi-view) submissions covered. */
 S3R_API int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raster_ms, uint64_t *chunks, int reset);
+/* Per-kernel CUDA-event time accumulated since the last reset (option "timing" = 1; reset through s3r_get_timing):
+ * entry `index` = one kernel of the frame pipeline in launch order.  Returns 0 and fills *name (static string), *ms (sum
+ * over the timed launches) and *launches; returns 1 when index is past the last kernel. */
+S3R_API int s3r_get_kernel_timing(S3RRenderer *r, uint32_t index, const char **name, double *ms, uint64_t *launches);
 S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
 /* options: "tma_store" (1 = cp.async.bulk tile write-out, default; 0 = plain stores),
  *          "pin_host" (1 = cudaHostRegister the caller's frame buffers; default 0 — only for callers that

@@ -1208,10 +1208,15 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                 if (win[j] != NO_TRI && x < f.W) {
                     const unsigned long long key = ((unsigned long long)__float_as_uint(depth[j]) << 32) |
                                                    (unsigned long long)(~f.head[(size_t)view * f.setup_cap + win[j]].z);
-                    // the best candidate so far also leaves its exact weights, tagged with its slot: a later, better
-                    // candidate overwrites them; shading checks the tag and falls back to the exact jump on a mismatch
+                    // the best candidate so far also leaves its exact weights: three aligned 64-bit words {weight, slot},
+                    // each single-copy atomic on its own, so a reader sees every word whole and can tell from the three
+                    // tags whether all of them belong to the triangle that holds the key.  A later, better candidate (this
+                    // tile's list may be shared by several CTAs) overwrites them in any order; shading checks the tags and
+                    // falls back to the exact jump on any mismatch.
                     if (atomicMax(krow + x, key) < key) {
-                        f.pstate[(size_t)(krow - f.keys) + x] = make_uint4(__float_as_uint(bw0[j]), __float_as_uint(bw1[j]), __float_as_uint(bw2[j]), win[j]);
+                        unsigned long long *ps = f.pstate + 3u * ((size_t)(krow - f.keys) + x);
+                        const unsigned long long tag = (unsigned long long)win[j] << 32;
+                        ps[0] = tag | __float_as_uint(bw0[j]); ps[1] = tag | __float_as_uint(bw1[j]); ps[2] = tag | __float_as_uint(bw2[j]);
                     }
                 }
             }
@@ -1674,8 +1679,9 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
                         w1 = walk_near(walk_near(w1, dy1, ny), __uint_as_float(src[4]), nx);
                         w2 = walk_near(walk_near(w2, dy2, ny), __uint_as_float(src[5]), nx);
                     }
-                } else if (const uint4 st = f.pstate[vbase + (size_t)(row0 + br0 + qr) * f.W + px]; st.w + 1u == src[13]) {
-                    w0 = __uint_as_float(st.x); w1 = __uint_as_float(st.y); w2 = __uint_as_float(st.z);   // left by the tile kernel
+                } else if (const unsigned long long *ps = f.pstate + 3u * (vbase + (size_t)(row0 + br0 + qr) * f.W + px), p0 = ps[0], p1 = ps[1], p2 = ps[2];
+                           (uint32_t)(p0 >> 32) + 1u == src[13] && (uint32_t)(p1 >> 32) + 1u == src[13] && (uint32_t)(p2 >> 32) + 1u == src[13]) {
+                    w0 = __uint_as_float((uint32_t)p0); w1 = __uint_as_float((uint32_t)p1); w2 = __uint_as_float((uint32_t)p2);   // left by the tile kernel, all three words the winner's
                 } else {   // (another CTA's candidate raced the winner's note) exact jump down the rows, then along the row
                     const uint32_t xy = src[12], ny = py - (xy >> 16), nx = px - (xy & 0xFFFFu);
                     w0 = walk_near(walk_near(__uint_as_float(src[0]), __uint_as_float(src[6]), ny), __uint_as_float(src[3]), nx);
@@ -1758,25 +1764,27 @@ cudaError_t configure_kernels() {
 
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-int launch_geometry(const Frame &f, cudaStream_t s) {
+static inline void mark(const LaunchMarks *m, const char *kernel) { if (m) { m->fn(m->ctx, kernel); } }
+
+int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     int launches = 0;
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
-    vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++;
-    triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++;
-    triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++;
+    vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
+    triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");
+    triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_setup");
     // cooperative binning of the big triangles, flat visibility pass over the recorded small ones (clipped or spawned),
     // and — by the last CTA to finish — the frame's tile statistics and overflow record
-    post_setup<<<dim3(persistent, f.n_views), 256, 0, s>>>(f); launches++;
+    post_setup<<<dim3(persistent, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "post_setup");
     return launches;
 }
 
-int launch_raster(const Frame &f, cudaStream_t s) {
+int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     if (f.direct_bin) {
-        tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+        tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster");
         return 1;
     }
     // general path (always one raster launch per frame): the queue holds every non-empty tile of the submission
-    tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f);
+    tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster_queue");
     // general path: the tile kernel only resolved the big triangles; shade the rows it covered
     uint32_t row0, nrows;
     if (f.row_stride == 1u) {
@@ -1787,15 +1795,15 @@ int launch_raster(const Frame &f, cudaStream_t s) {
         row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
     }
     if (nrows) {
-        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, sizeof(ShadeShared), s>>>(f, row0, nrows);
+        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, sizeof(ShadeShared), s>>>(f, row0, nrows); mark(m, "shade_tiles");
     }
     return 2;
 }
 
-int launch_geometry_small(const Frame &f, cudaStream_t s) {
-    geometry_small<<<f.n_views, 256, 0, s>>>(f);
+int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
+    geometry_small<<<f.n_views, 256, 0, s>>>(f); mark(m, "geometry_small");
     if (!f.coltab) { return 1; }
-    span_walk<<<dim3(ceil_div(f.H, 128u), SPAN_MAX * 3u, f.n_views), 128, 0, s>>>(f);
+    span_walk<<<dim3(ceil_div(f.H, 128u), SPAN_MAX * 3u, f.n_views), 128, 0, s>>>(f); mark(m, "span_walk");
     return 2;
 }
 

@@ -125,7 +125,7 @@ struct Frame {
     uint32_t big_cap;
     // general path: per-pixel depth keys (depth << 32 | ~order), indexed like `out`; the tile kernel's work queue
     unsigned long long *keys;
-    uint4 *pstate;         // exact weights + slot of the tile kernel's best candidate per pixel (checked by tag)
+    unsigned long long *pstate;   // [pixels][3] {slot << 32 | weight bits}: exact weights of the tile kernel's best candidate, each word tagged
     uint2 *raster_items;   // [views][items_cap] {tile, first entry of the chunk}
     uint32_t items_cap;
     // output
@@ -156,10 +156,12 @@ struct Frame {
     CUtensorMap out_map;    // 64-byte aligned member of a __grid_constant__ parameter
 };
 
-// Launchers (kernels.cu).  Each returns the number of kernels it enqueued.
-int launch_geometry(const Frame &f, cudaStream_t s);   // reset, vertex stage, clip/cull/setup, binning
-int launch_raster(const Frame &f, cudaStream_t s);     // per-tile visibility + shading + write-out
-int launch_geometry_small(const Frame &f, cudaStream_t s);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
+// Launchers (kernels.cu).  Each returns the number of kernels it enqueued.  `marks` (optional): called after every kernel
+// launch with the kernel's name — the host layer records a timing event there (option "timing").
+struct LaunchMarks { void (*fn)(void *ctx, const char *kernel); void *ctx; };
+int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);   // vertex stage, classify + direct walk, clip/setup, binning + flat walk
+int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);     // per-tile visibility + shading + write-out
+int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
 cudaError_t configure_kernels();
 void launch_exact_math(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed, unsigned long long *result,
                        cudaStream_t st);

@@ -6,6 +6,10 @@
 // data.bin discovery via dladdr (render.cpp:161-176).  There is no CPU rendering path in here.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
@@ -13,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 #include <string>
 #include <thread>
 #include <functional>
@@ -76,7 +81,7 @@ struct S3RRenderer {
     DevBuf<uint32_t> slot_of;
     DevBuf<unsigned long long> keys;   // general path: per-pixel depth keys ...
     DevBuf<uint2> raster_items;        // ... and the tile kernel's work queue
-    DevBuf<uint4> pstate;              // weights of the tile kernel's winners
+    DevBuf<unsigned long long> pstate; // weights of the tile kernel's winners: 3 tagged words per pixel
     int opt_flat_max = 128;
     uint32_t items_cap = 0;
     DevBuf<uint32_t> worklist;
@@ -97,6 +102,13 @@ struct S3RRenderer {
     size_t cams_pinned_views = 0;
     cudaEvent_t ev_cams[RING] = {}, ev_t0[RING] = {}, ev_t1[RING] = {}, ev_t2[RING] = {};
     bool slot_used[RING] = {}, slot_timed[RING] = {};
+    // per-kernel timing (option "timing"): an event after every kernel launch of a timed submission
+    static constexpr int MAX_MARKS = 12;
+    cudaEvent_t ev_mark[RING][MAX_MARKS] = {};
+    const char *mark_name[RING][MAX_MARKS] = {};
+    int n_marks[RING] = {};
+    struct KernelAcc { const char *name; double ms; uint64_t launches; };
+    std::vector<KernelAcc> kernel_acc;
     uint64_t chunk_counter = 0;
     int opt_timing = 0;
     double geometry_ms = 0, raster_ms = 0;
@@ -143,6 +155,7 @@ extern "C" int s3r_create(S3RRenderer **out, int device) {
     for (int i = 0; i < S3RRenderer::RING; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&r->ev_cams[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&r->ev_t0[i])); CUDA_TRY(cudaEventCreate(&r->ev_t1[i])); CUDA_TRY(cudaEventCreate(&r->ev_t2[i]));
+        for (int k = 0; k < S3RRenderer::MAX_MARKS; k++) { CUDA_TRY(cudaEventCreate(&r->ev_mark[i][k])); }
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < S3RRenderer::MAX_SLICES; i++) {
@@ -186,6 +199,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     if (r->copy_stream) { cudaStreamDestroy(r->copy_stream); }
     for (int i = 0; i < S3RRenderer::RING; i++) {
         if (r->ev_cams[i]) { cudaEventDestroy(r->ev_cams[i]); cudaEventDestroy(r->ev_t0[i]); cudaEventDestroy(r->ev_t1[i]); cudaEventDestroy(r->ev_t2[i]); }
+        for (int k = 0; k < S3RRenderer::MAX_MARKS; k++) { if (r->ev_mark[i][k]) { cudaEventDestroy(r->ev_mark[i][k]); } }
     }
     if (r->stream) { cudaStreamDestroy(r->stream); }
     delete r;
@@ -256,36 +270,51 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
 
 extern "C" int s3r_load_scene_file(S3RRenderer *r, const char *path) {
     if (!r || !path) { return fail(S3R_E_ARG, "null argument"); }
-    FILE *fp = fopen(path, "rb");
-    if (!fp) { return fail(S3R_E_IO, std::string("cannot open ") + path); }
-    fseek(fp, 0, SEEK_END);
-    const long size = ftell(fp);
-    fseek(fp, 0, SEEK_SET);
-    std::vector<uint64_t> raw((size_t)size / 8 + 2, 0);  // 8-byte aligned backing store
-    const size_t got = fread(raw.data(), 1, (size_t)size, fp);
-    fclose(fp);
-    if (got != (size_t)size) { return fail(S3R_E_IO, "short read"); }
-    const uint8_t *b = reinterpret_cast<const uint8_t *>(raw.data());
+    // The file is mapped, not read: a 20 M-triangle data.bin is 4 GB, and the sections are converted straight from the
+    // page cache.  Every section length is checked against what is left of the file BEFORE it is multiplied by the
+    // record size, so a hostile header cannot wrap the arithmetic.
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { return fail(S3R_E_IO, std::string("cannot open ") + path); }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 0) { close(fd); return fail(S3R_E_IO, std::string("cannot stat ") + path); }
+    const size_t size = (size_t)st.st_size;
+    if (size < 5 * 16) { close(fd); return fail(S3R_E_IO, "truncated file (five section headers expected)"); }
+    void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) { return fail(S3R_E_IO, std::string("cannot map ") + path); }
+    madvise(map, size, MADV_SEQUENTIAL);
+    const uint8_t *b = static_cast<const uint8_t *>(map);
     size_t off = 0;
-    auto header = [&](uint64_t &n) -> bool {
-        if (off + 16 > (size_t)size) { return false; }
-        memcpy(&n, b + off, 8);  // second word ignored, render.cpp:178-179
+    // one section: header {count, ignored} (render.cpp:178-179), then `padded(count)` records of `elem` bytes
+    auto section = [&](uint64_t &n, size_t elem, bool pad_odd, const uint8_t *&data) -> bool {
+        if (size - off < 16) { return false; }
+        memcpy(&n, b + off, 8);
         off += 16;
+        const uint64_t records = n + (pad_odd ? (n & 1) : 0);   // n < 2^64 - 1 is implied by the division below
+        if (n == UINT64_MAX || records > (size - off) / elem) { return false; }
+        data = b + off;
+        off += (size_t)records * elem;
         return true;
     };
-    uint64_t V, I, A, I2, NT;
-    if (!header(V) || off + V * 16 > (size_t)size) { return fail(S3R_E_IO, "truncated vertex section"); }
-    const float *vertices = reinterpret_cast<const float *>(b + off); off += V * 16;
-    if (!header(I) || off + (I + (I & 1)) * 8 > (size_t)size) { return fail(S3R_E_IO, "truncated index section"); }
-    const uint64_t *vidx = reinterpret_cast<const uint64_t *>(b + off); off += (I + (I & 1)) * 8;
-    if (!header(A) || off + A * 48 > (size_t)size) { return fail(S3R_E_IO, "truncated attribute section"); }
-    const void *attrs = b + off; off += A * 48;
-    if (!header(I2) || off + (I2 + (I2 & 1)) * 8 > (size_t)size) { return fail(S3R_E_IO, "truncated attribute-index section"); }
-    const uint64_t *aidx = reinterpret_cast<const uint64_t *>(b + off); off += (I2 + (I2 & 1)) * 8;
-    if (I2 != I) { return fail(S3R_E_SCENE, "index streams differ in length"); }
-    if (!header(NT) || off + NT * 4 > (size_t)size) { return fail(S3R_E_IO, "truncated texture section"); }
-    const uint32_t *texels = reinterpret_cast<const uint32_t *>(b + off);
-    return s3r_load_scene_arrays(r, vertices, V, vidx, aidx, I, attrs, A, texels, NT);
+    uint64_t V = 0, I = 0, A = 0, I2 = 0, NT = 0;
+    const uint8_t *vertices = nullptr, *vidx = nullptr, *attrs = nullptr, *aidx = nullptr, *texels = nullptr;
+    int rc = S3R_OK;
+    if (!section(V, 16, false, vertices)) { rc = fail(S3R_E_IO, "truncated vertex section"); }
+    else if (!section(I, 8, true, vidx)) { rc = fail(S3R_E_IO, "truncated index section"); }
+    else if (!section(A, 48, false, attrs)) { rc = fail(S3R_E_IO, "truncated attribute section"); }
+    else if (!section(I2, 8, true, aidx)) { rc = fail(S3R_E_IO, "truncated attribute-index section"); }
+    else if (I2 != I) { rc = fail(S3R_E_SCENE, "index streams differ in length"); }
+    else if (!section(NT, 4, false, texels)) { rc = fail(S3R_E_IO, "truncated texture section"); }
+    else {
+        try {
+            rc = s3r_load_scene_arrays(r, reinterpret_cast<const float *>(vertices), V, reinterpret_cast<const uint64_t *>(vidx),
+                                       reinterpret_cast<const uint64_t *>(aidx), I, attrs, A, reinterpret_cast<const uint32_t *>(texels), NT);
+        } catch (const std::exception &e) {   // allocation failure while converting: report, do not unwind through extern "C"
+            rc = fail(S3R_E_IO, std::string("scene conversion failed: ") + e.what());
+        }
+    }
+    munmap(map, size);
+    return rc;
 }
 
 extern "C" int s3r_scene_counts(const S3RRenderer *r, uint64_t *v, uint64_t *i, uint64_t *a, uint64_t *t) {
@@ -482,6 +511,36 @@ extern "C" int s3r_debug_band_edges(uint32_t tiles_y, int bands, int taper, uint
     return band_edges(tiles_y, nb, taper != 0, edges_out);
 }
 
+// Collects the stage and per-kernel times of the timed submission that used ring slot `slot`.
+static int retire_timed_slot(S3RRenderer *r, int slot) {
+    if (!r->slot_timed[slot]) { return S3R_OK; }
+    CUDA_TRY(cudaEventSynchronize(r->ev_t2[slot]));
+    float g = 0, q = 0;
+    cudaEventElapsedTime(&g, r->ev_t0[slot], r->ev_t1[slot]);
+    cudaEventElapsedTime(&q, r->ev_t1[slot], r->ev_t2[slot]);
+    r->geometry_ms += g; r->raster_ms += q; r->timed_chunks++;
+    cudaEvent_t prev = r->ev_t0[slot];
+    for (int k = 0; k < r->n_marks[slot]; k++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, prev, r->ev_mark[slot][k]);
+        prev = r->ev_mark[slot][k];
+        const char *name = r->mark_name[slot][k];
+        auto it = std::find_if(r->kernel_acc.begin(), r->kernel_acc.end(), [&](const S3RRenderer::KernelAcc &a) { return !strcmp(a.name, name); });
+        if (it == r->kernel_acc.end()) { r->kernel_acc.push_back({name, 0.0, 0}); it = r->kernel_acc.end() - 1; }
+        it->ms += ms; it->launches++;
+    }
+    r->n_marks[slot] = 0;
+    r->slot_timed[slot] = false;
+    return S3R_OK;
+}
+
+struct MarkCtx { S3RRenderer *r; int slot; cudaStream_t s; };
+static void mark_kernel(void *ctx, const char *kernel) {
+    MarkCtx *m = static_cast<MarkCtx *>(ctx);
+    int &n = m->r->n_marks[m->slot];
+    if (n < S3RRenderer::MAX_MARKS && cudaEventRecord(m->r->ev_mark[m->slot][n], m->s) == cudaSuccess) { m->r->mark_name[m->slot][n++] = kernel; }
+}
+
 // raster_bands > 1: the tile rows are rasterised in that many launches, with r->ev_raster[b] recorded
 // after band b (used by the staged host path to start the D2H of a band while the next one renders);
 // band_rows[b] receives the first pixel row (relative to y0) after band b.
@@ -507,14 +566,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     const int slot = (int)(r->chunk_counter++ % S3RRenderer::RING);
     if (r->slot_used[slot]) {  // the chunk that used this slot RING submissions ago
         CUDA_TRY(cudaEventSynchronize(r->ev_cams[slot]));
-        if (r->slot_timed[slot]) {
-            CUDA_TRY(cudaEventSynchronize(r->ev_t2[slot]));
-            float g = 0, q = 0;
-            cudaEventElapsedTime(&g, r->ev_t0[slot], r->ev_t1[slot]);
-            cudaEventElapsedTime(&q, r->ev_t1[slot], r->ev_t2[slot]);
-            r->geometry_ms += g; r->raster_ms += q; r->timed_chunks++;
-            r->slot_timed[slot] = false;
-        }
+        int rc2 = retire_timed_slot(r, slot);
+        if (rc2) { return rc2; }
     }
     float *staging = r->cams_pinned + (size_t)slot * r->cams_pinned_views * 12;
     memcpy(staging, cams, (size_t)n_views * 12 * sizeof(float));
@@ -522,6 +575,10 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));
     r->slot_used[slot] = true;
     const bool timed = r->opt_timing != 0;
+    MarkCtx mark_ctx{r, slot, s};
+    const LaunchMarks marks{mark_kernel, &mark_ctx};
+    const LaunchMarks *mk = timed ? &marks : nullptr;
+    r->n_marks[slot] = 0;
 
     f.pos_x = r->pos_x.p; f.pos_y = r->pos_y.p; f.pos_z = r->pos_z.p;
     f.vi0 = r->vi[0].p; f.vi1 = r->vi[1].p; f.vi2 = r->vi[2].p;
@@ -555,7 +612,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
             CUDA_TRY(cudaMemsetAsync(r->keys.p, 0, r->keys.n * sizeof(unsigned long long), s));
         }
         f.keys = r->keys.p;
-        CUDA_TRY(r->pstate.ensure((size_t)n_views * f.out_view_stride + 2));
+        CUDA_TRY(r->pstate.ensure(3u * ((size_t)n_views * f.out_view_stride + 2)));
         f.pstate = r->pstate.p;
     }
     f.out_packed24 = packed24 ? 1 : 0;
@@ -591,7 +648,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         CUDA_TRY(r->rowbase.ensure((size_t)r->setup_cap * r->views_cap));
         f.rowtab = r->rowtab.p; f.rowbase = r->rowbase.p;
     }
-    r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s) : launch_geometry(f, s));
+    r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s, mk) : launch_geometry(f, s, mk));
     if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
         CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
     }
@@ -602,7 +659,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     for (int b = 0; b + 1 < n_edges; b++) {
         f.raster_row0 = edge[b];
         f.raster_rows = edge[b + 1] - edge[b];
-        r->launches += (uint64_t)launch_raster(f, s);
+        r->launches += (uint64_t)launch_raster(f, s, mk);
         if (raster_bands > 1 || band_rows) {
             CUDA_TRY(cudaEventRecord(r->ev_raster[b], s));
             if (band_rows) {
@@ -758,7 +815,8 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
                                uint32_t y0, uint32_t y1, uint32_t *host_out) {
     if (!r || !cams || !host_out) { return fail(S3R_E_ARG, "null argument"); }
     if (!r->has_scene) { return fail(S3R_E_NOSCENE, "no scene loaded"); }
-    if (W == 0 || H == 0 || y0 >= y1 || y1 > H) { return fail(S3R_E_ARG, "bad frame geometry"); }
+    // SetupVis and the survivor heads pack box bounds in 16 bits: the same limits as s3r_render_device
+    if (W == 0 || H == 0 || W > 65535 || H > 65535 || y0 >= y1 || y1 > H || n_views == 0) { return fail(S3R_E_ARG, "bad frame geometry"); }
     CUDA_TRY(cudaSetDevice(r->device));
     const size_t view_px = (size_t)W * (y1 - y0);
     const bool pinned = pin_host(r, host_out, view_px * n_views * 4);
@@ -772,7 +830,8 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
         const size_t chunk_bytes = view_px * nv * bpp;
         CUDA_TRY(r->frame.ensure(view_px * nv));
         if (!pinned) { int rc = ensure_staging(r, chunk_bytes + 64); if (rc) { return rc; } }
-        for (int attempt = 0; attempt < 8; attempt++) {
+        bool rendered = false;
+        for (int attempt = 0; attempt < 8 && !rendered; attempt++) {
             // ---- enqueue: geometry, banded raster, one D2H per band/slice on the copy stream -----
             uint32_t band_rows[S3RRenderer::MAX_SLICES] = {};
             // band-pipelined raster/copy for the tile-kernel path only (see render_chunk)
@@ -835,9 +894,10 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
                     unpin_all(r);
                     CUDA_TRY(cudaMemcpy(dst, r->frame.p, view_px * nv * 4, cudaMemcpyDeviceToHost));
                 }
-                break;
+                rendered = true;
             }
         }
+        if (!rendered) { return fail(S3R_E_CUDA, "frame scratch still overflowing after 8 regrowths"); }
     }
     return S3R_OK;
 }
@@ -891,6 +951,8 @@ extern "C" int s3r_set_peer_frames(S3RRenderer *r, void *const *dev_ptrs, uint32
     if (!r || (n && !dev_ptrs) || n > (uint32_t)MAX_PEERS) { return fail(S3R_E_ARG, "bad peer frame list"); }
     for (uint32_t k = 0; k < n; k++) {
         if (!dev_ptrs[k]) { return fail(S3R_E_ARG, "null peer frame"); }
+        // shade_tiles stores 16-byte pieces at 16-byte offsets from the base
+        if (reinterpret_cast<uintptr_t>(dev_ptrs[k]) & 15u) { return fail(S3R_E_ARG, "peer frame is not 16-byte aligned"); }
         r->peer_out[k] = static_cast<uint32_t *>(dev_ptrs[k]);
     }
     r->n_peers = n;
@@ -1003,19 +1065,27 @@ extern "C" int s3r_get_timing(S3RRenderer *r, double *geometry_ms, double *raste
     if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
     CUDA_TRY(cudaSetDevice(r->device));
     for (int slot = 0; slot < S3RRenderer::RING; slot++) {  // drain the chunks still in the ring
-        if (r->slot_timed[slot]) {
-            CUDA_TRY(cudaEventSynchronize(r->ev_t2[slot]));
-            float g = 0, q = 0;
-            cudaEventElapsedTime(&g, r->ev_t0[slot], r->ev_t1[slot]);
-            cudaEventElapsedTime(&q, r->ev_t1[slot], r->ev_t2[slot]);
-            r->geometry_ms += g; r->raster_ms += q; r->timed_chunks++;
-            r->slot_timed[slot] = false;
-        }
+        int rc = retire_timed_slot(r, slot);
+        if (rc) { return rc; }
     }
     if (geometry_ms) { *geometry_ms = r->geometry_ms; }
     if (raster_ms) { *raster_ms = r->raster_ms; }
     if (chunks) { *chunks = r->timed_chunks; }
-    if (reset) { r->geometry_ms = r->raster_ms = 0; r->timed_chunks = 0; }
+    if (reset) { r->geometry_ms = r->raster_ms = 0; r->timed_chunks = 0; r->kernel_acc.clear(); }
+    return S3R_OK;
+}
+
+extern "C" int s3r_get_kernel_timing(S3RRenderer *r, uint32_t index, const char **name, double *ms, uint64_t *launches) {
+    if (!r) { return fail(S3R_E_ARG, "renderer is null"); }
+    CUDA_TRY(cudaSetDevice(r->device));
+    for (int slot = 0; slot < S3RRenderer::RING; slot++) {
+        int rc = retire_timed_slot(r, slot);
+        if (rc) { return rc; }
+    }
+    if (index >= r->kernel_acc.size()) { return 1; }   // past the last kernel
+    if (name) { *name = r->kernel_acc[index].name; }
+    if (ms) { *ms = r->kernel_acc[index].ms; }
+    if (launches) { *launches = r->kernel_acc[index].launches; }
     return S3R_OK;
 }
 
@@ -1251,16 +1321,25 @@ extern "C" int s3r_sink_submit(S3RSink *k, const uint32_t *dev_frame, void *stre
         if (k->io_error) { return fail(S3R_E_IO, "sink: write failed"); }
         k->busy[slot] = true;
     }
+    cudaError_t ce = cudaSuccess;
     if (k->format == 1) {
         const size_t cw = (k->W + 1u) / 2u, ch = (k->H + 1u) / 2u;
         uint8_t *yp = k->dev_yuv, *up = yp + (size_t)k->W * k->H, *vp = up + cw * ch;
         bgr0_to_i420<<<dim3((unsigned)((cw + 15u) / 16u), (unsigned)((ch + 15u) / 16u)), 256, 0, s>>>(dev_frame, k->W, k->H, yp, up, vp);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(k->host[slot], k->dev_yuv, k->frame_bytes, cudaMemcpyDeviceToHost, s));
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) { ce = cudaMemcpyAsync(k->host[slot], k->dev_yuv, k->frame_bytes, cudaMemcpyDeviceToHost, s); }
     } else {
-        CUDA_TRY(cudaMemcpyAsync(k->host[slot], dev_frame, k->frame_bytes, cudaMemcpyDeviceToHost, s));
+        ce = cudaMemcpyAsync(k->host[slot], dev_frame, k->frame_bytes, cudaMemcpyDeviceToHost, s);
     }
-    CUDA_TRY(cudaEventRecord(k->copied[slot], s));
+    if (ce == cudaSuccess) { ce = cudaEventRecord(k->copied[slot], s); }
+    if (ce != cudaSuccess) {   // nothing was queued for the writer: give the ring slot back, or the next submit on it waits forever
+        {
+            std::lock_guard<std::mutex> lock(k->mu);
+            k->busy[slot] = false;
+        }
+        k->cv.notify_all();
+        return fail(S3R_E_CUDA, std::string("sink submit: ") + cudaGetErrorString(ce));
+    }
     k->submitted++;
     {
         std::lock_guard<std::mutex> lock(k->mu);

@@ -105,13 +105,24 @@ class PeerFrames:
 
     ``render(...)`` makes this rank's renderer store its tile rows into ring slot ``k`` of EVERY rank
     (``Renderer.set_peer_frames`` + ``render_device_rows``); ``fence()`` is the per-frame ordering point (a
-    one-element all-reduce, stream-ordered).  After the fence of frame k every rank holds the complete frame in
-    its own slot ``k % ring``.  Ranks must be processes of one node (CUDA IPC over NVLink / NVSwitch)."""
+    one-element all-reduce).  After the fence of frame k every rank holds the complete frame in its own slot
+    ``k % ring``.  Ranks must be processes of one node (CUDA IPC over NVLink / NVSwitch).
+
+    Stream protocol: ``render`` enqueues on ``stream`` (default: torch's current stream, never the renderer's private
+    one) and records an event there; ``fence`` makes torch's current stream wait for that event before the
+    all-reduce, so the collective is ordered after this rank's peer stores whatever stream rendered them.
+    Ring protocol: slot ``k % ring`` is overwritten by frame ``k + ring``; a consumer of frame k must have enqueued
+    its reads (on a stream the next ``render`` call's stream waits for, e.g. the same stream) before ``render`` is
+    called ``ring`` more times.  Because every rank passes fence k + ring - 1 only after all ranks have enqueued
+    the reads that precede it in stream order, ring >= 2 keeps writers of frame k + ring behind readers of frame k.
+    """
 
     def __init__(self, renderer, height: int, width: int, rank: int, world: int, device, ring: int = 2, group=None):
         self.r, self.rank, self.world, self.ring, self.group = renderer, rank, world, ring, group
         self.height, self.width = height, width
-        self.frame_bytes = height * width * 4
+        self.device = device
+        # the shading kernel stores 16-byte pieces: every ring slot starts on a 16-byte boundary
+        self.frame_bytes = (height * width * 4 + 15) & ~15
         self.own_ptr, handle = renderer.peer_frame_alloc(self.frame_bytes * ring)
         handles = [None] * world
         if world > 1:
@@ -121,6 +132,11 @@ class PeerFrames:
         self.base = [self.own_ptr if k == rank else renderer.peer_frame_open(handles[k]) for k in range(world)]
         self.token = torch.zeros(1, dtype=torch.int32, device=device)
         self.count = 0
+        self._rendered = torch.cuda.Event()
+        self._pending = False
+        self._fence_stream = torch.cuda.Stream(device) if torch.cuda.is_available() else None
+        self._fences = {}        # frame number -> event recorded behind that frame's fence (fence_async)
+        self._consumed = []      # events the next fence must wait for (consumers that have finished reading)
 
     def destinations(self, slot: int):
         return [b + slot * self.frame_bytes for b in self.base]
@@ -129,18 +145,73 @@ class PeerFrames:
         """Enqueues this rank's share of the next frame; returns the ring slot it lands in."""
         slot = self.count % self.ring
         self.count += 1
+        ext = torch.cuda.ExternalStream(stream, device=self.device) if stream else torch.cuda.current_stream(self.device)
+        # pipelined fences (fence_async): frame k overwrites the slot of frame k - ring; every rank has finished with that
+        # frame once the fence of frame k - ring + 1 has completed here (a rank contributes to a fence only behind its
+        # registered consumers of the frames before it)
+        guard = self._fences.pop(self.count - self.ring, None)
+        if guard is not None:
+            ext.wait_event(guard)
         self.r.set_peer_frames(self.destinations(slot))
-        self.r.render_device_rows(camera, self.width, self.height, self.world, self.rank, 0, stream=stream)
+        self.r.render_device_rows(camera, self.width, self.height, self.world, self.rank, 0, stream=ext.cuda_stream)
         self.r.set_peer_frames([])
+        self._rendered.record(ext)
+        self._pending = True
         return slot
 
     def fence(self) -> None:
+        """Orders the frames across ranks: after it (in stream order on torch's current stream) every rank's rows of
+        the frames rendered so far are in place on this rank."""
+        if self._pending:
+            torch.cuda.current_stream(self.device).wait_event(self._rendered)
+            self._pending = False
         if self.world > 1:
             dist.all_reduce(self.token, group=self.group)
 
+    def fence_async(self) -> None:
+        """The fence of the frame just rendered, on a side stream: the rendering stream goes straight on to the next
+        frame's geometry while the all-reduce is in flight.  ``wait_frame`` / ``join`` order a consumer behind it."""
+        fs = self._fence_stream
+        fs.wait_event(self._rendered)
+        self._pending = False
+        for ev in self._consumed:
+            fs.wait_event(ev)
+        self._consumed = []
+        if self.world > 1:
+            with torch.cuda.stream(fs):
+                dist.all_reduce(self.token, group=self.group)
+        ev = torch.cuda.Event()
+        ev.record(fs)
+        self._fences[self.count - 1] = ev
+        for k in [k for k in self._fences if k < self.count - self.ring]:
+            del self._fences[k]
+
+    def wait_frame(self, stream=None) -> None:
+        """Makes `stream` (default: torch's current stream) wait for the fence of the last fenced frame."""
+        if self._fences:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self._fences[max(self._fences)])
+
+    def consumed(self, stream=None) -> None:
+        """Call after enqueuing a consumer's reads of assembled frames on `stream`: the next fence waits for them, so no
+        rank overwrites a ring slot that is still being read."""
+        ev = torch.cuda.Event()
+        ev.record(stream or torch.cuda.current_stream(self.device))
+        self._consumed.append(ev)
+
+    def join(self, stream=None) -> None:
+        self.wait_frame(stream)
+
+    def drain(self) -> None:
+        if self._fence_stream is not None:
+            self._fence_stream.synchronize()
+
+    def slot_ptr(self, slot: int) -> int:
+        """Device pointer of this rank's copy of ring slot `slot`."""
+        return self.own_ptr + slot * self.frame_bytes
+
     def read(self, slot: int):
         """This rank's copy of ring slot `slot` as a host array (call after the fence and a device synchronize)."""
-        return self.r.read_device(self.own_ptr + slot * self.frame_bytes, (self.height, self.width))
+        return self.r.read_device(self.slot_ptr(slot), (self.height, self.width))
 
     def close(self) -> None:
         for k, b in enumerate(self.base):

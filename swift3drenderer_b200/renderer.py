@@ -72,7 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
-    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing",
 ]
 
 
@@ -148,6 +148,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_sink_submit.argtypes = [vp, vp, vp]
     lib.s3r_sink_close.argtypes = [vp, ctypes.POINTER(u64)]
     lib.s3r_debug_band_edges.argtypes = [u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u32), ctypes.c_int]
+    lib.s3r_get_kernel_timing.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     if path is None:
         _lib = lib
     return lib
@@ -333,6 +334,16 @@ class Renderer:
         g, q, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
         self._check(self._lib.s3r_get_timing(self._h, ctypes.byref(g), ctypes.byref(q), ctypes.byref(n), int(reset)))
         return {"geometry_ms": g.value, "raster_ms": q.value, "chunks": n.value}
+
+    def kernel_timing(self) -> dict:
+        """{kernel name: {"ms": summed CUDA-event time, "launches": n}} since the last ``timing(reset=True)``."""
+        out, i = {}, 0
+        while True:
+            name, ms, n = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_uint64()
+            if self._check(self._lib.s3r_get_kernel_timing(self._h, i, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(n))) != 0:
+                return out
+            out[name.value.decode()] = {"ms": ms.value, "launches": int(n.value)}
+            i += 1
 
     @property
     def kernel_launches(self) -> int:

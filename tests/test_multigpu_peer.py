@@ -37,19 +37,21 @@ def _worker(rank, world, port, out_dir):
     W, H = 800, 450
     pf = multigpu.PeerFrames(r, H, W, rank, world, dev, ring=2)
     ok = True
-    for f in range(6):
+    for f in range(6):       # capacity regrowth happens here (a regrowth on any rank repeats the frame on all of them)
         for attempt in range(4):
             slot = pf.render(mats[f])
-            again = r.finish()
-            flag = torch.tensor([1 if again else 0], device=dev)
-            dist.all_reduce(flag)           # a capacity regrowth on any rank repeats the frame on all of them
+            flag = torch.tensor([1 if r.finish() else 0], device=dev)
+            dist.all_reduce(flag)
+            pf.fence()
             if flag.item() == 0:
                 break
             pf.count -= 1
+    for f in range(6):       # checked pass: nothing but the fence orders this rank's reads after its peers' stores
+        slot = pf.render(mats[f])
         pf.fence()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
+        torch.cuda.current_stream(dev).synchronize()   # my fence has completed, hence every rank's render before its fence
         got = pf.read(slot)
+        assert not r.finish()
         want = r.render(mats[f], W, H)[0]
         ok = ok and bool(np.array_equal(got, want))
         dist.barrier()

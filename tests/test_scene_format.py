@@ -118,3 +118,42 @@ def test_hazard_scene_is_a_valid_data_bin(tmp_path):
     back = S.read_data_bin(path)
     assert np.array_equal(back.vertices, sc.vertices) and np.array_equal(back.vertex_indices, sc.vertex_indices)
     assert back.attributes.tobytes() == sc.attributes.tobytes() and np.array_equal(back.textures, sc.textures)
+
+
+def test_atlas_builder_against_the_reference_ppm_atlases():
+    """SURVEY 8(f) row 3, pinned to the reference's own fixtures (data-generator/ppms/*.ppm, addressing
+    render-cpp/render.cpp:126-130).  The two shipped atlases were baked by a sibling tool from higher-resolution
+    originals that are not in the reference, so their coarser levels cannot be reproduced bit for bit from the stored
+    256x256 base; what IS pinned: the layout (level (Lx, Ly) at column 511 & ~(2Lx-1), row 511 & ~(2Ly-1); row and
+    column 511 white; the base block verbatim) and that every level is the box-filtered base to within a few grey
+    levels on average — i.e. the builder produces atlases the reference's addressing reads the same way."""
+    import zlib
+    from swift3drenderer_b200 import assets
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "shipped_ppm_4k.npz"))
+    tx = S.read_data_bin(assets.ensure_shipped_data_bin()).textures.reshape(-1, 512, 512)
+    if zlib.crc32(np.ascontiguousarray(tx, "<u4").tobytes()) != int(fx["textures_crc32"]):
+        pytest.skip("this checkout's data.bin holds procedural atlases (generated without /root/reference)")
+
+    def rgb(a):
+        return np.stack([(a >> 16) & 255, (a >> 8) & 255, a & 255], -1).astype(np.float64)
+
+    def off(n):
+        return 511 & ~(2 * n - 1)
+
+    for k in range(tx.shape[0]):
+        a = tx[k]
+        assert (a[:, 511] == 0xFFFFFF).all() and (a[511, :] == 0xFFFFFF).all()
+        b = S.build_ripmap_atlas(rgb(a[:256, :256]).astype(np.uint8))
+        assert np.array_equal(b[:256, :256], a[:256, :256])                    # base level verbatim, same place
+        assert (b[:, 511] == 0xFFFFFF).all() and (b[511, :] == 0xFFFFFF).all()
+        worst = 0.0
+        for ly in (256, 128, 64, 32, 16, 8, 4, 2, 1):
+            for lx in (256, 128, 64, 32, 16, 8, 4, 2, 1):
+                ra = rgb(a[off(ly):off(ly) + ly, off(lx):off(lx) + lx]); rb = rgb(b[off(ly):off(ly) + ly, off(lx):off(lx) + lx])
+                err = np.abs(ra - rb).mean()
+                worst = max(worst, err)
+                assert err <= 5.0, (k, lx, ly, err)
+                if lx >= 16 and ly >= 16 and lx < 256:   # ... and the level really sits where the addressing reads it:
+                    shifted = rgb(a[off(ly):off(ly) + ly, off(lx) + 1:off(lx) + lx + 1])   # one texel to the right is worse
+                    assert err < np.abs(shifted - rb).mean(), (k, lx, ly)
+        assert worst > 0.0   # (the fixtures really are not a plain box filter — see the docstring)
