@@ -160,7 +160,10 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *          frame by span_walk instead of by exact jumps in every tile, default),
  *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/
  *          copy pipeline depth of host renders, default 8), "copy_threads" (staging -> caller copy workers),
- *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth) */
+ *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth),
+ *          "clusters" (1 = general path: vertex stage + front tests + direct walk in one kernel over the load-time clusters,
+ *          raster-space vertices in shared memory only, default; 0 = vertex_stage + triangle_classify over the raw stream),
+ *          "cluster_cull" (1 = whole clusters are rejected by their bounds, default; 0 = every triangle is tested) */
 
 /* Test hook: out[i] = the device build of walk_jump(start[i], delta[i], steps[i]) — the exact result of
  * steps[i] sequential binary32 additions (render-cpp/render.cpp:374-379).  Host arrays. */
@@ -185,6 +188,16 @@ S3R_API int s3r_sink_close(S3RSink *sink, uint64_t *frames_written);
  * result[1..4] = operands and values of the first one (bit patterns). */
 S3R_API int s3r_debug_exact_math(S3RRenderer *r, uint32_t mode, uint64_t first, uint64_t count, uint32_t seed,
                                  uint64_t result[5]);
+
+/* Test hook, callable without a GPU: the load-time spatial pre-partition of a triangle stream (csrc/cluster.hpp) — runs of
+ * consecutive, spatially close triangles with a bounding sphere and their longest edge, in Morton order, which the general
+ * path's front kernel rejects wholesale when they lie behind the near plane, off screen, outside the rows a GPU owns or
+ * are too small to pass `area >= 10` (render-cpp/render.cpp:306-317).  counts_out = {clusters, cluster vertices, triangles};
+ * hdr_out: (clusters + 1) x 32 bytes {cx, cy, cz, radius, max_edge, t0, v_off, tri_off}; pos_out: three planes of v_cap
+ * floats; tri_out: one word per triangle (v0 | v1 << 8 | v2 << 16 | batch slot << 24), needs room for index_count / 3. */
+S3R_API int s3r_debug_clusters(const float *vertices_xyzw, uint64_t vertex_count, const uint64_t *vertex_indices,
+                               uint64_t index_count, void *hdr_out, uint64_t hdr_cap, float *pos_out, uint8_t *vslot_out,
+                               uint64_t v_cap, uint32_t *tri_out, uint64_t counts_out[3]);
 
 /* Test hook, callable without a GPU: the tile-row band edges of a host render (s3r_render_host pipelines raster launches
  * with device-to-host copies band by band; the last band is tapered).  Returns the number of edges written (bands + 1),

@@ -27,6 +27,7 @@
 // hand-scheduled operators are in exact_math.cuh (device-checked against the compiler's, bit for bit).
 #include <type_traits>
 #include "pipeline.cuh"
+#include "cluster.hpp"
 #include "walk.cuh"
 #include "exact_math.cuh"
 
@@ -92,6 +93,7 @@ constexpr uint32_t SMALL_MAX = 16;      // triangles whose whole bbox is narrowe
 // K0 — reset
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reset_body(const Frame &f, uint32_t view, uint32_t i, uint32_t stride) {
+    if (!f.counters) { return; }   // (vertex stage re-run for a raster-vertex dump: the frame's counters stay)
     if (i < C_COUNT) { f.counters[view * C_COUNT + i] = 0; }
     for (uint32_t t = i; t < f.n_tiles; t += stride) { f.tile_count[view * f.tile_stride + t] = 0; }
 }
@@ -418,8 +420,12 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
 __device__ __forceinline__ Corner gather_corner(const Frame &f, const Cam &cam, uint32_t view, uint32_t vi, uint32_t ai) {
     Corner c;
     c.cv = xform(cam, __ldg(f.pos_x + vi), __ldg(f.pos_y + vi), __ldg(f.pos_z + vi), 1.0f);
-    const float4 r = f.rv[(size_t)view * f.Vpad + vi];
-    c.rv = make_float3(r.x, r.y, r.z);
+    if (f.rv) {
+        const float4 r = f.rv[(size_t)view * f.Vpad + vi];
+        c.rv = make_float3(r.x, r.y, r.z);
+    } else {   // cluster front: raster-space vertices never reach HBM; the vertex stage's own expression gives the same bits
+        c.rv = project(c.cv, f.factor, f.half_w, f.half_h);
+    }
     const uint4 a = __ldg(f.attr + 2 * (size_t)ai);
     c.n = xform(cam, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), 0.0f);
     c.kind = a.w;
@@ -555,7 +561,6 @@ __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, ui
 constexpr uint32_t CLS_PER_CTA = 1024;   // triangles per classify CTA (four per thread)
 
 struct WalkShared {
-    uint32_t cand[CLS_PER_CTA];        // triangles that passed the front tests (| ITEM_STRADDLE)
     float par[12][256];                // per parked box: ws[3], dx[3], dy[3], rz[3]  (SoA: conflict-free)
     float ck[9][256];                  // row-start weights at box rows 4, 8, 12 (checkpoints: a row item replays at most 3 row steps)
     uint32_t xy[256];                  // xmin | ymin << 16
@@ -568,47 +573,36 @@ struct WalkShared {
     uint32_t work_base;
 };
 
-__global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
-    __shared__ WalkShared wsh;
-    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
-    if (tid == 0) { wsh.n_cand = 0; }
-    if (tid < 4) { wsh.stats[tid] = 0; }
-    __syncthreads();
-    const float4 *rv = f.rv + (size_t)view * f.Vpad;
-    uint32_t n_near = 0, n_clip = 0, n_cull = 0, n_direct = 0;   // per-thread statistics, reduced once at the end
+struct FrontCounts { uint32_t n_near, n_clip, n_cull, n_direct; };
 
-    // ---- front: near reject, straddle, area cull, screen/band reject (render.cpp:306-317), 4 triangles per thread ----
-#pragma unroll 2
-    for (uint32_t pass = 0; pass < CLS_PER_CTA / 256u; pass++) {
-        const uint32_t t = blockIdx.x * CLS_PER_CTA + pass * 256u + tid;
-        uint32_t cand = 0;   // 1 candidate, 2 candidate that straddles the near plane
-        if (t < f.T) {
-            const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
-            if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
-                n_near++;
-            } else if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
-                cand = 2; n_clip++;
-            } else {
-                // the order of the three culls does not matter for the result (all are 'continue's before any side
-                // effect, render.cpp:311-317); the area test removes ~80 % of a dense field, so it goes first
-                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
-                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
-                // screen partition: a triangle whose rows cannot meet this submission's rows contributes nothing
-                // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
-                const bool off = (max_x < 0 || max_y < f.band_lo) || (min_x >= f.fw || min_y >= f.band_hi);
-                if (edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10 || off) { n_cull++; } else { cand = 1; }
-            }
-        }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
-        uint32_t base = 0;
-        if (lane == 0 && m) { base = atomicAdd(&wsh.n_cand, __popc(m)); }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (cand) { wsh.cand[base + __popc(m & ((1u << lane) - 1u))] = t | (cand == 2 ? ITEM_STRADDLE : 0u); }
+// The front tests of one triangle from its raster-space vertices (render.cpp:306-317): 0 rejected, 1 candidate,
+// 2 candidate that straddles the near plane.
+__device__ __forceinline__ uint32_t front_test(const Frame &f, const float4 &r0, const float4 &r1, const float4 &r2, FrontCounts &n) {
+    if (fmaxf(fmaxf(r0.z, r1.z), r2.z) <= kNear) {  // render.cpp:306
+        n.n_near++;
+        return 0u;
     }
-    __syncthreads();
-    const uint32_t n_cand = wsh.n_cand;
+    if (fminf(fminf(r0.z, r1.z), r2.z) < kNear) {  // render.cpp:308
+        n.n_clip++;
+        return 2u;
+    }
+    // the order of the three culls does not matter for the result (all are 'continue's before any side
+    // effect, render.cpp:311-317); the area test removes ~80 % of a dense field
+    const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+    const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+    // screen partition: a triangle whose rows cannot meet this submission's rows contributes nothing
+    // (ymax = (uint)min(H - 1, max_y) < y0 follows from max_y < y0; ymin >= y1 from min_y >= y1)
+    const bool off = (max_x < 0 || max_y < f.band_lo) || (min_x >= f.fw || min_y >= f.band_hi);
+    if (edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y) < 10 || off) { n.n_cull++; return 0u; }
+    return 1u;
+}
 
-    // ---- candidates, densely packed, 256 per round: exact boxes, row ownership, coverage setup, walk ------------
+// Candidates, densely packed, 256 per round: exact boxes, row ownership, coverage setup, and the direct walk of every
+// unclipped triangle under 16 x 16 pixels.  `fetch(i, item, r0, r1, r2)` hands out candidate i: its order key
+// (| ITEM_STRADDLE) and, for non-straddlers, its three raster-space vertices.  All 256 threads call.
+template <typename Fetch>
+__device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, WalkShared &wsh, uint32_t n_cand, FrontCounts &n, Fetch fetch) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     for (uint32_t cbase = 0; cbase < n_cand; cbase += 256u) {
         if (tid < 4) { wsh.cls_count[tid] = 0; }
@@ -616,11 +610,11 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
         uint32_t route = 0;   // 1 work item for K2b, 3 walked here
         uint32_t item = 0, my_cls = 0, my_rows = 0, my_off = 0;
         if (cbase + tid < n_cand) {
-            item = wsh.cand[cbase + tid];
+            float4 r0, r1, r2;
+            fetch(cbase + tid, item, r0, r1, r2);
             if (item & ITEM_STRADDLE) {
                 route = 1;
             } else {
-                const float4 r0 = rv[__ldg(f.vi0 + item)], r1 = rv[__ldg(f.vi1 + item)], r2 = rv[__ldg(f.vi2 + item)];
                 const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
                 const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
                 const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
@@ -637,7 +631,7 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
                         rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
                     }
                     if (rows) {
-                        route = 3; n_direct++;
+                        route = 3; n.n_direct++;
                         VisCore vc;
                         vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
                                  edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y), xmin, ymin, vc);
@@ -658,12 +652,12 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
                         my_cls = (xmax - xmin) >> 2;
                         my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(rows));
                     } else {
-                        n_cull++;
+                        n.n_cull++;
                     }
                 } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
                     route = 1;
                 } else {
-                    n_cull++;
+                    n.n_cull++;
                 }
             }
         }
@@ -709,20 +703,209 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
         }
         __syncthreads();   // parked boxes and items are rewritten by the next round
     }
+}
 
-    // ---- statistics: one shared-memory atomic per warp, one global atomic per CTA and counter --------------------
-    n_near = __reduce_add_sync(0xFFFFFFFFu, n_near); n_clip = __reduce_add_sync(0xFFFFFFFFu, n_clip);
-    n_direct = __reduce_add_sync(0xFFFFFFFFu, n_direct); n_cull = __reduce_add_sync(0xFFFFFFFFu, n_cull);
+// statistics: one shared-memory atomic per warp, one global atomic per CTA and counter (all 256 threads call)
+__device__ __forceinline__ void publish_front_counts(const Frame &f, uint32_t view, WalkShared &wsh, FrontCounts n) {
+    const uint32_t tid = threadIdx.x, lane = lane_id();
+    n.n_near = __reduce_add_sync(0xFFFFFFFFu, n.n_near); n.n_clip = __reduce_add_sync(0xFFFFFFFFu, n.n_clip);
+    n.n_direct = __reduce_add_sync(0xFFFFFFFFu, n.n_direct); n.n_cull = __reduce_add_sync(0xFFFFFFFFu, n.n_cull);
     if (lane == 0) {
-        if (n_near) { atomicAdd(&wsh.stats[0], n_near); }
-        if (n_clip) { atomicAdd(&wsh.stats[1], n_clip); }
-        if (n_direct) { atomicAdd(&wsh.stats[2], n_direct); }
-        if (n_cull) { atomicAdd(&wsh.stats[3], n_cull); }
+        if (n.n_near) { atomicAdd(&wsh.stats[0], n.n_near); }
+        if (n.n_clip) { atomicAdd(&wsh.stats[1], n.n_clip); }
+        if (n.n_direct) { atomicAdd(&wsh.stats[2], n.n_direct); }
+        if (n.n_cull) { atomicAdd(&wsh.stats[3], n.n_cull); }
     }
     __syncthreads();
     if (tid < 4 && wsh.stats[tid]) {
         atomicAdd(f.counters + view * C_COUNT + (tid == 2u ? (uint32_t)C_DIRECT : (uint32_t)C_NEAR + tid), wsh.stats[tid]);   // C_NEAR, C_CLIPPED, C_DIRECT, C_CULLED
     }
+}
+
+struct ClassifyShared {
+    WalkShared w;
+    uint32_t cand[CLS_PER_CTA];        // triangles that passed the front tests (| ITEM_STRADDLE)
+};
+
+__global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
+    __shared__ ClassifyShared csh;
+    WalkShared &wsh = csh.w;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    if (tid == 0) { wsh.n_cand = 0; }
+    if (tid < 4) { wsh.stats[tid] = 0; }
+    __syncthreads();
+    const float4 *rv = f.rv + (size_t)view * f.Vpad;
+    FrontCounts n = {0u, 0u, 0u, 0u};   // per-thread statistics, reduced once at the end
+
+    // ---- front: near reject, straddle, area cull, screen/band reject (render.cpp:306-317), 4 triangles per thread ----
+#pragma unroll 2
+    for (uint32_t pass = 0; pass < CLS_PER_CTA / 256u; pass++) {
+        const uint32_t t = blockIdx.x * CLS_PER_CTA + pass * 256u + tid;
+        uint32_t cand = 0;   // 1 candidate, 2 candidate that straddles the near plane
+        if (t < f.T) {
+            const float4 r0 = rv[__ldg(f.vi0 + t)], r1 = rv[__ldg(f.vi1 + t)], r2 = rv[__ldg(f.vi2 + t)];
+            cand = front_test(f, r0, r1, r2, n);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
+        uint32_t base = 0;
+        if (lane == 0 && m) { base = atomicAdd(&wsh.n_cand, __popc(m)); }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (cand) { csh.cand[base + __popc(m & ((1u << lane) - 1u))] = t | (cand == 2 ? ITEM_STRADDLE : 0u); }
+    }
+    __syncthreads();
+    walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
+        item = csh.cand[i];
+        if (!(item & ITEM_STRADDLE)) { r0 = rv[__ldg(f.vi0 + item)]; r1 = rv[__ldg(f.vi1 + item)]; r2 = rv[__ldg(f.vi2 + item)]; }
+    });
+    publish_front_counts(f, view, wsh, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2a over the spatial pre-partition (cluster.hpp): one CTA per batch of CL_BATCH clusters.
+//   1. one thread per cluster: a conservative verdict from the bounding sphere — every vertex at or behind the near
+//      plane (all its triangles are near-rejected, render.cpp:306), or every triangle certainly culled: off screen, outside
+//      the rows this submission owns, or too small to reach `area >= 10` (render.cpp:311-317).  Such a cluster costs
+//      32 bytes; its vertices are never transformed.  On an n-GPU screen partition a rank skips what misses its rows,
+//      so the geometry work shrinks with n.
+//   2. the vertex stage (render.cpp:285-289) of the surviving clusters, streamed from the cluster-private position
+//      arrays into SHARED memory — raster-space vertices never travel to HBM;
+//   3. the front tests, one thread per triangle word, corners gathered from shared memory; warp-ballot compaction;
+//   4. the candidates' coverage setup and direct walk (walk_candidates), exactly as in triangle_classify.
+// Every skipped triangle is proven rejected by the reference's own per-triangle tests, so the frame cannot change.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CL_DEAD = 0xFFFFFFFFu;
+
+struct FrontShared {
+    float4 rv[CL_BATCH * CL_MAX_VERTS];      // raster-space vertices of the batch's surviving clusters
+    WalkShared w;
+    uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // position in the batch | 0x8000 for a straddler
+    uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in rv[], CL_DEAD = cluster skipped
+    uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
+};
+static_assert(CL_BATCH * CL_MAX_TRIS <= 0x8000, "candidate entries are 15-bit positions plus the straddle flag");
+static_assert(sizeof(FrontShared) <= 55 * 1024, "FrontShared must leave room for four CTAs per SM");
+
+// 0: process per triangle; 1: every triangle near-rejected; 2: every triangle culled (off screen / not ours / too small)
+__device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &cam, float cx, float cy, float cz, float radius, float max_edge) {
+    const float3 cc = xform(cam, cx, cy, cz, 1.0f);
+    const float ax = fabsf(cx) + radius, ay = fabsf(cy) + radius, az = fabsf(cz) + radius;
+    float rho[3], err = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float m0 = cam.m[4 * i], m1 = cam.m[4 * i + 1], m2 = cam.m[4 * i + 2], m3 = cam.m[4 * i + 3];
+        // |binary32 transform - exact transform| of any point of the cluster: four products and three sums, each within
+        // 2^-24 of the running magnitude; 2^-21 of the summed magnitudes is more than twice that
+        const float e = 0x1p-21f * (fabsf(m0) * ax + fabsf(m1) * ay + fabsf(m2) * az + fabsf(m3));
+        const float norm = sqrtf(m0 * m0 + m1 * m1 + m2 * m2) * 1.000001f;
+        // every vertex's computed camera-space coordinate i lies within rho[i] of the computed centre's
+        rho[i] = (norm * radius + 2.f * e) * 1.000001f + 1e-30f;
+        err = fmaxf(err, e);
+    }
+    const float d = -cc.z, d_min = d - rho[2], d_max = d + rho[2];
+    // near reject (render.cpp:306): every vertex has rv.z = -cv.z <= near.  -cv.z == 0 makes rv.z NaN in the reference's
+    // expression (0 / 0), so only clusters strictly behind the eye plane or strictly between it and the near plane count.
+    if (d_max < 0.f || (d_min > 0.f && d_max <= kNear)) { return 1u; }
+    if (!(d_min > kNear * 1.000001f)) { return 0u; }   // may touch the near plane (or bounds are not finite): per triangle
+    // every vertex strictly in front: raster coordinates by interval arithmetic over the box [cc - rho, cc + rho]
+    const float x_lo = cc.x - rho[0], x_hi = cc.x + rho[0], y_lo = -cc.y - rho[1], y_hi = -cc.y + rho[1];   // raster y grows downwards (-cv.y)
+    const float inv_min = f.factor / d_min, inv_max = f.factor / d_max;   // d_min < d_max, both positive
+    const float qx_hi = x_hi * (x_hi >= 0.f ? inv_min : inv_max), qx_lo = x_lo * (x_lo >= 0.f ? inv_max : inv_min);
+    const float qy_hi = y_hi * (y_hi >= 0.f ? inv_min : inv_max), qy_lo = y_lo * (y_lo >= 0.f ? inv_max : inv_min);
+    // slack: rounding of the vertices' own projections and of this evaluation (a few 2^-24 of the magnitudes)
+    const float sx = 0x1p-18f * (fmaxf(fabsf(qx_lo), fabsf(qx_hi)) + f.fw) + 0.01f, sy = 0x1p-18f * (fmaxf(fabsf(qy_lo), fabsf(qy_hi)) + f.fh) + 0.01f;
+    const float sx_hi = qx_hi + f.half_w + sx, sx_lo = qx_lo + f.half_w - sx, sy_hi = qy_hi + f.half_h + sy, sy_lo = qy_lo + f.half_h - sy;
+    // off screen / outside the band (render.cpp:311-314 and the partition's row range)
+    if (sx_hi < 0.f || sy_hi < f.band_lo || sx_lo >= f.fw || sy_lo >= f.band_hi) { return 2u; }
+    if (f.row_stride != 1u) {   // interleaved tile rows: does the cluster reach a row this submission owns?
+        const uint32_t ylo = (uint32_t)fmaxf(0.f, floorf(sy_lo)), yhi = (uint32_t)fminf(f.fh - 1.f, sy_hi);
+        if (ylo > yhi || owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) == 0u) { return 2u; }
+    }
+    // too small (render.cpp:316-317): |area| <= product of two projected edges.  A camera-space segment of length L at
+    // depth >= d_min whose endpoints project at tangents (tu, tv) is at most factor / d_min * L * sqrt(1 + tu^2 + tv^2)
+    // pixels long.  L: the longest object-space edge through the matrix (largest singular value bounded by Gershgorin on
+    // the Gram matrix; 1 for a camera's orthonormal rows) plus the endpoints' rounding.
+    float gram = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            row += fabsf(cam.m[4 * i] * cam.m[4 * j] + cam.m[4 * i + 1] * cam.m[4 * j + 1] + cam.m[4 * i + 2] * cam.m[4 * j + 2]);
+        }
+        gram = fmaxf(gram, row);
+    }
+    const float len = sqrtf(gram) * 1.000001f * max_edge + 4.f * err;
+    const float tu = fmaxf(fabsf(x_lo), fabsf(x_hi)) / d_min, tv = fmaxf(fabsf(y_lo), fabsf(y_hi)) / d_min;
+    const float pixels = inv_min * len * sqrtf(1.f + tu * tu + tv * tv) * 1.00001f + 2.f * (sx + sy);
+    if (pixels <= 3.09f) { return 2u; }   // (3.09 + rounding)^2 < 10
+    return 0u;
+}
+
+__global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ Frame f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FrontShared &sh = *reinterpret_cast<FrontShared *>(smem_raw);
+    WalkShared &wsh = sh.w;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    const uint32_t c0 = blockIdx.x * CL_BATCH, nc = min(CL_BATCH, f.n_clusters - c0);
+    const Cam cam = load_cam(f.cams + 12 * view);
+    if (tid == 0) { wsh.n_cand = 0; }
+    if (tid < 4) { wsh.stats[tid] = 0; }
+    FrontCounts n = {0u, 0u, 0u, 0u};
+    const uint4 first = __ldg(f.cl_hdr + 2 * (size_t)c0 + 1), last = __ldg(f.cl_hdr + 2 * (size_t)(c0 + nc) + 1);
+    const uint32_t v_begin = first.z, v_end = last.z, t_begin = first.w, t_end = last.w;
+
+    // ---- 1. cluster verdicts ---------------------------------------------------------------------------------------
+    if (tid < CL_BATCH) {
+        uint32_t base = CL_DEAD, delta = 0;
+        if (tid < nc) {
+            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid)), h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
+            const uint32_t n_tris = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w - h1.w;
+            const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
+                                                                      __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+            if (verdict == 0u) { base = h1.z - v_begin; }
+            else if (verdict == 1u) { n.n_near += n_tris; }
+            else { n.n_cull += n_tris; }
+            delta = h1.y - h1.w;   // t0 - tri_off (mod 2^32)
+        }
+        sh.ctab[tid] = base; sh.cdelta[tid] = delta;
+    }
+    __syncthreads();
+
+    // ---- 2. vertex stage of the surviving clusters, into shared memory --------------------------------------------------
+    for (uint32_t j = v_begin + tid; j < v_end; j += 256u) {
+        const uint32_t base = sh.ctab[__ldg(f.cl_vslot + j)];
+        if (base != CL_DEAD) {
+            const float3 cv = xform(cam, __ldg(f.cl_px + j), __ldg(f.cl_py + j), __ldg(f.cl_pz + j), 1.0f);
+            const float3 r = project(cv, f.factor, f.half_w, f.half_h);
+            sh.rv[j - v_begin] = make_float4(r.x, r.y, r.z, 0.f);
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. front tests, one thread per triangle word --------------------------------------------------------------------
+    for (uint32_t jb = t_begin; jb < t_end; jb += 256u) {
+        const uint32_t j = jb + tid;
+        uint32_t cand = 0;
+        if (j < t_end) {
+            const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
+            if (base != CL_DEAD) { cand = front_test(f, sh.rv[base + (w & 255u)], sh.rv[base + ((w >> 8) & 255u)], sh.rv[base + ((w >> 16) & 255u)], n); }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
+        uint32_t pos = 0;
+        if (lane == 0 && m) { pos = atomicAdd(&wsh.n_cand, __popc(m)); }
+        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        if (cand) { sh.cand[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((j - t_begin) | (cand == 2 ? 0x8000u : 0u)); }
+    }
+    __syncthreads();
+
+    // ---- 4. candidates: coverage setup + direct walk ---------------------------------------------------------------------
+    walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
+        const uint32_t e = sh.cand[i], j = t_begin + (e & 0x7FFFu);
+        const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, base = sh.ctab[slot];
+        item = (j + sh.cdelta[slot]) | ((e & 0x8000u) ? ITEM_STRADDLE : 0u);   // the original triangle index is the order key
+        r0 = sh.rv[base + (w & 255u)]; r1 = sh.rv[base + ((w >> 8) & 255u)]; r2 = sh.rv[base + ((w >> 16) & 255u)];
+    });
+    publish_front_counts(f, view, wsh, n);
 }
 
 // K2b: dense setup over the compacted work list (persistent grid-stride; every lane has a survivor
@@ -1755,6 +1938,10 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(tile_raster_queue, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
     // both keep ~40 KB of static shared memory per CTA: without the carve-out hint the driver may leave too little for 4-6 CTAs per SM
+    e = cudaFuncSetAttribute(cluster_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontShared));
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(cluster_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
     if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1769,8 +1956,16 @@ static inline void mark(const LaunchMarks *m, const char *kernel) { if (m) { m->
 int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     int launches = 0;
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
-    vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
-    triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");
+    if (f.cl_hdr) {
+        // spatial pre-partition: vertex stage + front + direct walk in one kernel over the clusters; the frame's counters
+        // and tile histograms (zeroed by vertex_stage on the other path) are cleared by two small memsets
+        cudaMemsetAsync(f.counters, 0, (size_t)f.n_views * C_COUNT * sizeof(uint32_t), s);
+        cudaMemsetAsync(f.tile_count, 0, (size_t)f.n_views * f.tile_stride * sizeof(uint32_t), s);
+        cluster_front<<<dim3(max(1u, ceil_div(f.n_clusters, CL_BATCH)), f.n_views), 256, sizeof(FrontShared), s>>>(f); launches++; mark(m, "cluster_front");
+    } else {
+        vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
+        triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");
+    }
     triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_setup");
     // cooperative binning of the big triangles, flat visibility pass over the recorded small ones (clipped or spawned),
     // and — by the last CTA to finish — the frame's tile statistics and overflow record
@@ -1805,6 +2000,11 @@ int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *m) 
     if (!f.coltab) { return 1; }
     span_walk<<<dim3(ceil_div(f.H, 128u), SPAN_MAX * 3u, f.n_views), 128, 0, s>>>(f); mark(m, "span_walk");
     return 2;
+}
+
+// the vertex stage alone (raster-vertex dumps when the frame itself went through the cluster front)
+void launch_vertex_stage(const Frame &f, cudaStream_t s) {
+    vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f);
 }
 
 // test hook: the device build of walk_jump on arrays (tests compare it with sequential adds)

@@ -97,6 +97,14 @@ struct Frame {
     const uint4 *attr;
     const uint32_t *texels;
     uint32_t V, Vpad, T, A, n_tex;
+    // spatial pre-partition of the triangle stream (cluster.hpp); cl_hdr == null: the unclustered front (vertex_stage +
+    // triangle_classify) runs instead
+    const uint4 *cl_hdr;          // 2 x uint4 per cluster, n_clusters + 1 (sentinel)
+    const float *cl_px, *cl_py, *cl_pz;
+    const uint8_t *cl_vslot;
+    const uint32_t *cl_tri;
+    uint32_t n_clusters;
+    int cluster_cull;             // 0: every cluster is processed per triangle (A/B and tests)
     // views
     const float *cams;  // n_views x 12
     uint32_t n_views;
@@ -108,7 +116,7 @@ struct Frame {
     uint32_t rs_magic;                               // floor(2^32 / row_stride) + 1: a / row_stride == umulhi(a, rs_magic) for a * row_stride < 2^32
     uint32_t raster_row0, raster_rows;   // tile rows [raster_row0, raster_row0 + raster_rows) of the band go in one raster launch
     // per-view scratch
-    float4 *rv;
+    float4 *rv;           // null on the cluster path: raster-space vertices live in shared memory only
     SetupVis *vis;
     SetupShade *shade;
     uint32_t *slot_of;    // [views][2T] order key -> survivor slot (written for recorded survivors only)
@@ -162,6 +170,7 @@ struct LaunchMarks { void (*fn)(void *ctx, const char *kernel); void *ctx; };
 int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);   // vertex stage, classify + direct walk, clip/setup, binning + flat walk
 int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);     // per-tile visibility + shading + write-out
 int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
+void launch_vertex_stage(const Frame &f, cudaStream_t s);   // vertex stage alone into f.rv (raster-vertex dumps)
 cudaError_t configure_kernels();
 void launch_exact_math(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed, unsigned long long *result,
                        cudaStream_t st);

@@ -25,6 +25,7 @@
 
 #include "../../include/render.h"
 #include "../../include/s3r_b200.h"
+#include "cluster.hpp"
 #include "hostcopy.hpp"
 #include "pipeline.cuh"
 
@@ -70,6 +71,14 @@ struct S3RRenderer {
     DevBuf<uint32_t> vi[3], ai[3];
     DevBuf<uint4> attr;
     DevBuf<uint32_t> texels;
+    // spatial pre-partition of the triangle stream (cluster.hpp), built at load
+    DevBuf<uint4> cl_hdr;
+    DevBuf<float> cl_px, cl_py, cl_pz;
+    DevBuf<uint8_t> cl_vslot;
+    DevBuf<uint32_t> cl_tri;
+    uint32_t n_clusters = 0;
+    int opt_clusters = 1, opt_cluster_cull = 1;
+    Frame last_frame;   // parameter block of the last submission (raster-vertex dumps on the cluster path)
     // per-view scratch
     uint32_t views_cap = 0, tile_stride = 0;
     uint32_t setup_cap = 0, tile_cap = 0, big_cap = 0;
@@ -185,6 +194,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -257,6 +267,20 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
         CUDA_TRY(cudaMemcpy(r->vi[k].p, v[k].data(), v[k].size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->ai[k].p, a[k].data(), a[k].size() * 4, cudaMemcpyHostToDevice));
     }
+    r->n_clusters = 0;
+    if (T > 0) {   // clusters of consecutive, spatially close triangles for the general path's front kernel
+        ClusterSet cs;
+        build_clusters(px.data(), py.data(), pz.data(), v[0].data(), v[1].data(), v[2].data(), T, cs);
+        CUDA_TRY(r->cl_hdr.ensure(cs.hdr.size() * 2)); CUDA_TRY(r->cl_px.ensure(cs.px.size())); CUDA_TRY(r->cl_py.ensure(cs.px.size()));
+        CUDA_TRY(r->cl_pz.ensure(cs.px.size())); CUDA_TRY(r->cl_vslot.ensure(cs.vslot.size())); CUDA_TRY(r->cl_tri.ensure(cs.tri.size()));
+        CUDA_TRY(cudaMemcpy(r->cl_hdr.p, cs.hdr.data(), cs.hdr.size() * sizeof(ClusterHeader), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->cl_px.p, cs.px.data(), cs.px.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->cl_py.p, cs.py.data(), cs.py.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->cl_pz.p, cs.pz.data(), cs.pz.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->cl_vslot.p, cs.vslot.data(), cs.vslot.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->cl_tri.p, cs.tri.data(), cs.tri.size() * 4, cudaMemcpyHostToDevice));
+        r->n_clusters = cs.n_clusters;
+    }
     CUDA_TRY(r->attr.ensure(at.size()));
     CUDA_TRY(cudaMemcpy(r->attr.p, at.data(), at.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     CUDA_TRY(r->texels.ensure(std::max<uint64_t>(n_texels, 1)));
@@ -315,6 +339,38 @@ extern "C" int s3r_load_scene_file(S3RRenderer *r, const char *path) {
     }
     munmap(map, size);
     return rc;
+}
+
+// Test hook, callable without a GPU: the spatial pre-partition (cluster.hpp) of a triangle stream.  counts_out =
+// {clusters, cluster vertices, triangles}; the arrays are filled when they are non-null and large enough.
+extern "C" int s3r_debug_clusters(const float *vertices, uint64_t V, const uint64_t *vidx, uint64_t I, void *hdr_out, uint64_t hdr_cap,
+                                  float *pos_out, uint8_t *vslot_out, uint64_t v_cap, uint32_t *tri_out, uint64_t counts_out[3]) {
+    if (!vertices || !vidx || !counts_out || I % 3) { return fail(S3R_E_ARG, "bad cluster request"); }
+    const uint64_t T = I / 3;
+    try {
+        std::vector<float> px(V), py(V), pz(V);
+        for (uint64_t i = 0; i < V; i++) { px[i] = vertices[4 * i]; py[i] = vertices[4 * i + 1]; pz[i] = vertices[4 * i + 2]; }
+        std::vector<uint32_t> v[3];
+        for (int k = 0; k < 3; k++) { v[k].resize(T); }
+        for (uint64_t t = 0; t < T; t++) {
+            for (int k = 0; k < 3; k++) {
+                if (vidx[3 * t + k] >= V) { return fail(S3R_E_SCENE, "index out of range"); }
+                v[k][t] = (uint32_t)vidx[3 * t + k];
+            }
+        }
+        ClusterSet cs;
+        build_clusters(px.data(), py.data(), pz.data(), v[0].data(), v[1].data(), v[2].data(), T, cs);
+        counts_out[0] = cs.n_clusters; counts_out[1] = cs.px.size(); counts_out[2] = cs.tri.size();
+        if (hdr_out && hdr_cap >= cs.hdr.size()) { memcpy(hdr_out, cs.hdr.data(), cs.hdr.size() * sizeof(ClusterHeader)); }
+        if (pos_out && vslot_out && v_cap >= cs.px.size()) {
+            memcpy(pos_out, cs.px.data(), cs.px.size() * 4); memcpy(pos_out + v_cap, cs.py.data(), cs.px.size() * 4);
+            memcpy(pos_out + 2 * v_cap, cs.pz.data(), cs.px.size() * 4); memcpy(vslot_out, cs.vslot.data(), cs.vslot.size());
+        }
+        if (tri_out) { memcpy(tri_out, cs.tri.data(), cs.tri.size() * 4); }
+    } catch (const std::exception &e) {
+        return fail(S3R_E_IO, std::string("clustering failed: ") + e.what());
+    }
+    return S3R_OK;
 }
 
 extern "C" int s3r_scene_counts(const S3RRenderer *r, uint64_t *v, uint64_t *i, uint64_t *a, uint64_t *t) {
@@ -404,6 +460,8 @@ static bool uses_direct_bin(const S3RRenderer *r) {
     return r->opt_fused_small && 2ull * r->T <= (uint64_t)SORT_CAP && r->setup_cap >= 2ull * r->T;
 }
 
+static bool uses_clusters(const S3RRenderer *r) { return r->opt_clusters && r->n_clusters > 0; }
+
 static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     const uint32_t T = (uint32_t)r->T;
     if (r->setup_cap == 0) {
@@ -424,7 +482,7 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
         r->tile_stride = std::max(tile_stride, r->tile_stride);
     }
     const size_t vc = r->views_cap;
-    CUDA_TRY(r->rv.ensure(vc * r->Vpad));
+    if (uses_direct_bin(r) || !uses_clusters(r)) { CUDA_TRY(r->rv.ensure(vc * r->Vpad)); }   // the cluster front keeps raster-space vertices on chip
     CUDA_TRY(r->vis.ensure(vc * r->setup_cap));
     CUDA_TRY(r->shade.ensure(vc * r->setup_cap));
     CUDA_TRY(r->head.ensure(vc * r->setup_cap));
@@ -590,7 +648,13 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.W = W; f.H = H; f.y0 = y0; f.y1 = y1;
     f.fw = (float)W; f.fh = (float)H; f.half_w = f.fw / 2; f.half_h = f.fh / 2;  // screen_size / 2, render.cpp:284,288
     f.factor = r->factor_override != 0.f ? r->factor_override : s3r_factor(H);
-    f.rv = r->rv.p; f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
+    f.rv = r->rv.p;
+    if (!uses_direct_bin(r) && uses_clusters(r)) {
+        f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
+        f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
+        f.rv = nullptr;
+    }
+    f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
     f.band_lo = (float)y0; f.band_hi = (float)y1;
     f.counters = r->counters.p;
     f.sticky = r->sticky.p;
@@ -673,6 +737,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t2[slot], s)); r->slot_timed[slot] = true; }
     CUDA_TRY(cudaGetLastError());
+    r->last_frame = f;
     return S3R_OK;
 }
 
@@ -986,6 +1051,17 @@ extern "C" int s3r_dump_raster_vertices(S3RRenderer *r, uint32_t view, float *ou
     if (!r || !out) { return fail(S3R_E_ARG, "null argument"); }
     if (view >= r->last_views || cap < r->V) { return fail(S3R_E_ARG, "view/capacity out of range"); }
     CUDA_TRY(cudaSetDevice(r->device));
+    if (!r->last_frame.rv) {
+        // the frame went through the cluster front, which keeps raster-space vertices in shared memory: run the vertex
+        // stage alone over the original vertex stream with the same camera, factor and frame size
+        CUDA_TRY(cudaStreamSynchronize(r->last_stream ? r->last_stream : r->stream));
+        CUDA_TRY(r->rv.ensure((size_t)r->views_cap * r->Vpad));
+        Frame f = r->last_frame;
+        f.rv = r->rv.p; f.counters = nullptr; f.n_tiles = 0;
+        launch_vertex_stage(f, r->stream);
+        r->launches++;
+        CUDA_TRY(cudaStreamSynchronize(r->stream));
+    }
     CUDA_TRY(cudaMemcpy(out, r->rv.p + (size_t)view * r->Vpad, r->V * sizeof(float4), cudaMemcpyDeviceToHost));
     return S3R_OK;
 }
@@ -1095,6 +1171,8 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "spans")) { r->opt_spans = value != 0; return S3R_OK; }
+    if (!strcmp(name, "clusters")) { cudaStreamSynchronize(r->stream); r->opt_clusters = value != 0; return S3R_OK; }
+    if (!strcmp(name, "cluster_cull")) { r->opt_cluster_cull = value != 0; return S3R_OK; }
     if (!strcmp(name, "tensor_store")) { r->opt_tmap = value != 0; return S3R_OK; }
     if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
         if (value < 16 || value > 65536) { return fail(S3R_E_ARG, "flat_max out of range"); }

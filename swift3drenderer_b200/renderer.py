@@ -72,7 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
-    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing", "s3r_debug_clusters",
 ]
 
 
@@ -148,6 +148,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_sink_submit.argtypes = [vp, vp, vp]
     lib.s3r_sink_close.argtypes = [vp, ctypes.POINTER(u64)]
     lib.s3r_debug_band_edges.argtypes = [u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u32), ctypes.c_int]
+    lib.s3r_debug_clusters.argtypes = [vp, u64, vp, u64, vp, u64, vp, vp, u64, vp, ctypes.POINTER(u64)]
     lib.s3r_get_kernel_timing.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     if path is None:
         _lib = lib
@@ -183,6 +184,30 @@ def camera_path(inputs) -> np.ndarray:
     """(n, 12) camera matrices: pose k is the state after k + 1 Input records."""
     cam = Camera()
     return np.stack([cam.update(r) for r in inputs]) if len(inputs) else np.zeros((0, 12), np.float32)
+
+
+CLUSTER_HDR_DTYPE = np.dtype([("center", "<f4", (3,)), ("radius", "<f4"), ("max_edge", "<f4"), ("t0", "<u4"), ("v_off", "<u4"), ("tri_off", "<u4")])
+
+
+def debug_clusters(scene) -> dict:
+    """The load-time spatial pre-partition of ``scene``'s triangle stream (test hook, no GPU needed)."""
+    lib = load_library()
+    v = np.ascontiguousarray(scene.vertices, "<f4")
+    vi = np.ascontiguousarray(scene.vertex_indices, "<u8")
+    counts = (ctypes.c_uint64 * 3)()
+    rc = lib.s3r_debug_clusters(v.ctypes.data, v.shape[0], vi.ctypes.data, vi.shape[0], None, 0, None, None, 0, None, counts)
+    if rc < 0:
+        raise RendererError(lib.s3r_last_error().decode())
+    nc, nv, nt = int(counts[0]), int(counts[1]), int(counts[2])
+    hdr = np.zeros(nc + 1, CLUSTER_HDR_DTYPE)
+    pos = np.zeros((3, max(nv, 1)), np.float32)
+    vslot = np.zeros(max(nv, 1), np.uint8)
+    tri = np.zeros(max(nt, 1), np.uint32)
+    rc = lib.s3r_debug_clusters(v.ctypes.data, v.shape[0], vi.ctypes.data, vi.shape[0], hdr.ctypes.data, nc + 1, pos.ctypes.data,
+                                vslot.ctypes.data, max(nv, 1), tri.ctypes.data, counts)
+    if rc < 0:
+        raise RendererError(lib.s3r_last_error().decode())
+    return {"hdr": hdr, "pos": pos[:, :nv], "vslot": vslot[:nv], "tri": tri[:nt]}
 
 
 def tile_height() -> int:

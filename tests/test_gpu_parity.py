@@ -576,3 +576,85 @@ def test_frame_sink_writes_device_frames(gpu_renderer, renderer_lib, tmp_path):
         rec = body[i * (6 + n):(i + 1) * (6 + n)]
         assert rec[:6] == b"FRAME\n"
         assert np.array_equal(np.frombuffer(rec[6:], np.uint8), _i420_reference(want[i])), f"y4m frame {f}"
+
+
+def _cluster_scenes():
+    return (("field", lambda: S.icosahedron_field(20000, seed=12, extent=(300.0, 170.0, 160.0), r_range=(0.5, 4.0), center=(0.0, 0.0, -420.0)), "spin"),
+            ("inside", lambda: S.icosahedron_field(6000, seed=13, extent=60), "spin"),   # camera inside the field: clusters behind, beside, across the near plane
+            ("clip", lambda: S.clip_stress_scene(3000), "strafe"),
+            ("floor", lambda: S.shipped_scene(2, regular_floor=True), "flythrough"))
+
+
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_cluster_front_equals_the_unclustered_front_and_the_oracle(which, renderer_lib, oracle_port):
+    """The spatial pre-partition is invisible: frames AND the per-triangle statistics (near-rejected / clipped / culled /
+    rasterised, render.cpp:306-317) are the same whether whole clusters are rejected by their bounds, every triangle of every
+    cluster is tested, or the raw triangle stream is classified — whole frames, bands and interleaved tile rows."""
+    import torch
+    name, build, script = _cluster_scenes()[which]
+    sc = build()
+    r = renderer_lib.Renderer(0)
+    try:
+        r.set_option("fused_small", 0)   # ("floor" has 1 849 triangles: force it onto the general path)
+        r.load_scene(sc)
+        osc = oracle_port.OracleScene(sc)
+        n = 600 if script == "flythrough" else 24
+        mats = renderer_lib.camera_path(S.input_script(script, n))
+        W, H = 800, 450
+        th = renderer_lib.tile_height()
+        for f in ((40, 100, 330) if script == "flythrough" else (0, 7, 23)):
+            o = osc.render(mats[f], W, H)
+            ref_stats = None
+            for clusters, cull in ((1, 1), (1, 0), (0, 0)):
+                r.set_option("clusters", clusters); r.set_option("cluster_cull", cull)
+                got = r.render(mats[f], W, H)[0]
+                assert_same(got, o["pixels"], f"{name} frame {f} clusters={clusters} cull={cull}")
+                st = r.stats()
+                assert st["near_rejected"] == o["stats"]["near_rejected"] and st["clipped"] == o["stats"]["clipped"]
+                assert st["setups"] == o["stats"]["rasterized"] and st["culled"] == o["stats"]["offscreen"] + o["stats"]["small_or_backfacing"]
+                ref_stats = ref_stats or st
+                assert st == ref_stats
+            r.set_option("clusters", 1); r.set_option("cluster_cull", 1)
+            parts = [r.render(mats[f], W, H, y0=H * k // 3, y1=H * (k + 1) // 3)[0] for k in range(3)]
+            assert_same(np.concatenate(parts, 0), o["pixels"], f"{name} frame {f}: 3 bands through the cluster front")
+            frame = np.zeros((H, W), np.uint32)
+            for phase in range(4):
+                rows, frame_rows, buf_rows = renderer_lib.rows_layout(H, 4, phase, th)
+                buf = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
+                for attempt in range(4):
+                    r.render_device_rows(mats[f], W, H, 4, phase, buf.data_ptr())
+                    if not r.finish():
+                        break
+                frame[frame_rows] = buf.cpu().numpy().view(np.uint32)[buf_rows]
+            assert_same(frame, o["pixels"], f"{name} frame {f}: 4 interleaved phases through the cluster front")
+    finally:
+        r.close()
+
+
+def test_cluster_rejection_is_conservative_for_any_matrix(renderer_lib, oracle_port):
+    """s3r_render_device takes any 3x4 matrix, not only a camera's orthonormal rows: scaled, sheared and far-away views
+    (most clusters too small, off screen or behind) still give the oracle's frame and statistics."""
+    sc = S.icosahedron_field(8000, seed=21, extent=(200.0, 120.0, 100.0), r_range=(0.5, 6.0), center=(0.0, 0.0, -300.0))
+    r = renderer_lib.Renderer(0)
+    try:
+        r.load_scene(sc)
+        osc = oracle_port.OracleScene(sc)
+        base = renderer_lib.camera_path(S.input_script("spin", 6))[5].reshape(3, 4)
+        views = []
+        for scale, shear, back in ((1.0, 0.0, 0.0), (1.7, 0.0, 0.0), (0.45, 0.0, 0.0), (1.0, 0.35, 0.0), (1.0, 0.0, 900.0), (1.0, 0.0, -250.0)):
+            m = base.copy()
+            m[:, :3] *= scale
+            m[0, :3] += shear * m[1, :3]
+            m[2, 3] -= back                      # camera-space z shifts: the field recedes (back > 0) or swallows the camera
+            views.append(m.reshape(12).astype(np.float32))
+        culled_clusters = 0
+        for k, m in enumerate(views):
+            o = osc.render(m, 640, 360)
+            assert_same(r.render(m, 640, 360)[0], o["pixels"], f"matrix {k}")
+            st = r.stats()
+            assert st["near_rejected"] == o["stats"]["near_rejected"] and st["clipped"] == o["stats"]["clipped"]
+            assert st["setups"] == o["stats"]["rasterized"] and st["culled"] == o["stats"]["offscreen"] + o["stats"]["small_or_backfacing"]
+            culled_clusters += st["culled"]
+        assert culled_clusters > 0
+    finally:
+        r.close()
