@@ -38,10 +38,18 @@ namespace s3r {
 // ------------------------------------------------------------------------------------------------
 struct Cam { float m[12]; };
 
-__device__ __forceinline__ Cam load_cam(const float *p) {
+// The view's 3 x 4 camera matrix: from the parameter block when the submission has a single view (no upload, no global
+// load), otherwise from the uploaded array.
+__device__ __forceinline__ Cam load_cam(const Frame &f, uint32_t view) {
     Cam c;
+    if (f.cam_inline) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) { c.m[i] = __ldg(p + i); }
+        for (int i = 0; i < 12; i++) { c.m[i] = f.cam0[i]; }
+    } else {
+        const float *p = f.cams + 12 * view;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { c.m[i] = __ldg(p + i); }
+    }
     return c;
 }
 
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(256) vertex_stage(const __grid_constant__ Fram
     reset_body(f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     if (i4 >= f.Vpad) { return; }
-    vertex_body(f, load_cam(f.cams + 12 * blockIdx.y), blockIdx.y, i4);
+    vertex_body(f, load_cam(f, blockIdx.y), blockIdx.y, i4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
     WalkShared &wsh = sh.w;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
     const uint32_t c0 = blockIdx.x * CL_BATCH, nc = min(CL_BATCH, f.n_clusters - c0);
-    const Cam cam = load_cam(f.cams + 12 * view);
+    const Cam cam = load_cam(f, view);
     if (tid == 0) { wsh.n_cand = 0; }
     if (tid < 4) { wsh.stats[tid] = 0; }
     FrontCounts n = {0u, 0u, 0u, 0u};
@@ -913,7 +921,7 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
 __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x;
-    const Cam cam = load_cam(f.cams + 12 * view);
+    const Cam cam = load_cam(f, view);
     const uint32_t n_work = f.counters[view * C_COUNT + C_WORK];
     for (uint32_t base = blockIdx.x * 256u; base < n_work; base += gridDim.x * 256u) {
         if (tid == 0) { sh.count = min(256u, n_work - base); }
@@ -953,8 +961,16 @@ __device__ __forceinline__ void bin_big_body(const Frame &f, uint32_t view) {
 __device__ __forceinline__ void finalize_body(const Frame &f, uint32_t view, uint32_t *s_sum, uint32_t *s_max) {
     const uint32_t tid = threadIdx.x;
     uint32_t sum = 0, mx = 0;
-    for (uint32_t t = tid; t < f.n_tiles; t += 256u) {
-        const uint32_t c = __ldcg(f.tile_count + view * f.tile_stride + t);
+    // (the counts are fetched eight at a time: one CTA walks the whole table, and a dependent L2 round trip per
+    // iteration was 10 us of every frame)
+    for (uint32_t t0 = 0; t0 < f.n_tiles; t0 += 8u * 256u) {
+      uint32_t cs[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { const uint32_t t = t0 + k * 256u + tid; cs[k] = t < f.n_tiles ? __ldcg(f.tile_count + view * f.tile_stride + t) : 0u; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t t = t0 + k * 256u + tid, c = cs[k];
+        if (t >= f.n_tiles) { continue; }
         sum += c; mx = max(mx, c);
         // the tile kernel's work queue: one item per RASTER_CHUNK entries of a non-empty bin list
         const uint32_t n = min(c, f.tile_cap), chunks = (n + RASTER_CHUNK - 1u) / RASTER_CHUNK;
@@ -964,6 +980,7 @@ __device__ __forceinline__ void finalize_body(const Frame &f, uint32_t view, uin
                 f.raster_items[(size_t)view * f.items_cap + base + k] = make_uint2(t, k * RASTER_CHUNK);
             }
         }
+      }
     }
     atomicAdd(s_sum, sum);
     atomicMax(s_max, mx);
@@ -989,7 +1006,7 @@ __device__ __forceinline__ void finalize_body(const Frame &f, uint32_t view, uin
 __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
     const uint32_t view = blockIdx.x, tid = threadIdx.x;
-    const Cam cam = load_cam(f.cams + 12 * view);
+    const Cam cam = load_cam(f, view);
     if (tid < C_COUNT) { f.counters[view * C_COUNT + tid] = 0; }
     for (uint32_t i4 = tid * 4u; i4 < f.Vpad; i4 += 1024u) { vertex_body(f, cam, view, i4); }
     __syncthreads();
@@ -1786,7 +1803,7 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
         }
         __syncthreads();
         const uint32_t count = sh.count, n_tri = sh.n_tri;
-        const Cam cam = load_cam(f.cams + 12 * view);
+        const Cam cam = load_cam(f, view);
 #pragma unroll 1
         for (uint32_t tb = 0; tb < n_tri; tb += SHADE_TRIS) {
             // ---- 2. setups of this pass's triangles ------------------------------------------------
@@ -1978,9 +1995,13 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         tile_raster<<<dim3(f.tiles_x, f.raster_rows, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster");
         return 1;
     }
-    // general path (always one raster launch per frame): the queue holds every non-empty tile of the submission
-    tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster_queue");
-    // general path: the tile kernel only resolved the big triangles; shade the rows it covered
+    // general path: the queue holds every non-empty tile of the submission, so the tile kernel runs once per frame, with
+    // the first band; the bands only cut the shading pass (the host path copies band k while band k + 1 is shaded)
+    int launches = 0;
+    if (f.raster_row0 == 0u) {
+        tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster_queue");
+        launches++;
+    }
     uint32_t row0, nrows;
     if (f.row_stride == 1u) {
         const uint32_t ya = (f.tile_row0 + f.raster_row0) * TILE_H, yb = ya + f.raster_rows * TILE_H;
@@ -1991,8 +2012,9 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     }
     if (nrows) {
         shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, sizeof(ShadeShared), s>>>(f, row0, nrows); mark(m, "shade_tiles");
+        launches++;
     }
-    return 2;
+    return launches;
 }
 
 int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *m) {

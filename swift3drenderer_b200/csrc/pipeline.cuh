@@ -107,6 +107,8 @@ struct Frame {
     int cluster_cull;             // 0: every cluster is processed per triangle (A/B and tests)
     // views
     const float *cams;  // n_views x 12
+    float cam0[12];     // the matrix itself when the submission has one view (cam_inline): nothing is uploaded
+    int cam_inline;
     uint32_t n_views;
     uint32_t W, H, y0, y1;
     float fw, fh, half_w, half_h, factor;

@@ -112,7 +112,7 @@ struct S3RRenderer {
     cudaEvent_t ev_cams[RING] = {}, ev_t0[RING] = {}, ev_t1[RING] = {}, ev_t2[RING] = {};
     bool slot_used[RING] = {}, slot_timed[RING] = {};
     // per-kernel timing (option "timing"): an event after every kernel launch of a timed submission
-    static constexpr int MAX_MARKS = 12;
+    static constexpr int MAX_MARKS = 40;
     cudaEvent_t ev_mark[RING][MAX_MARKS] = {};
     const char *mark_name[RING][MAX_MARKS] = {};
     int n_marks[RING] = {};
@@ -128,7 +128,8 @@ struct S3RRenderer {
     uint64_t launches = 0;
     int opt_tma = 1, opt_pin_host = 0;   // pinning caller memory is opt-in: see pin_host()
     // staged host output (default path of s3r_render_host)
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_geometry = nullptr;
     static constexpr int MAX_SLICES = 64;
     cudaEvent_t ev_raster[MAX_SLICES] = {}, ev_copy[MAX_SLICES] = {};
     uint8_t *staging = nullptr;
@@ -167,6 +168,8 @@ extern "C" int s3r_create(S3RRenderer **out, int device) {
         for (int k = 0; k < S3RRenderer::MAX_MARKS; k++) { CUDA_TRY(cudaEventCreate(&r->ev_mark[i][k])); }
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&r->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&r->ev_geometry, cudaEventDisableTiming));
     for (int i = 0; i < S3RRenderer::MAX_SLICES; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&r->ev_raster[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&r->ev_copy[i], cudaEventDisableTiming));
@@ -207,6 +210,8 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
         if (r->ev_raster[i]) { cudaEventDestroy(r->ev_raster[i]); cudaEventDestroy(r->ev_copy[i]); }
     }
     if (r->copy_stream) { cudaStreamDestroy(r->copy_stream); }
+    if (r->aux_stream) { cudaStreamDestroy(r->aux_stream); }
+    if (r->ev_geometry) { cudaEventDestroy(r->ev_geometry); }
     for (int i = 0; i < S3RRenderer::RING; i++) {
         if (r->ev_cams[i]) { cudaEventDestroy(r->ev_cams[i]); cudaEventDestroy(r->ev_t0[i]); cudaEventDestroy(r->ev_t1[i]); cudaEventDestroy(r->ev_t2[i]); }
         for (int k = 0; k < S3RRenderer::MAX_MARKS; k++) { if (r->ev_mark[i][k]) { cudaEventDestroy(r->ev_mark[i][k]); } }
@@ -627,11 +632,20 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         int rc2 = retire_timed_slot(r, slot);
         if (rc2) { return rc2; }
     }
-    float *staging = r->cams_pinned + (size_t)slot * r->cams_pinned_views * 12;
-    memcpy(staging, cams, (size_t)n_views * 12 * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(r->cams.p, staging, (size_t)n_views * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));
-    r->slot_used[slot] = true;
+    if (n_views == 1) {
+        // one view: the matrix travels in the kernels' parameter block (an H2D copy in front of the first kernel costs
+        // more than the kernel launch itself)
+        memcpy(f.cam0, cams, 12 * sizeof(float));
+        f.cam_inline = 1;
+        CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));   // (keeps the ring's retire logic uniform; an event record is not a copy)
+        r->slot_used[slot] = true;
+    } else {
+        float *staging = r->cams_pinned + (size_t)slot * r->cams_pinned_views * 12;
+        memcpy(staging, cams, (size_t)n_views * 12 * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(r->cams.p, staging, (size_t)n_views * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));
+        r->slot_used[slot] = true;
+    }
     const bool timed = r->opt_timing != 0;
     MarkCtx mark_ctx{r, slot, s};
     const LaunchMarks marks{mark_kernel, &mark_ctx};
@@ -713,11 +727,16 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         f.rowtab = r->rowtab.p; f.rowbase = r->rowbase.p;
     }
     r->launches += (uint64_t)(f.direct_bin ? launch_geometry_small(f, s, mk) : launch_geometry(f, s, mk));
-    if (r->sticky_host) {  // overflow record of this submission, read back without an extra sync
-        CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, s));
+    if (r->sticky_host) {
+        // overflow record of this submission, read back on a side stream behind the geometry kernels: a 16-byte copy IN the
+        // rendering stream would sit between post_setup and the raster kernels (10 us of every frame)
+        CUDA_TRY(cudaEventRecord(r->ev_geometry, s));
+        CUDA_TRY(cudaStreamWaitEvent(r->aux_stream, r->ev_geometry, 0));
+        CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, r->aux_stream));
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
-    const int nb = f.direct_bin ? std::max(1, std::min<int>(raster_bands, (int)f.tiles_y)) : 1;   // the general path's tile queue spans the frame
+    // (general path: the tile kernel runs with the first band over the whole frame, the bands cut the shading pass)
+    const int nb = std::max(1, std::min<int>(raster_bands, (int)f.tiles_y));
     uint32_t edge[S3RRenderer::MAX_SLICES + 1];
     const int n_edges = band_edges(f.tiles_y, nb, r->opt_band_taper && after_band, edge);
     for (int b = 0; b + 1 < n_edges; b++) {
@@ -793,6 +812,7 @@ extern "C" int s3r_render_device_rows(S3RRenderer *r, const float *cams, uint32_
 static int finish_on(S3RRenderer *r, cudaStream_t s) {
     CUDA_TRY(cudaSetDevice(r->device));
     CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(r->aux_stream));   // the overflow record's copy
     if (r->last_views == 0 || !r->sticky.p) { return S3R_OK; }
     uint32_t sticky[4];
     memcpy(sticky, r->sticky_host, sizeof(sticky));   // copied after the geometry of the last submission; the sync above covers it
@@ -899,8 +919,8 @@ extern "C" int s3r_render_host(S3RRenderer *r, const float *cams, uint32_t n_vie
         for (int attempt = 0; attempt < 8 && !rendered; attempt++) {
             // ---- enqueue: geometry, banded raster, one D2H per band/slice on the copy stream -----
             uint32_t band_rows[S3RRenderer::MAX_SLICES] = {};
-            // band-pipelined raster/copy for the tile-kernel path only (see render_chunk)
-            const int bands = nv == 1 && uses_direct_bin(r) ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
+            // band-pipelined raster (small scenes) or shading (general path) and copy: band k crosses PCIe while band k + 1 renders
+            const int bands = nv == 1 ? std::max(1, std::min(r->opt_host_bands, S3RRenderer::MAX_SLICES)) : 1;
             std::vector<CopySlice> slices;
             uint8_t *target = pinned ? reinterpret_cast<uint8_t *>(dst) : r->staging;
             if (pinned) { plant_sentinels(dst, view_px * nv); }

@@ -5,14 +5,15 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import numpy as np, torch
 from swift3drenderer_b200 import renderer as R, scene as S
 
+import bench
 n_solids = int(os.environ.get("C3_SOLIDS", "1000000"))
-path = f"/dev/shm/s3r_c3_{n_solids}.data.bin"
-if not os.path.exists(path):
-    S.write_data_bin(path, S.c3_scene(n_solids))
+path = bench.c3_data_bin(n_solids)   # the bench's own scene file (generated once per box)
 r = R.Renderer(0)
 r.load_scene_file(path)
-inp = np.zeros(4, S.INPUT_DTYPE)
-mats = R.camera_path(inp)
+mats = R.camera_path(bench.drift_inputs(4))
+for opt in os.environ.get("S3R_OPTS", "").split(","):   # e.g. S3R_OPTS=clusters=0,cluster_cull=0
+    if "=" in opt:
+        r.set_option(opt.split("=")[0], int(opt.split("=")[1]))
 W, H = 3840, 2160
 world, phase = int(os.environ.get("C3_WORLD", "8")), int(os.environ.get("C3_PHASE", "3"))
 rows, _, _ = R.rows_layout(H, world, phase)
