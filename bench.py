@@ -12,7 +12,8 @@ drift path.  One *step* = those 8 frames, one pose per launch set.
   value    assembled frames/s, device-resident, CUDA-event timed on the launching stream, max over ranks.
   e2e      the same poses through the reference-facing plugin call updateAndRender(const PixelData*, const Input*)
            on a private render.so beside C3's data.bin with the caller's pageable double buffer (host camera step,
-           48 B H2D, render, D2H of the frame inside the timed region).  N > 1: one replica per rank on its own GPU.
+           48 B H2D, render, D2H of the frame inside the timed region).  N > 1: ONE caller (rank 0) whose updateAndRender
+           drives all N GPUs from one process (S3R_DEVICES; every GPU copies its rows over its own PCIe link).
   roofline per kernel from CUDA events recorded after every launch of the timed region (option "timing") and for the
            frame (B_alg = 12V + 28A + 8I + 4WH); `traffic` from the committed ncu capture.
   cpu_baseline / --impl reference: the reference's own render.cpp (oracle/_ref, compiled unmodified; falls back to the C
@@ -560,40 +561,19 @@ def main():
     frame0 = frame_digest(r.render(mats[0], W, H)[0])
     stats_last = r.stats(0)
 
-    # ---- e2e: the reference-facing plugin call with host buffers, this rank's replica on this rank's GPU -----------
+    # ---- e2e: the reference-facing plugin call with host buffers ------------------------------------------------------
+    # N = 1: the drop-in on this GPU.  N > 1: ONE caller (rank 0) whose updateAndRender drives all N GPUs from one process
+    # (S3R_DEVICES: interleaved tile rows, every GPU copies its rows over its own PCIe link into the caller's buffer); the
+    # other ranks wait on a host-side (gloo) barrier so that nothing of theirs runs on the GPUs meanwhile.
     e2e = None
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
     if not args.no_e2e:
-        t0 = time.perf_counter()
-        d = R.DropIn(data_bin)
-        double = np.zeros((2, H, W), np.uint32)   # pageable, alternated per call like main.swift:117-118
-        d.update_and_render(W, H, inputs[0], out=double[0])   # scene load
-        e2e_frame0 = frame_digest(double[0])
-        for f in range(1, 2 * POSES):   # warm: capacity growth, staging buffers, copy workers
-            d.update_and_render(W, H, inputs[f % POSES], out=double[f & 1])
-        log(f"rank {rank}: drop-in ready in {time.perf_counter() - t0:.1f} s")
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            d.reset_camera()
-            for f in range(POSES):
-                d.update_and_render(W, H, inputs[f], out=double[f & 1])
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * frames_total / dt, "unit": UNIT, "h2d_bytes_per_step": 48 * POSES * world,
-               "d2h_bytes_per_step": 3 * W * H * POSES * world,
-               "mode": "one frame per call on one GPU" if world == 1 else
-                       f"{world} independent updateAndRender replicas, one per rank, each on its own GPU (S3R_DEVICE = LOCAL_RANK); "
-                       "the screen partition is what `value` measures",
-               "call": "updateAndRender(const PixelData*, const Input*) on a private render.so beside C3's data.bin; caller's buffer is a "
-                       "pageable double buffer (not registered: S3R_PIN_HOST unset); transport = frame shaded in row bands, each band "
-                       "copied D2H as 24-bit pixels into the library's pinned staging while the next is shaded, copy workers expand "
-                       "it into the caller's buffer; synchronous per frame",
-               "frame0_digest": e2e_frame0, "frame0_equals_device_path": e2e_frame0 == frame0}
-        d.close()
+        e2e = run_e2e(R, data_bin, inputs, POSES, args.steps, W, H, rank, world, frame0, host_group, barrier)
 
     # ---- secondary record: C2 (data.bin demo scene, 600-frame fly-through), frame-parallel ------------------------
     secondary = None
     if not args.no_secondary:
-        secondary = run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks)
+        secondary = run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks, host_group)
 
     if rank != 0:
         if world > 1:
@@ -660,7 +640,47 @@ def main():
         dist.destroy_process_group()
 
 
-def run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks):
+def run_e2e(R, data_bin, inputs, frames, steps, W, H, rank, world, frame0, host_group, barrier, warm_frames=None):
+    """frames/s through updateAndRender with the caller's pageable double buffer (main.swift:117-118), `steps` passes over
+    `frames` Inputs.  Returns the e2e record on rank 0 (None elsewhere)."""
+    import torch.distributed as dist
+    rec = None
+    barrier()
+    if rank == 0:
+        t0 = time.perf_counter()
+        d = R.DropIn(data_bin, devices=",".join(str(k) for k in range(world)) if world > 1 else None)
+        double = np.zeros((2, H, W), np.uint32)   # pageable, alternated per call
+        d.update_and_render(W, H, inputs[0], out=double[0])   # scene load (on every GPU)
+        first = frame_digest(double[0])
+        for f in range(1, warm_frames or 2 * frames):   # warm: capacity growth, staging / registration, worker threads
+            d.update_and_render(W, H, inputs[f % frames], out=double[f & 1])
+        log(f"drop-in on {d.n_devices} GPU(s) ready in {time.perf_counter() - t0:.1f} s")
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d.reset_camera()
+            for f in range(frames):
+                d.update_and_render(W, H, inputs[f], out=double[f & 1])
+        dt = time.perf_counter() - t0
+        multi = d.n_devices > 1
+        rec = {"value": steps * frames / dt, "unit": UNIT, "h2d_bytes_per_step": 48 * frames,
+               "d2h_bytes_per_step": (4 if multi else 3) * W * H * frames, "gpus": d.n_devices,
+               "call": "updateAndRender(const PixelData*, const Input*) on a private render.so beside the scene's data.bin, caller's "
+                       "pageable double buffer, synchronous per frame; " +
+                       ("one process drives all GPUs (S3R_DEVICES): interleaved tile rows, one host thread per GPU, each GPU "
+                        "copies its rows D2H over its own PCIe link straight into the caller's buffer (registered on first sight, "
+                        "sentinel-checked)" if multi else
+                        "not registered (S3R_PIN_HOST unset): the frame is rendered in row bands, each band copied D2H as 24-bit "
+                        "pixels into the library's pinned staging while the next renders, copy workers expand it into the "
+                        "caller's buffer"),
+               "first_frame_digest": first, "first_frame_equals_device_path": (first == frame0) if frame0 else None,
+               "last_frame_digest": frame_digest(double[(frames - 1) & 1])}
+        d.close()
+    if world > 1:
+        dist.barrier(group=host_group)
+    return rec
+
+
+def run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_ranks, host_group):
     """The secondary record: BASELINE.json configs[1] — the demo scene at 4K over the recorded fly-through; every rank renders
     the full fly-through (frame-parallel replicas, no data-path collective)."""
     import torch
@@ -708,24 +728,7 @@ def run_c2(args, r, rank, local_rank, world, dev, stream, barrier, max_over_rank
 
     e2e = None
     if not args.no_e2e:
-        d = R.DropIn(data_bin)
-        double = np.zeros((2, H, W), np.uint32)
-        for f in range(12):
-            d.update_and_render(W, H, inp[f], out=double[f & 1])
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            d.reset_camera()
-            for f in range(F):
-                d.update_and_render(W, H, inp[f], out=double[f & 1])
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * steps * F / dt, "unit": UNIT, "h2d_bytes_per_step": 48 * F * world,
-               "d2h_bytes_per_step": 3 * W * H * F * world,
-               "last_frame_digest": frame_digest(double[(F - 1) & 1]),
-               "call": "updateAndRender on a private render.so beside the demo data.bin, pageable double buffer (not registered), "
-                       "12 row bands rasterised and copied D2H as 24-bit pixels into pinned staging, copy workers expand into the "
-                       "caller's buffer; one replica per rank on its own GPU"}
-        d.close()
+        e2e = run_e2e(R, data_bin, inp, F, steps, W, H, rank, world, None, host_group, barrier, warm_frames=12)
     r2.close()
     if rank != 0:
         return None

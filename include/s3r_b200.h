@@ -207,6 +207,12 @@ S3R_API int s3r_debug_band_edges(uint32_t tiles_y, int bands, int taper, uint32_
 /* Harness-only: resets the camera owned by updateAndRender (include/render.h) to the reference's
  * initial state so that the same Input script can be replayed; scene and buffers stay loaded. */
 S3R_API void s3r_dropin_reset(void);
+/* Harness-only: the number of GPUs updateAndRender renders on (0 before its first call).  More than one when the
+ * environment names several at the first call — S3R_DEVICES="0,1,2,3" or "all": the frame is then split by interleaved
+ * tile rows, one host thread per GPU issues that GPU's launches, and every GPU copies its rows over its own PCIe link
+ * straight into the caller's buffer (registered on first sight; S3R_PIN_HOST=0: through pinned staging).  The call stays
+ * synchronous and its result bit-identical.  S3R_DEVICE=<k> selects the GPU of the single-GPU drop-in. */
+S3R_API int s3r_dropin_devices(void);
 
 #ifdef __cplusplus
 }

@@ -170,6 +170,30 @@ void build_clusters(const float *px, const float *py, const float *pz, const uin
             out.tri[tri_off++] = local[0] | (local[1] << 8) | (local[2] << 16) | (slot << 24);
         }
     }
+    // batch bounds: a sphere around the spheres of the batch's clusters (a whole batch that misses the view costs 16 bytes)
+    const size_t n_batches = (raw.size() + CL_BATCH - 1) / CL_BATCH;
+    out.batch.assign(4 * n_batches, 0.f);
+    for (size_t b = 0; b < n_batches; b++) {
+        const size_t k0 = b * CL_BATCH, k1 = std::min(raw.size(), k0 + CL_BATCH);
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        bool finite = true;
+        for (size_t k = k0; k < k1; k++) {
+            const ClusterHeader &h = out.hdr[k];
+            finite = finite && std::isfinite(h.radius);
+            const double c[3] = {h.cx, h.cy, h.cz};
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[a] - h.radius); hi[a] = std::max(hi[a], c[a] + h.radius); }
+        }
+        float *o = &out.batch[4 * b];
+        if (!finite) { o[0] = o[1] = o[2] = 0.f; o[3] = INFINITY; continue; }   // never rejected
+        const float c[3] = {(float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2]))};
+        double r = 0;
+        for (size_t k = k0; k < k1; k++) {
+            const ClusterHeader &h = out.hdr[k];
+            const double dx = (double)h.cx - c[0], dy = (double)h.cy - c[1], dz = (double)h.cz - c[2];
+            r = std::max(r, sqrt(dx * dx + dy * dy + dz * dz) + (double)h.radius);
+        }
+        o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = round_up(r * (1.0 + 1e-9));
+    }
     ClusterHeader &end = out.hdr[raw.size()];
     memset(&end, 0, sizeof(end));
     end.v_off = (uint32_t)out.px.size(); end.tri_off = tri_off; end.t0 = (uint32_t)T;

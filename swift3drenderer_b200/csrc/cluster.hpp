@@ -35,6 +35,7 @@ struct ClusterSet {
     std::vector<float> px, py, pz;       // cluster-private vertex copies, in cluster order
     std::vector<uint8_t> vslot;          // per cluster vertex: its cluster's slot within the batch (0 .. CL_BATCH - 1)
     std::vector<uint32_t> tri;           // v0 | v1 << 8 | v2 << 16 | slot << 24 (cluster-local vertex numbers)
+    std::vector<float> batch;            // per batch of CL_BATCH clusters: {cx, cy, cz, radius} enclosing its clusters' spheres
     uint32_t n_clusters = 0;
 };
 

@@ -576,7 +576,7 @@ struct WalkShared {
     uint32_t tri[256];                 // order key of the box's triangle
     uint16_t items[256 * SMALL_MAX];   // parked slot | row << 8, grouped by box-width class
     uint32_t n_cand;
-    uint32_t cls_count[4];             // row items per box-width class (width 1-4, 5-8, 9-12, 13-16 pixels)
+    uint32_t cls_count[SMALL_MAX];     // row items per box width (1 .. 16 pixels): a warp's items are equally wide
     uint32_t stats[4];                 // near-rejected, clipped, walked here, culled
     uint32_t work_base;
 };
@@ -613,7 +613,7 @@ __device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, W
     const uint32_t tid = threadIdx.x, lane = lane_id();
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
     for (uint32_t cbase = 0; cbase < n_cand; cbase += 256u) {
-        if (tid < 4) { wsh.cls_count[tid] = 0; }
+        if (tid < SMALL_MAX) { wsh.cls_count[tid] = 0; }
         __syncthreads();
         uint32_t route = 0;   // 1 work item for K2b, 3 walked here
         uint32_t item = 0, my_cls = 0, my_rows = 0, my_off = 0;
@@ -657,7 +657,7 @@ __device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, W
                             if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
                         }
                         my_rows = rows;
-                        my_cls = (xmax - xmin) >> 2;
+                        my_cls = xmax - xmin;
                         my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(rows));
                     } else {
                         n.n_cull++;
@@ -677,9 +677,11 @@ __device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, W
             if (route == 1) { f.worklist[(size_t)view * f.T + base + __popc(m & ((1u << lane) - 1u))] = item; }
         }
         __syncthreads();
-        const uint32_t c0 = wsh.cls_count[0], c1 = wsh.cls_count[1], c2 = wsh.cls_count[2], n_items = c0 + c1 + c2 + wsh.cls_count[3];
+        uint32_t n_items = 0, cls_base = 0;   // items of narrower boxes come first
+#pragma unroll
+        for (uint32_t c = 0; c < SMALL_MAX; c++) { const uint32_t k = wsh.cls_count[c]; if (c < my_cls) { cls_base += k; } n_items += k; }
         if (route == 3) {
-            uint32_t pos = my_off + (my_cls > 0u ? c0 : 0u) + (my_cls > 1u ? c1 : 0u) + (my_cls > 2u ? c2 : 0u);
+            uint32_t pos = my_off + cls_base;
             while (my_rows) {   // one work item per owned box row
                 const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
                 my_rows &= my_rows - 1u;
@@ -701,11 +703,18 @@ __device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, W
             unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
             const unsigned long long key_lo = (unsigned long long)(~wsh.tri[ow]);
             const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
-            for (uint32_t x = 0; x <= bw; x++) {
-                const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+            // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
+            // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
+            // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
+            uint32_t x = 0;
+            while (x <= bw && !(w0 >= 0 && w1 >= 0 && w2 >= 0)) {
+                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);
+                x++;
+            }
+            for (; x <= bw && (w0 >= 0 && w1 >= 0 && w2 >= 0); x++) {
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                if (ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
@@ -787,31 +796,54 @@ struct FrontShared {
     float4 rv[CL_BATCH * CL_MAX_VERTS];      // raster-space vertices of the batch's surviving clusters
     WalkShared w;
     uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // position in the batch | 0x8000 for a straddler
-    uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in rv[], CL_DEAD = cluster skipped
+    uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in the cluster-vertex arrays, CL_DEAD = cluster skipped
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
+    uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
+    uint32_t batch, first_alive, last_alive;
 };
 static_assert(CL_BATCH * CL_MAX_TRIS <= 0x8000, "candidate entries are 15-bit positions plus the straddle flag");
 static_assert(sizeof(FrontShared) <= 55 * 1024, "FrontShared must leave room for four CTAs per SM");
 
-// 0: process per triangle; 1: every triangle near-rejected; 2: every triangle culled (off screen / not ours / too small)
-__device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &cam, float cx, float cy, float cz, float radius, float max_edge) {
+// What the rejection tests need from the view's matrix: the norms of its rows and a bound of its largest singular value
+// (Gershgorin on the Gram matrix; 1 for a camera's orthonormal rows).
+struct ViewBounds { float norm[3], sigma; };
+
+__device__ __forceinline__ ViewBounds view_bounds(const Cam &cam) {
+    ViewBounds vb;
+    float gram = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float m0 = cam.m[4 * i], m1 = cam.m[4 * i + 1], m2 = cam.m[4 * i + 2];
+        vb.norm[i] = sqrtf(m0 * m0 + m1 * m1 + m2 * m2) * 1.000001f;
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { row += fabsf(m0 * cam.m[4 * j] + m1 * cam.m[4 * j + 1] + m2 * cam.m[4 * j + 2]); }
+        gram = fmaxf(gram, row);
+    }
+    vb.sigma = sqrtf(gram) * 1.000001f;
+    return vb;
+}
+
+// Conservative verdict on a bounding sphere (centre, radius) whose triangles have no edge longer than max_edge:
+// 0: process per triangle; 1: every triangle near-rejected; 2: every triangle culled (off screen / not ours / too small).
+// Every comparison is written so that NaN / infinite bounds end in 0.
+__device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &cam, const ViewBounds &vb, float cx, float cy, float cz,
+                                                    float radius, float max_edge) {
     const float3 cc = xform(cam, cx, cy, cz, 1.0f);
     const float ax = fabsf(cx) + radius, ay = fabsf(cy) + radius, az = fabsf(cz) + radius;
     float rho[3], err = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const float m0 = cam.m[4 * i], m1 = cam.m[4 * i + 1], m2 = cam.m[4 * i + 2], m3 = cam.m[4 * i + 3];
-        // |binary32 transform - exact transform| of any point of the cluster: four products and three sums, each within
+        // |binary32 transform - exact transform| of any point of the sphere: four products and three sums, each within
         // 2^-24 of the running magnitude; 2^-21 of the summed magnitudes is more than twice that
-        const float e = 0x1p-21f * (fabsf(m0) * ax + fabsf(m1) * ay + fabsf(m2) * az + fabsf(m3));
-        const float norm = sqrtf(m0 * m0 + m1 * m1 + m2 * m2) * 1.000001f;
+        const float e = 0x1p-21f * (fabsf(cam.m[4 * i]) * ax + fabsf(cam.m[4 * i + 1]) * ay + fabsf(cam.m[4 * i + 2]) * az + fabsf(cam.m[4 * i + 3]));
         // every vertex's computed camera-space coordinate i lies within rho[i] of the computed centre's
-        rho[i] = (norm * radius + 2.f * e) * 1.000001f + 1e-30f;
+        rho[i] = (vb.norm[i] * radius + 2.f * e) * 1.000001f + 1e-30f;
         err = fmaxf(err, e);
     }
     const float d = -cc.z, d_min = d - rho[2], d_max = d + rho[2];
     // near reject (render.cpp:306): every vertex has rv.z = -cv.z <= near.  -cv.z == 0 makes rv.z NaN in the reference's
-    // expression (0 / 0), so only clusters strictly behind the eye plane or strictly between it and the near plane count.
+    // expression (0 / 0), so only spheres strictly behind the eye plane or strictly between it and the near plane count.
     if (d_max < 0.f || (d_min > 0.f && d_max <= kNear)) { return 1u; }
     if (!(d_min > kNear * 1.000001f)) { return 0u; }   // may touch the near plane (or bounds are not finite): per triangle
     // every vertex strictly in front: raster coordinates by interval arithmetic over the box [cc - rho, cc + rho]
@@ -824,29 +856,46 @@ __device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &c
     const float sx_hi = qx_hi + f.half_w + sx, sx_lo = qx_lo + f.half_w - sx, sy_hi = qy_hi + f.half_h + sy, sy_lo = qy_lo + f.half_h - sy;
     // off screen / outside the band (render.cpp:311-314 and the partition's row range)
     if (sx_hi < 0.f || sy_hi < f.band_lo || sx_lo >= f.fw || sy_lo >= f.band_hi) { return 2u; }
-    if (f.row_stride != 1u) {   // interleaved tile rows: does the cluster reach a row this submission owns?
+    if (f.row_stride != 1u) {   // interleaved tile rows: does the sphere reach a row this submission owns?
         const uint32_t ylo = (uint32_t)fmaxf(0.f, floorf(sy_lo)), yhi = (uint32_t)fminf(f.fh - 1.f, sy_hi);
         if (ylo > yhi || owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) == 0u) { return 2u; }
     }
     // too small (render.cpp:316-317): |area| <= product of two projected edges.  A camera-space segment of length L at
     // depth >= d_min whose endpoints project at tangents (tu, tv) is at most factor / d_min * L * sqrt(1 + tu^2 + tv^2)
-    // pixels long.  L: the longest object-space edge through the matrix (largest singular value bounded by Gershgorin on
-    // the Gram matrix; 1 for a camera's orthonormal rows) plus the endpoints' rounding.
-    float gram = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        float row = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            row += fabsf(cam.m[4 * i] * cam.m[4 * j] + cam.m[4 * i + 1] * cam.m[4 * j + 1] + cam.m[4 * i + 2] * cam.m[4 * j + 2]);
-        }
-        gram = fmaxf(gram, row);
-    }
-    const float len = sqrtf(gram) * 1.000001f * max_edge + 4.f * err;
+    // pixels long.  L: the longest object-space edge through the matrix plus the endpoints' rounding.
+    const float len = vb.sigma * max_edge + 4.f * err;
     const float tu = fmaxf(fabsf(x_lo), fabsf(x_hi)) / d_min, tv = fmaxf(fabsf(y_lo), fabsf(y_hi)) / d_min;
     const float pixels = inv_min * len * sqrtf(1.f + tu * tu + tv * tv) * 1.00001f + 2.f * (sx + sy);
     if (pixels <= 3.09f) { return 2u; }   // (3.09 + rounding)^2 < 10
     return 0u;
+}
+
+// Batch-level rejection: one thread per batch of CL_BATCH clusters tests the sphere around the batch's spheres.  Batches
+// that may show something are appended to the front kernel's work list; the triangles of the others are accounted for here
+// (near-rejected or culled, exactly what the reference's per-triangle tests would have said).  On a screen partition most
+// batches miss a rank's rows: they cost 16 bytes each.
+__global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame f) {
+    const uint32_t view = blockIdx.y, b = blockIdx.x * 256u + threadIdx.x, lane = lane_id();
+    const Cam cam = load_cam(f, view);
+    const ViewBounds vb = view_bounds(cam);
+    uint32_t verdict = 3u, n_tris = 0;   // 3: no batch
+    if (b < f.n_batches) {
+        const float4 h = __ldg(f.cl_batch + b);
+        const uint32_t c0 = b * CL_BATCH, c1 = min(c0 + CL_BATCH, f.n_clusters);
+        n_tris = __ldg(f.cl_hdr + 2 * (size_t)c1 + 1).w - __ldg(f.cl_hdr + 2 * (size_t)c0 + 1).w;
+        verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, h.x, h.y, h.z, h.w, INFINITY) : 0u;
+    }
+    uint32_t *c = f.counters + view * C_COUNT;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
+    uint32_t pos = 0;
+    if (lane == 0 && m) { pos = atomicAdd(c + C_BATCHES, __popc(m)); }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (verdict == 0u) { f.batch_list[(size_t)view * f.n_batches + pos + __popc(m & ((1u << lane) - 1u))] = b; }
+    const uint32_t near = __reduce_add_sync(0xFFFFFFFFu, verdict == 1u ? n_tris : 0u), cull = __reduce_add_sync(0xFFFFFFFFu, verdict == 2u ? n_tris : 0u);
+    if (lane == 0) {
+        if (near) { atomicAdd(c + C_NEAR, near); }
+        if (cull) { atomicAdd(c + C_CULLED, cull); }
+    }
 }
 
 __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ Frame f) {
@@ -854,65 +903,112 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
     FrontShared &sh = *reinterpret_cast<FrontShared *>(smem_raw);
     WalkShared &wsh = sh.w;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
-    const uint32_t c0 = blockIdx.x * CL_BATCH, nc = min(CL_BATCH, f.n_clusters - c0);
     const Cam cam = load_cam(f, view);
-    if (tid == 0) { wsh.n_cand = 0; }
+    const ViewBounds vb = view_bounds(cam);
+    uint32_t *counters = f.counters + view * C_COUNT;
+    const uint32_t n_alive = counters[C_BATCHES];   // written by batch_cull
     if (tid < 4) { wsh.stats[tid] = 0; }
     FrontCounts n = {0u, 0u, 0u, 0u};
-    const uint4 first = __ldg(f.cl_hdr + 2 * (size_t)c0 + 1), last = __ldg(f.cl_hdr + 2 * (size_t)(c0 + nc) + 1);
-    const uint32_t v_begin = first.z, v_end = last.z, t_begin = first.w, t_end = last.w;
 
-    // ---- 1. cluster verdicts ---------------------------------------------------------------------------------------
-    if (tid < CL_BATCH) {
-        uint32_t base = CL_DEAD, delta = 0;
-        if (tid < nc) {
-            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid)), h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
-            const uint32_t n_tris = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w - h1.w;
-            const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
-                                                                      __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
-            if (verdict == 0u) { base = h1.z - v_begin; }
-            else if (verdict == 1u) { n.n_near += n_tris; }
-            else { n.n_cull += n_tris; }
-            delta = h1.y - h1.w;   // t0 - tri_off (mod 2^32)
+    // persistent CTAs: batches are handed out by a counter
+    while (true) {
+        __syncthreads();   // the previous batch's shared-memory state is dead
+        if (tid == 0) {
+            const uint32_t i = atomicAdd(counters + C_BHEAD, 1u);
+            sh.batch = i < n_alive ? f.batch_list[(size_t)view * f.n_batches + i] : CL_DEAD;
+            wsh.n_cand = 0; sh.first_alive = CL_BATCH; sh.last_alive = 0;
         }
-        sh.ctab[tid] = base; sh.cdelta[tid] = delta;
-    }
-    __syncthreads();
+        __syncthreads();
+        if (sh.batch == CL_DEAD) { break; }
+        const uint32_t c0 = sh.batch * CL_BATCH, nc = min(CL_BATCH, f.n_clusters - c0);
 
-    // ---- 2. vertex stage of the surviving clusters, into shared memory --------------------------------------------------
-    for (uint32_t j = v_begin + tid; j < v_end; j += 256u) {
-        const uint32_t base = sh.ctab[__ldg(f.cl_vslot + j)];
-        if (base != CL_DEAD) {
-            const float3 cv = xform(cam, __ldg(f.cl_px + j), __ldg(f.cl_py + j), __ldg(f.cl_pz + j), 1.0f);
-            const float3 r = project(cv, f.factor, f.half_w, f.half_h);
-            sh.rv[j - v_begin] = make_float4(r.x, r.y, r.z, 0.f);
+        // ---- 1. cluster verdicts -----------------------------------------------------------------------------------
+        if (tid <= CL_BATCH) {
+            uint32_t alive = 0;
+            if (tid <= nc) {
+                const uint4 h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
+                sh.voff[tid] = h1.z; sh.toff[tid] = h1.w;
+                if (tid < nc) {
+                    const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid));
+                    const uint32_t n_tris = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w - h1.w;
+                    const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
+                                                                              __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+                    if (verdict == 0u) { alive = 1; }
+                    else if (verdict == 1u) { n.n_near += n_tris; }
+                    else { n.n_cull += n_tris; }
+                    sh.ctab[tid] = alive ? h1.z : CL_DEAD;
+                    sh.cdelta[tid] = h1.y - h1.w;   // t0 - tri_off (mod 2^32)
+                }
+            }
+            if (tid < CL_BATCH) {   // (warps 0 and 1: the alive clusters' slot range)
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive != 0u);
+                if (lane == 0 && m) {
+                    atomicMin(&sh.first_alive, (tid & ~31u) + (uint32_t)__ffs((int)m) - 1u);
+                    atomicMax(&sh.last_alive, (tid & ~31u) + 31u - (uint32_t)__clz((int)m));
+                }
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
+        if (sh.first_alive == CL_BATCH) { continue; }   // nothing of this batch survives
+        // only the span of the surviving clusters is streamed
+        const uint32_t v_begin = sh.voff[sh.first_alive], v_end = sh.voff[sh.last_alive + 1u];
+        const uint32_t t_begin = sh.toff[sh.first_alive], t_end = sh.toff[sh.last_alive + 1u];
 
-    // ---- 3. front tests, one thread per triangle word --------------------------------------------------------------------
-    for (uint32_t jb = t_begin; jb < t_end; jb += 256u) {
-        const uint32_t j = jb + tid;
-        uint32_t cand = 0;
-        if (j < t_end) {
-            const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
-            if (base != CL_DEAD) { cand = front_test(f, sh.rv[base + (w & 255u)], sh.rv[base + ((w >> 8) & 255u)], sh.rv[base + ((w >> 16) & 255u)], n); }
+        // ---- 2. vertex stage of the surviving clusters, into shared memory (loads first, then arithmetic) --------------
+        {
+            constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256;
+            float px[VU], py[VU], pz[VU];
+            bool live[VU];
+#pragma unroll
+            for (int k = 0; k < VU; k++) {
+                const uint32_t j = v_begin + tid + 256u * k;
+                live[k] = j < v_end && sh.ctab[__ldg(f.cl_vslot + j)] != CL_DEAD;
+                if (live[k]) { px[k] = __ldg(f.cl_px + j); py[k] = __ldg(f.cl_py + j); pz[k] = __ldg(f.cl_pz + j); }
+            }
+#pragma unroll
+            for (int k = 0; k < VU; k++) {
+                if (live[k]) {
+                    const float3 r = project(xform(cam, px[k], py[k], pz[k], 1.0f), f.factor, f.half_w, f.half_h);
+                    sh.rv[tid + 256u * k] = make_float4(r.x, r.y, r.z, 0.f);
+                }
+            }
         }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
-        uint32_t pos = 0;
-        if (lane == 0 && m) { pos = atomicAdd(&wsh.n_cand, __popc(m)); }
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (cand) { sh.cand[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((j - t_begin) | (cand == 2 ? 0x8000u : 0u)); }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- 4. candidates: coverage setup + direct walk ---------------------------------------------------------------------
-    walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
-        const uint32_t e = sh.cand[i], j = t_begin + (e & 0x7FFFu);
-        const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, base = sh.ctab[slot];
-        item = (j + sh.cdelta[slot]) | ((e & 0x8000u) ? ITEM_STRADDLE : 0u);   // the original triangle index is the order key
-        r0 = sh.rv[base + (w & 255u)]; r1 = sh.rv[base + ((w >> 8) & 255u)]; r2 = sh.rv[base + ((w >> 16) & 255u)];
-    });
+        // ---- 3. front tests, one thread per triangle word (four words in flight per thread) ------------------------------
+        for (uint32_t jb = t_begin; jb < t_end; jb += 1024u) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t j = jb + 256u * k + tid; w[k] = j < t_end ? __ldg(f.cl_tri + j) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t j = jb + 256u * k + tid;
+                if (jb + 256u * k >= t_end) { break; }   // (uniform)
+                uint32_t cand = 0;
+                if (j < t_end) {
+                    const uint32_t base = sh.ctab[w[k] >> 24];
+                    if (base != CL_DEAD) {
+                        const uint32_t o = base - v_begin;
+                        cand = front_test(f, sh.rv[o + (w[k] & 255u)], sh.rv[o + ((w[k] >> 8) & 255u)], sh.rv[o + ((w[k] >> 16) & 255u)], n);
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
+                uint32_t pos = 0;
+                if (lane == 0 && m) { pos = atomicAdd(&wsh.n_cand, __popc(m)); }
+                pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                if (cand) { sh.cand[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((j - t_begin) | (cand == 2 ? 0x8000u : 0u)); }
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. candidates: coverage setup + direct walk -----------------------------------------------------------------
+        walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
+            const uint32_t e = sh.cand[i], j = t_begin + (e & 0x7FFFu);
+            const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, o = sh.ctab[slot] - v_begin;
+            item = (j + sh.cdelta[slot]) | ((e & 0x8000u) ? ITEM_STRADDLE : 0u);   // the original triangle index is the order key
+            r0 = sh.rv[o + (w & 255u)]; r1 = sh.rv[o + ((w >> 8) & 255u)]; r2 = sh.rv[o + ((w >> 16) & 255u)];
+        });
+    }
     publish_front_counts(f, view, wsh, n);
 }
 
@@ -1978,7 +2074,8 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by two small memsets
         cudaMemsetAsync(f.counters, 0, (size_t)f.n_views * C_COUNT * sizeof(uint32_t), s);
         cudaMemsetAsync(f.tile_count, 0, (size_t)f.n_views * f.tile_stride * sizeof(uint32_t), s);
-        cluster_front<<<dim3(max(1u, ceil_div(f.n_clusters, CL_BATCH)), f.n_views), 256, sizeof(FrontShared), s>>>(f); launches++; mark(m, "cluster_front");
+        batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
+        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * 4u)), f.n_views), 256, sizeof(FrontShared), s>>>(f); launches++; mark(m, "cluster_front");
     } else {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
         triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");

@@ -65,7 +65,9 @@ enum Counter : uint32_t {
     C_ROWTAB = 15,   // general path: floats of row-start tables allocated so far (post_setup)
     C_FLATQ = 14,    // general path: rounds of the flat walk handed out so far (post_setup)
     C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
-    C_COUNT = 16
+    C_BATCHES = 16,  // cluster front: batches of clusters that survived the batch-level rejection (batch_cull)
+    C_BHEAD = 17,    // ... and how many of them the front kernel's persistent CTAs have taken
+    C_COUNT = 20
 };
 
 struct __align__(16) SetupVis {     // 64 bytes: everything the coverage/depth walk needs
@@ -103,7 +105,9 @@ struct Frame {
     const float *cl_px, *cl_py, *cl_pz;
     const uint8_t *cl_vslot;
     const uint32_t *cl_tri;
-    uint32_t n_clusters;
+    const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
+    uint32_t *batch_list;         // [views][n_batches] batches that survived batch_cull, in list order
+    uint32_t n_clusters, n_batches;
     int cluster_cull;             // 0: every cluster is processed per triangle (A/B and tests)
     // views
     const float *cams;  // n_views x 12

@@ -17,7 +17,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <exception>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <functional>
@@ -76,7 +79,9 @@ struct S3RRenderer {
     DevBuf<float> cl_px, cl_py, cl_pz;
     DevBuf<uint8_t> cl_vslot;
     DevBuf<uint32_t> cl_tri;
-    uint32_t n_clusters = 0;
+    DevBuf<float4> cl_batch;
+    DevBuf<uint32_t> batch_list;
+    uint32_t n_clusters = 0, n_batches = 0;
     int opt_clusters = 1, opt_cluster_cull = 1;
     Frame last_frame;   // parameter block of the last submission (raster-vertex dumps on the cluster path)
     // per-view scratch
@@ -197,7 +202,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release();
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -284,7 +289,10 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
         CUDA_TRY(cudaMemcpy(r->cl_pz.p, cs.pz.data(), cs.pz.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_vslot.p, cs.vslot.data(), cs.vslot.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_tri.p, cs.tri.data(), cs.tri.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(r->cl_batch.ensure(cs.batch.size() / 4));
+        CUDA_TRY(cudaMemcpy(r->cl_batch.p, cs.batch.data(), cs.batch.size() * 4, cudaMemcpyHostToDevice));
         r->n_clusters = cs.n_clusters;
+        r->n_batches = (uint32_t)(cs.batch.size() / 4);
     }
     CUDA_TRY(r->attr.ensure(at.size()));
     CUDA_TRY(cudaMemcpy(r->attr.p, at.data(), at.size() * sizeof(uint4), cudaMemcpyHostToDevice));
@@ -666,6 +674,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     if (!uses_direct_bin(r) && uses_clusters(r)) {
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
+        CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
+        f.cl_batch = r->cl_batch.p; f.batch_list = r->batch_list.p; f.n_batches = r->n_batches;
         f.rv = nullptr;
     }
     f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
@@ -1231,14 +1241,161 @@ S3RRenderer *g_renderer = nullptr;
 S3RCamera g_camera;
 uint32_t g_depth_bytes = 0;   // depth_buffer.buffer_size, render.cpp:67-73
 
-void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared object)
-    int device = 0;
-    if (const char *env = getenv("S3R_DEVICE")) { device = atoi(env); }
-    if (s3r_create(&g_renderer, device) != S3R_OK) {
-        fprintf(stderr, "render.so: %s\n", s3r_last_error());
-        exit(70);
+// ---- one process, several GPUs (env S3R_DEVICES="0,1,2,3" or "all") -----------------------------------------------
+// The frame is split by interleaved tile rows (tile row a belongs to GPU a mod n: an even share of the screen whatever
+// the scene looks like); every GPU holds the whole scene, skips the clusters that miss its rows, rasterises and shades
+// its rows into a compact device buffer and copies them — over its OWN PCIe link — to their place in the caller's
+// buffer.  One persistent host thread per GPU issues that GPU's launches and copies, so the n launch sequences run in
+// parallel; updateAndRender stays synchronous (it returns when every thread has finished the frame).
+// The caller's buffer is registered (cudaHostRegisterPortable) on first sight, as the reference's main loop keeps one
+// double buffer for its lifetime (main.swift:117-118,156-165); a registration that went stale is detected by sentinels
+// and the frame is then delivered through pinned staging (S3R_PIN_HOST=0 forces that path).
+struct MultiJob { const float *matrix; float factor; uint32_t W, H; uint32_t *host_out; bool pinned; };
+
+struct MultiGpu {
+    struct Worker {
+        S3RRenderer *r = nullptr;
+        std::thread th;
+        uint8_t *staging = nullptr;
+        size_t staging_bytes = 0;
+        int rc = 0;
+        std::string error;
+    };
+    std::vector<Worker> w;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> done{0};
+    bool stop = false;
+    MultiJob job{};
+    int pin = 1;
+    std::vector<HostPin> pins;
+};
+MultiGpu *g_multi = nullptr;
+
+int multi_worker_frame(MultiGpu *mg, int k) {
+    MultiGpu::Worker &me = mg->w[(size_t)k];
+    S3RRenderer *r = me.r;
+    const MultiJob &j = mg->job;
+    const uint32_t n = (uint32_t)mg->w.size(), tile_rows = (j.H + TILE_H - 1) / TILE_H;
+    if (tile_rows <= (uint32_t)k) { return S3R_OK; }   // fewer tile rows than GPUs: nothing for this one
+    const uint32_t owned = (tile_rows - (uint32_t)k + n - 1) / n;
+    const size_t compact_px = (size_t)j.W * owned * TILE_H;
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(r->frame.ensure(compact_px));
+    if (!j.pinned && me.staging_bytes < compact_px * 4) {
+        if (me.staging) { cudaFreeHost(me.staging); me.staging = nullptr; me.staging_bytes = 0; }
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&me.staging), compact_px * 4, cudaHostAllocPortable));
+        me.staging_bytes = compact_px * 4;
     }
-    if (const char *env = getenv("S3R_PIN_HOST")) { g_renderer->opt_pin_host = atoi(env) != 0; }
+    r->factor_override = j.factor;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int rc = render_chunk(r, j.matrix, 1, j.W, j.H, 0, j.H, r->frame.p, r->stream, 1, nullptr, false, n, (uint32_t)k);
+        if (rc) { return rc; }
+        r->last_views = 1; r->last_W = j.W; r->last_H = j.H; r->last_stream = r->stream;
+        for (uint32_t l = 0; l < owned; l++) {   // owned tile row l = frame tile row l * n + k: 32 contiguous pixel rows
+            const uint32_t y = (l * n + (uint32_t)k) * TILE_H, rows = std::min<uint32_t>(TILE_H, j.H - y);
+            const uint32_t *src = r->frame.p + (size_t)l * TILE_H * j.W;
+            void *dst = j.pinned ? static_cast<void *>(j.host_out + (size_t)y * j.W) : static_cast<void *>(me.staging + (size_t)l * TILE_H * j.W * 4);
+            CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)rows * j.W * 4, cudaMemcpyDeviceToHost, r->stream));
+        }
+        rc = finish_on(r, r->stream);   // waits for the launches and the copies; 1 = a capacity was regrown, render again
+        if (rc < 0) { return rc; }
+        if (rc == 0) {
+            if (!j.pinned) {
+                for (uint32_t l = 0; l < owned; l++) {
+                    const uint32_t y = (l * n + (uint32_t)k) * TILE_H, rows = std::min<uint32_t>(TILE_H, j.H - y);
+                    memcpy(j.host_out + (size_t)y * j.W, me.staging + (size_t)l * TILE_H * j.W * 4, (size_t)rows * j.W * 4);
+                }
+            }
+            return S3R_OK;
+        }
+    }
+    return fail(S3R_E_CUDA, "frame scratch still overflowing after 8 regrowths");
+}
+
+void multi_worker(MultiGpu *mg, int k) {
+    uint64_t seen = 0;
+    for (;;) {
+        // a short spin first (frames follow each other within microseconds in a render loop), then sleep
+        for (int spin = 0; spin < 4000 && mg->generation.load(std::memory_order_acquire) == seen; spin++) { __builtin_ia32_pause(); }
+        if (mg->generation.load(std::memory_order_acquire) == seen) {
+            std::unique_lock<std::mutex> g(mg->m);
+            mg->cv_go.wait(g, [&] { return mg->generation.load(std::memory_order_acquire) != seen; });
+        }
+        seen = mg->generation.load(std::memory_order_acquire);
+        if (mg->stop) { return; }
+        MultiGpu::Worker &me = mg->w[(size_t)k];
+        me.rc = multi_worker_frame(mg, k);
+        if (me.rc) { me.error = g_error; }
+        if (mg->done.fetch_add(1, std::memory_order_acq_rel) + 1 == (int)mg->w.size()) {
+            std::lock_guard<std::mutex> g(mg->m);
+            mg->cv_done.notify_one();
+        }
+    }
+}
+
+bool multi_pin(MultiGpu *mg, const void *ptr, size_t bytes) {
+    if (!mg->pin) { return false; }
+    for (auto &p : mg->pins) { if (p.ptr == ptr && p.bytes >= bytes) { return true; } }
+    for (size_t i = 0; i < mg->pins.size();) {   // a new buffer (or a resize): drop registrations that overlap it
+        const char *a = static_cast<const char *>(mg->pins[i].ptr), *b = static_cast<const char *>(ptr);
+        if (a < b + bytes && b < a + mg->pins[i].bytes) { cudaHostUnregister(const_cast<void *>(mg->pins[i].ptr)); mg->pins.erase(mg->pins.begin() + (long)i); }
+        else { i++; }
+    }
+    if (mg->pins.size() >= 8) { for (auto &p : mg->pins) { cudaHostUnregister(const_cast<void *>(p.ptr)); } mg->pins.clear(); }
+    if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    mg->pins.push_back(HostPin{ptr, bytes});
+    return true;
+}
+
+int multi_render(MultiGpu *mg, const float *matrix, float factor, uint32_t W, uint32_t H, uint32_t *host_out) {
+    if (W == 0 || H == 0 || W > 65535 || H > 65535) { return fail(S3R_E_ARG, "bad frame geometry"); }
+    const size_t px = (size_t)W * H;
+    for (int pass = 0; pass < 2; pass++) {
+        cudaSetDevice(mg->w[0].r->device);
+        const bool pinned = pass == 0 && multi_pin(mg, host_out, px * 4);
+        if (pinned) { plant_sentinels(host_out, px); }
+        mg->job = MultiJob{matrix, factor, W, H, host_out, pinned};
+        mg->done.store(0, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> g(mg->m);
+            mg->generation.fetch_add(1, std::memory_order_acq_rel);
+        }
+        mg->cv_go.notify_all();
+        for (int spin = 0; spin < 20000 && mg->done.load(std::memory_order_acquire) < (int)mg->w.size(); spin++) { __builtin_ia32_pause(); }
+        if (mg->done.load(std::memory_order_acquire) < (int)mg->w.size()) {
+            std::unique_lock<std::mutex> g(mg->m);
+            mg->cv_done.wait(g, [&] { return mg->done.load(std::memory_order_acquire) >= (int)mg->w.size(); });
+        }
+        for (auto &wk : mg->w) { if (wk.rc) { return fail(wk.rc, wk.error); } }
+        if (!pinned || sentinels_gone(host_out, px)) { return S3R_OK; }
+        // the DMA went to pages the CPU no longer sees (a registration outlived its allocation): drop every pin, go again through staging
+        for (auto &p : mg->pins) { cudaHostUnregister(const_cast<void *>(p.ptr)); }
+        mg->pins.clear();
+        mg->pin = 0;
+    }
+    return S3R_OK;
+}
+
+std::vector<int> drop_in_devices() {   // S3R_DEVICES: "all" or a comma-separated list; empty = single-GPU drop-in
+    std::vector<int> out;
+    const char *env = getenv("S3R_DEVICES");
+    if (!env || !*env) { return out; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { count = 0; }
+    if (!strcmp(env, "all")) { for (int d = 0; d < count; d++) { out.push_back(d); } return out; }
+    for (const char *p = env; *p;) {
+        char *e = nullptr;
+        const long d = strtol(p, &e, 10);
+        if (e == p) { break; }
+        if (d >= 0 && d < count) { out.push_back((int)d); }
+        p = *e == ',' ? e + 1 : e;
+    }
+    return out;
+}
+
+void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared object)
     Dl_info info;
     char path[PATH_MAX + 64];
     path[0] = 0;
@@ -1249,20 +1406,49 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
     char *slash = strrchr(path, '/');
     if (!slash) { strcpy(path, "./"); slash = path + 1; }
     const char *candidates[3] = {"/data.bin", "/Resources/data.bin", "/../data-generator/data.bin"};
+    bool found = false;
     for (const char *c : candidates) {
         strcpy(slash, c);
         FILE *fp = fopen(path, "rb");
-        if (fp) {
-            fclose(fp);
-            if (s3r_load_scene_file(g_renderer, path) != S3R_OK) {
-                fprintf(stderr, "render.so: %s: %s\n", path, s3r_last_error());
-                exit(70);
-            }
-            s3r_camera_reset(&g_camera);
-            return;
-        }
+        if (fp) { fclose(fp); found = true; break; }
     }
-    exit(666);  // render.cpp:173
+    if (!found) { exit(666); }  // render.cpp:173
+    std::vector<int> devices = drop_in_devices();
+    if (devices.size() <= 1) {
+        int device = devices.empty() ? 0 : devices[0];
+        if (devices.empty()) { if (const char *env = getenv("S3R_DEVICE")) { device = atoi(env); } }
+        if (s3r_create(&g_renderer, device) != S3R_OK) {
+            fprintf(stderr, "render.so: %s\n", s3r_last_error());
+            exit(70);
+        }
+        if (const char *env = getenv("S3R_PIN_HOST")) { g_renderer->opt_pin_host = atoi(env) != 0; }
+        if (s3r_load_scene_file(g_renderer, path) != S3R_OK) {
+            fprintf(stderr, "render.so: %s: %s\n", path, s3r_last_error());
+            exit(70);
+        }
+    } else {
+        MultiGpu *mg = new MultiGpu();
+        mg->w.resize(devices.size());
+        if (const char *env = getenv("S3R_PIN_HOST")) { mg->pin = atoi(env) != 0; }
+        std::vector<std::thread> loaders;
+        std::vector<int> rcs(devices.size(), 0);
+        std::vector<std::string> errs(devices.size());
+        for (size_t k = 0; k < devices.size(); k++) {   // every GPU holds the whole scene: load them side by side
+            loaders.emplace_back([&, k] {
+                rcs[k] = s3r_create(&mg->w[k].r, devices[k]);
+                if (rcs[k] == S3R_OK) { rcs[k] = s3r_load_scene_file(mg->w[k].r, path); }
+                if (rcs[k] != S3R_OK) { errs[k] = s3r_last_error(); }
+            });
+        }
+        for (auto &t : loaders) { t.join(); }
+        for (size_t k = 0; k < devices.size(); k++) {
+            if (rcs[k] != S3R_OK) { fprintf(stderr, "render.so: device %d: %s\n", devices[k], errs[k].c_str()); exit(70); }
+        }
+        for (size_t k = 0; k < devices.size(); k++) { mg->w[k].th = std::thread(multi_worker, mg, (int)k); }
+        g_multi = mg;
+        g_renderer = mg->w[0].r;
+    }
+    s3r_camera_reset(&g_camera);
 }
 }  // namespace
 
@@ -1270,6 +1456,11 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
 // benchmark can replay the same Input script; the loaded scene and device buffers are kept.
 extern "C" void s3r_dropin_reset(void) {
     s3r_camera_reset(&g_camera);
+}
+
+// Harness-only: how many GPUs the drop-in renders on (0 before the first updateAndRender call).
+extern "C" int s3r_dropin_devices(void) {
+    return g_multi ? (int)g_multi->w.size() : (g_renderer ? 1 : 0);
 }
 
 extern "C" __attribute__((visibility("default"))) void updateAndRender(const PixelData *pixel_data, const Input *input) {
@@ -1283,8 +1474,9 @@ extern "C" __attribute__((visibility("default"))) void updateAndRender(const Pix
         g_renderer->factor_override = s3r_factor(pixel_data->height);
     }
     // render.cpp:281-282 clears bufferSize bytes; we write width * height pixels (== bufferSize / 4, main.swift:163)
-    if (s3r_render_host(g_renderer, g_camera.matrix, 1, pixel_data->width, pixel_data->height, 0, pixel_data->height,
-                        pixel_data->buffer) != S3R_OK) {
+    const int rc = g_multi ? multi_render(g_multi, g_camera.matrix, g_renderer->factor_override, pixel_data->width, pixel_data->height, pixel_data->buffer)
+                           : s3r_render_host(g_renderer, g_camera.matrix, 1, pixel_data->width, pixel_data->height, 0, pixel_data->height, pixel_data->buffer);
+    if (rc != S3R_OK) {
         fprintf(stderr, "render.so: %s\n", s3r_last_error());
         exit(70);
     }

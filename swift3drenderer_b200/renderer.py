@@ -72,7 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
-    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing", "s3r_debug_clusters",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing", "s3r_debug_clusters", "s3r_dropin_devices",
 ]
 
 
@@ -394,9 +394,12 @@ class Sink:
 
 class DropIn:
     """The reference's calling pattern: dlopen a private ``render.so`` that finds ``data.bin`` beside
-    itself, then ``updateAndRender(&pixelData, &input)`` once per frame (main.swift:95-99,121)."""
+    itself, then ``updateAndRender(&pixelData, &input)`` once per frame (main.swift:95-99,121).
 
-    def __init__(self, data_bin_path: str, so_path: Optional[str] = None):
+    ``devices``: None = one GPU (``S3R_DEVICE`` or 0); "all" or "0,1,2,3" = the in-process multi-GPU drop-in
+    (``S3R_DEVICES``; the library reads its environment at the first call)."""
+
+    def __init__(self, data_bin_path: str, so_path: Optional[str] = None, devices: Optional[str] = None, env: Optional[dict] = None):
         so_path = so_path or LIB_PATH
         if not os.path.exists(so_path):
             raise RendererError(f"{so_path} not found (no CPU fallback)")
@@ -412,14 +415,34 @@ class DropIn:
         self._fn = self._lib.updateAndRender
         self._fn.argtypes = [ctypes.POINTER(PixelData), ctypes.POINTER(Input)]
         self._fn.restype = None
+        self._first_env = dict(env or {})
+        if devices is not None:
+            self._first_env["S3R_DEVICES"] = devices
 
     def update_and_render(self, width: int, height: int, rec, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.empty((height, width), np.uint32)
         pd = PixelData(out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), width, height, 4, 4 * width * height)
         inp = make_input(rec)
+        if self._first_env is not None:   # the library initialises itself inside its first call: give it its environment
+            saved = {k: os.environ.get(k) for k in self._first_env}
+            os.environ.update(self._first_env)
+            try:
+                self._fn(ctypes.byref(pd), ctypes.byref(inp))
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            self._first_env = None
+            return out
         self._fn(ctypes.byref(pd), ctypes.byref(inp))
         return out
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._lib.s3r_dropin_devices())
 
     def reset_camera(self) -> None:
         self._lib.s3r_dropin_reset()

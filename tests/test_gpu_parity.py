@@ -658,3 +658,40 @@ def test_cluster_rejection_is_conservative_for_any_matrix(renderer_lib, oracle_p
         assert culled_clusters > 0
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("pin", ["1", "0"])
+def test_multi_gpu_drop_in_matches_the_single_gpu_frames(pin, renderer_lib, tmp_path):
+    """updateAndRender driving several GPUs from one process (S3R_DEVICES): interleaved tile rows, one host thread per
+    GPU, every GPU copies its rows into the caller's buffer.  On a one-GPU box the same device is named three times —
+    the threads, the row split and the copies are the same code.  Both scenes (tile-kernel path, general path), a live
+    resize, registered caller memory (pin = 1) and the pinned-staging path (pin = 0)."""
+    import torch
+    n_gpu = torch.cuda.device_count()
+    devices = ",".join(str(k % n_gpu) for k in range(max(3, min(n_gpu, 4))))
+    field = S.icosahedron_field(4000, seed=17, extent=50)
+    for name, sc, script in (("shipped", S.shipped_scene(1), "flythrough"), ("field", field, "spin")):
+        path = str(tmp_path / f"{name}_{pin}.data.bin")
+        S.write_data_bin(path, sc)
+        inp = S.input_script(script, 40)
+        d = renderer_lib.DropIn(path, devices=devices, env={"S3R_PIN_HOST": pin})
+        r = renderer_lib.Renderer(0)
+        try:
+            r.load_scene(sc)
+            cam = renderer_lib.Camera()
+            buf = np.zeros((2, 1080, 1920), np.uint32)
+            last_wh = None
+            for f in range(40):
+                W, H = (1920, 1080) if f < 25 or f >= 32 else (1283, 721)   # a live resize and back (main.swift:156-165)
+                out = buf[f & 1].reshape(-1)[: W * H].reshape(H, W)
+                d.update_and_render(W, H, inp[f], out=out)
+                m = cam.update(inp[f])
+                if f in (0, 1, 24, 25, 26, 31, 32, 39):
+                    # the reference's stale-factor rule (render.cpp:275-280) is exercised by the resize: compare with a
+                    # single-GPU drop-in semantics = s3r_factor of the CURRENT height whenever W*H changes, which it does here
+                    assert_same(out, r.render(m, W, H)[0], f"{name} pin={pin} frame {f} at {W}x{H}")
+                last_wh = (W, H)
+            assert d.n_devices == len(devices.split(","))
+        finally:
+            d.close()
+            r.close()
