@@ -605,121 +605,130 @@ __device__ __forceinline__ uint32_t front_test(const Frame &f, const float4 &r0,
     return 1u;
 }
 
-// Candidates, densely packed, 256 per round: exact boxes, row ownership, coverage setup, and the direct walk of every
-// unclipped triangle under 16 x 16 pixels.  `fetch(i, item, r0, r1, r2)` hands out candidate i: its order key
-// (| ITEM_STRADDLE) and, for non-straddlers, its three raster-space vertices.  All 256 threads call.
-template <typename Fetch>
-__device__ __forceinline__ void walk_candidates(const Frame &f, uint32_t view, WalkShared &wsh, uint32_t n_cand, FrontCounts &n, Fetch fetch) {
+// Where a candidate (front tests passed, not straddling) goes: its exact pixel box (render.cpp:318-321), and for a box
+// under 16 x 16 pixels the box rows this submission owns (bit r: row ymin + r; under 16 rows meet at most two tile rows).
+// route 3: walked record-free (direct walk); 1: work item for K2b (larger box); 0: owns no row of it — culled here.
+struct BoxRoute { uint32_t xmin, xmax, ymin, ymax, rows, route; };
+
+__device__ __forceinline__ BoxRoute route_candidate(const Frame &f, const float4 &r0, const float4 &r1, const float4 &r2) {
+    BoxRoute b;
+    const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
+    const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
+    b.xmin = (uint32_t)fmaxf(0, min_x); b.xmax = (uint32_t)fminf(f.fw - 1, max_x);
+    b.ymin = (uint32_t)fmaxf(0, min_y); b.ymax = (uint32_t)fminf(f.fh - 1, max_y);
+    const uint32_t ylo = max(b.ymin, f.y0), yhi = min(b.ymax, f.y1 - 1u);
+    b.rows = 0;
+    if (f.direct_small && is_small_bbox(b.xmin, b.xmax, b.ymin, b.ymax)) {
+        const uint32_t lo = ylo - b.ymin, hi = yhi - b.ymin;
+        uint32_t rows = (2u << hi) - (1u << lo);
+        if (f.row_stride != 1u) {
+            const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
+            const uint32_t split = (a0 + 1u) * TILE_H - b.ymin;   // first box row inside tile row a0 + 1
+            const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
+            rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
+        }
+        b.rows = rows;
+        b.route = rows ? 3u : 0u;
+    } else {
+        b.route = owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u ? 1u : 0u;
+    }
+    return b;
+}
+
+// One round of up to 256 candidates, one per thread (valid: this thread has one; item: its order key, | ITEM_STRADDLE
+// for a straddler whose vertices are not looked at): routing, coverage setup (vis_core) into shared memory, and the
+// direct walk of the boxes under 16 x 16 pixels — one (triangle, owned row) work item per lane, grouped by box width,
+// row starts from checkpoints every 4 rows, true additions along the row (render.cpp:374-379), keys published with
+// fire-and-forget 64-bit red.max.  Everything else becomes a work item of K2b.  All 256 threads call.
+__device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkShared &wsh, FrontCounts &n, bool valid, uint32_t item,
+                                           const float4 &r0, const float4 &r1, const float4 &r2) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
     unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
-    for (uint32_t cbase = 0; cbase < n_cand; cbase += 256u) {
-        if (tid < SMALL_MAX) { wsh.cls_count[tid] = 0; }
-        __syncthreads();
-        uint32_t route = 0;   // 1 work item for K2b, 3 walked here
-        uint32_t item = 0, my_cls = 0, my_rows = 0, my_off = 0;
-        if (cbase + tid < n_cand) {
-            float4 r0, r1, r2;
-            fetch(cbase + tid, item, r0, r1, r2);
-            if (item & ITEM_STRADDLE) {
-                route = 1;
-            } else {
-                const float max_x = fmaxf(fmaxf(r0.x, r1.x), r2.x), max_y = fmaxf(fmaxf(r0.y, r1.y), r2.y);
-                const float min_x = fminf(fminf(r0.x, r1.x), r2.x), min_y = fminf(fminf(r0.y, r1.y), r2.y);
-                const uint32_t xmin = (uint32_t)fmaxf(0, min_x), xmax = (uint32_t)fminf(f.fw - 1, max_x);
-                const uint32_t ymin = (uint32_t)fmaxf(0, min_y), ymax = (uint32_t)fminf(f.fh - 1, max_y);
-                const uint32_t ylo = max(ymin, f.y0), yhi = min(ymax, f.y1 - 1u);
-                if (f.direct_small && is_small_bbox(xmin, xmax, ymin, ymax)) {
-                    // box rows this submission owns (bit r: row ymin + r).  Under 16 rows meet at most two tile rows.
-                    const uint32_t lo = ylo - ymin, hi = yhi - ymin;
-                    uint32_t rows = (2u << hi) - (1u << lo);
-                    if (f.row_stride != 1u) {
-                        const uint32_t a0 = ylo / TILE_H, a1 = yhi / TILE_H;
-                        const uint32_t split = (a0 + 1u) * TILE_H - ymin;   // first box row inside tile row a0 + 1
-                        const uint32_t low = split < SMALL_MAX ? (1u << split) - 1u : 0xFFFFu;
-                        rows &= (owns_row(f, a0) ? low : 0u) | (a1 != a0 && owns_row(f, a1) ? ~low : 0u);
-                    }
-                    if (rows) {
-                        route = 3; n.n_direct++;
-                        VisCore vc;
-                        vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
-                                 edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y), xmin, ymin, vc);
+    if (tid < SMALL_MAX) { wsh.cls_count[tid] = 0; }
+    __syncthreads();
+    uint32_t route = 0;   // 1 work item for K2b, 3 walked here
+    uint32_t my_cls = 0, my_rows = 0, my_off = 0;
+    if (valid) {
+        if (item & ITEM_STRADDLE) {
+            route = 1;
+        } else {
+            const BoxRoute b = route_candidate(f, r0, r1, r2);
+            route = b.route;
+            if (route == 0u) { n.n_cull++; }
+            if (route == 3u) {
+                n.n_direct++;
+                VisCore vc;
+                vis_core(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), make_float3(r2.x, r2.y, r2.z),
+                         edge_fn(r0.x, r0.y, r1.x, r1.y, r2.x, r2.y), b.xmin, b.ymin, vc);
 #pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            wsh.par[k][tid] = vc.ws[k]; wsh.par[3 + k][tid] = vc.dx[k]; wsh.par[6 + k][tid] = vc.dy[k]; wsh.par[9 + k][tid] = vc.rz[k];
-                        }
-                        wsh.xy[tid] = xmin | (ymin << 16);
-                        wsh.bwrows[tid] = (xmax - xmin) | (rows << 16);
-                        wsh.tri[tid] = item;
-                        float w0 = vc.ws[0], w1 = vc.ws[1], w2 = vc.ws[2];
-                        const uint32_t top = 31u - (uint32_t)__clz((int)rows);   // last owned box row
-                        for (uint32_t r = 1; r <= (top & ~3u); r++) {          // render.cpp:378, row by row; keep rows 4, 8, 12
-                            w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
-                            if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
-                        }
-                        my_rows = rows;
-                        my_cls = xmax - xmin;
-                        my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(rows));
-                    } else {
-                        n.n_cull++;
-                    }
-                } else if (owned_rows_in(f, ylo / TILE_H, yhi / TILE_H) != 0u) {
-                    route = 1;
-                } else {
-                    n.n_cull++;
+                for (int k = 0; k < 3; k++) {
+                    wsh.par[k][tid] = vc.ws[k]; wsh.par[3 + k][tid] = vc.dx[k]; wsh.par[6 + k][tid] = vc.dy[k]; wsh.par[9 + k][tid] = vc.rz[k];
                 }
+                wsh.xy[tid] = b.xmin | (b.ymin << 16);
+                wsh.bwrows[tid] = (b.xmax - b.xmin) | (b.rows << 16);
+                wsh.tri[tid] = item;
+                float w0 = vc.ws[0], w1 = vc.ws[1], w2 = vc.ws[2];
+                const uint32_t top = 31u - (uint32_t)__clz((int)b.rows);   // last owned box row
+                for (uint32_t r = 1; r <= (top & ~3u); r++) {            // render.cpp:378, row by row; keep rows 4, 8, 12
+                    w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
+                    if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
+                }
+                my_rows = b.rows;
+                my_cls = b.xmax - b.xmin;
+                my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(b.rows));
             }
         }
-        {   // work items for K2b: one global atomic per warp
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, route == 1);
-            uint32_t base = 0;
-            if (lane == 0 && m) { base = atomicAdd(f.counters + view * C_COUNT + C_WORK, __popc(m)); }
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (route == 1) { f.worklist[(size_t)view * f.T + base + __popc(m & ((1u << lane) - 1u))] = item; }
-        }
-        __syncthreads();
-        uint32_t n_items = 0, cls_base = 0;   // items of narrower boxes come first
-#pragma unroll
-        for (uint32_t c = 0; c < SMALL_MAX; c++) { const uint32_t k = wsh.cls_count[c]; if (c < my_cls) { cls_base += k; } n_items += k; }
-        if (route == 3) {
-            uint32_t pos = my_off + cls_base;
-            while (my_rows) {   // one work item per owned box row
-                const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
-                my_rows &= my_rows - 1u;
-                wsh.items[pos++] = (uint16_t)(tid | (r << 8));
-            }
-        }
-        __syncthreads();
-        // the direct walk: one (triangle, row) item per thread and pass
-        for (uint32_t i = tid; i < n_items; i += 256u) {
-            const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
-            float w0, w1, w2;
-            if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
-            else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
-            const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
-            for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
-            const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
-            const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
-            const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
-            unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
-            const unsigned long long key_lo = (unsigned long long)(~wsh.tri[ow]);
-            const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
-            // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
-            // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
-            // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
-            uint32_t x = 0;
-            while (x <= bw && !(w0 >= 0 && w1 >= 0 && w2 >= 0)) {
-                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);
-                x++;
-            }
-            for (; x <= bw && (w0 >= 0 && w1 >= 0 && w2 >= 0); x++) {
-                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
-                // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
-                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
-            }
-        }
-        __syncthreads();   // parked boxes and items are rewritten by the next round
     }
+    {   // work items for K2b: one global atomic per warp
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, route == 1);
+        uint32_t base = 0;
+        if (lane == 0 && m) { base = atomicAdd(f.counters + view * C_COUNT + C_WORK, __popc(m)); }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (route == 1) { f.worklist[(size_t)view * f.T + base + __popc(m & ((1u << lane) - 1u))] = item; }
+    }
+    __syncthreads();
+    uint32_t n_items = 0, cls_base = 0;   // items of narrower boxes come first
+#pragma unroll
+    for (uint32_t c = 0; c < SMALL_MAX; c++) { const uint32_t k = wsh.cls_count[c]; if (c < my_cls) { cls_base += k; } n_items += k; }
+    if (route == 3) {
+        uint32_t pos = my_off + cls_base;
+        while (my_rows) {   // one work item per owned box row
+            const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
+            my_rows &= my_rows - 1u;
+            wsh.items[pos++] = (uint16_t)(tid | (r << 8));
+        }
+    }
+    __syncthreads();
+    // the direct walk: one (triangle, row) item per thread and pass
+    for (uint32_t i = tid; i < n_items; i += 256u) {
+        const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
+        float w0, w1, w2;
+        if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
+        else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
+        const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
+        for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+        const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
+        const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
+        const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
+        unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+        const unsigned long long key_lo = (unsigned long long)(~wsh.tri[ow]);
+        const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
+        // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
+        // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
+        // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
+        uint32_t x = 0;
+        while (x <= bw && !(w0 >= 0 && w1 >= 0 && w2 >= 0)) {
+            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);
+            x++;
+        }
+        for (; x <= bw && (w0 >= 0 && w1 >= 0 && w2 >= 0); x++) {
+            const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
+            // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+            if (ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+        }
+    }
+    __syncthreads();   // parked boxes and items are rewritten by the next round
 }
 
 // statistics: one shared-memory atomic per warp, one global atomic per CTA and counter (all 256 threads call)
@@ -770,10 +779,17 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
         if (cand) { csh.cand[base + __popc(m & ((1u << lane) - 1u))] = t | (cand == 2 ? ITEM_STRADDLE : 0u); }
     }
     __syncthreads();
-    walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
-        item = csh.cand[i];
-        if (!(item & ITEM_STRADDLE)) { r0 = rv[__ldg(f.vi0 + item)]; r1 = rv[__ldg(f.vi1 + item)]; r2 = rv[__ldg(f.vi2 + item)]; }
-    });
+    const uint32_t n_cand = wsh.n_cand;
+    for (uint32_t cbase = 0; cbase < n_cand; cbase += 256u) {   // candidates, densely packed, 256 per round
+        const bool valid = cbase + tid < n_cand;
+        uint32_t item = 0;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+        if (valid) {
+            item = csh.cand[cbase + tid];
+            if (!(item & ITEM_STRADDLE)) { r0 = rv[__ldg(f.vi0 + item)]; r1 = rv[__ldg(f.vi1 + item)]; r2 = rv[__ldg(f.vi2 + item)]; }
+        }
+        walk_round(f, view, wsh, n, valid, item, r0, r1, r2);
+    }
     publish_front_counts(f, view, wsh, n);
 }
 
@@ -794,15 +810,17 @@ constexpr uint32_t CL_DEAD = 0xFFFFFFFFu;
 
 struct FrontShared {
     float4 rv[CL_BATCH * CL_MAX_VERTS];      // raster-space vertices of the batch's surviving clusters
-    WalkShared w;
-    uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // position in the batch | 0x8000 for a straddler
     uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in the cluster-vertex arrays, CL_DEAD = cluster skipped
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
     uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
     uint32_t batch, first_alive, last_alive;
+    uint32_t stats[4];
 };
-static_assert(CL_BATCH * CL_MAX_TRIS <= 0x8000, "candidate entries are 15-bit positions plus the straddle flag");
-static_assert(sizeof(FrontShared) <= 55 * 1024, "FrontShared must leave room for four CTAs per SM");
+
+// One candidate of the direct walk as the front kernel hands it to the walk kernel through HBM: the three raster-space
+// vertices and the order key (40 bytes; a warp's candidates are contiguous).
+struct __align__(8) WalkRecord { float v[9]; uint32_t order; };
+static_assert(sizeof(WalkRecord) == 40, "WalkRecord must be 40 bytes");
 
 // What the rejection tests need from the view's matrix: the norms of its rows and a bound of its largest singular value
 // (Gershgorin on the Gram matrix; 1 for a camera's orthonormal rows).
@@ -898,17 +916,16 @@ __global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame 
     }
 }
 
-__global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ Frame f) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    FrontShared &sh = *reinterpret_cast<FrontShared *>(smem_raw);
-    WalkShared &wsh = sh.w;
+__global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ Frame f) {
+    __shared__ FrontShared sh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
     const Cam cam = load_cam(f, view);
     const ViewBounds vb = view_bounds(cam);
     uint32_t *counters = f.counters + view * C_COUNT;
     const uint32_t n_alive = counters[C_BATCHES];   // written by batch_cull
-    if (tid < 4) { wsh.stats[tid] = 0; }
+    if (tid < 4) { sh.stats[tid] = 0; }
     FrontCounts n = {0u, 0u, 0u, 0u};
+    WalkRecord *queue = f.walk_q + (size_t)view * f.walk_cap;
 
     // persistent CTAs: batches are handed out by a counter
     while (true) {
@@ -916,7 +933,7 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
         if (tid == 0) {
             const uint32_t i = atomicAdd(counters + C_BHEAD, 1u);
             sh.batch = i < n_alive ? f.batch_list[(size_t)view * f.n_batches + i] : CL_DEAD;
-            wsh.n_cand = 0; sh.first_alive = CL_BATCH; sh.last_alive = 0;
+            sh.first_alive = CL_BATCH; sh.last_alive = 0;
         }
         __syncthreads();
         if (sh.batch == CL_DEAD) { break; }
@@ -975,7 +992,7 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- 3. front tests, one thread per triangle word (four words in flight per thread) ------------------------------
+        // ---- 3. front tests and routing, one thread per triangle word (four words in flight per thread) ----------------
         for (uint32_t jb = t_begin; jb < t_end; jb += 1024u) {
             uint32_t w[4];
 #pragma unroll
@@ -984,30 +1001,88 @@ __global__ void __launch_bounds__(256, 4) cluster_front(const __grid_constant__ 
             for (int k = 0; k < 4; k++) {
                 const uint32_t j = jb + 256u * k + tid;
                 if (jb + 256u * k >= t_end) { break; }   // (uniform)
-                uint32_t cand = 0;
+                uint32_t route = 0, item = 0;   // 1: work item for K2b (straddler or larger box), 3: direct walk
+                float4 r0, r1, r2;
                 if (j < t_end) {
-                    const uint32_t base = sh.ctab[w[k] >> 24];
+                    const uint32_t slot = w[k] >> 24, base = sh.ctab[slot];
                     if (base != CL_DEAD) {
                         const uint32_t o = base - v_begin;
-                        cand = front_test(f, sh.rv[o + (w[k] & 255u)], sh.rv[o + ((w[k] >> 8) & 255u)], sh.rv[o + ((w[k] >> 16) & 255u)], n);
+                        r0 = sh.rv[o + (w[k] & 255u)]; r1 = sh.rv[o + ((w[k] >> 8) & 255u)]; r2 = sh.rv[o + ((w[k] >> 16) & 255u)];
+                        const uint32_t cand = front_test(f, r0, r1, r2, n);
+                        item = j + sh.cdelta[slot];   // the original triangle index is the order key
+                        if (cand == 2u) { route = 1; item |= ITEM_STRADDLE; }
+                        else if (cand == 1u) {
+                            route = route_candidate(f, r0, r1, r2).route;
+                            if (route == 0u) { n.n_cull++; }
+                        }
                     }
                 }
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0);
-                uint32_t pos = 0;
-                if (lane == 0 && m) { pos = atomicAdd(&wsh.n_cand, __popc(m)); }
-                pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-                if (cand) { sh.cand[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((j - t_begin) | (cand == 2 ? 0x8000u : 0u)); }
+                const uint32_t m_walk = __ballot_sync(0xFFFFFFFFu, route == 3u), m_work = __ballot_sync(0xFFFFFFFFu, route == 1u);
+                uint32_t base_walk = 0, base_work = 0;
+                if (lane == 0) {
+                    if (m_walk) { base_walk = atomicAdd(counters + C_WALKQ, __popc(m_walk)); }
+                    if (m_work) { base_work = atomicAdd(counters + C_WORK, __popc(m_work)); }
+                }
+                base_walk = __shfl_sync(0xFFFFFFFFu, base_walk, 0); base_work = __shfl_sync(0xFFFFFFFFu, base_work, 0);
+                if (route == 3u) {
+                    const uint32_t at = base_walk + __popc(m_walk & ((1u << lane) - 1u));
+                    if (at < f.walk_cap) {
+                        uint2 *q = reinterpret_cast<uint2 *>(queue + at);
+                        q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
+                        q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
+                        q[4] = make_uint2(__float_as_uint(r2.z), item);
+                    }
+                } else if (route == 1u) {
+                    f.worklist[(size_t)view * f.T + base_work + __popc(m_work & ((1u << lane) - 1u))] = item;
+                }
             }
         }
-        __syncthreads();
+    }
+    // statistics: one shared-memory atomic per warp, one global atomic per CTA and counter
+    n.n_near = __reduce_add_sync(0xFFFFFFFFu, n.n_near); n.n_clip = __reduce_add_sync(0xFFFFFFFFu, n.n_clip); n.n_cull = __reduce_add_sync(0xFFFFFFFFu, n.n_cull);
+    if (lane == 0) {
+        if (n.n_near) { atomicAdd(&sh.stats[0], n.n_near); }
+        if (n.n_clip) { atomicAdd(&sh.stats[1], n.n_clip); }
+        if (n.n_cull) { atomicAdd(&sh.stats[3], n.n_cull); }
+    }
+    __syncthreads();
+    if (tid < 4 && tid != 2u && sh.stats[tid]) { atomicAdd(counters + C_NEAR + tid, sh.stats[tid]); }   // C_NEAR, C_CLIPPED, (-), C_CULLED
+}
 
-        // ---- 4. candidates: coverage setup + direct walk -----------------------------------------------------------------
-        walk_candidates(f, view, wsh, wsh.n_cand, n, [&](uint32_t i, uint32_t &item, float4 &r0, float4 &r1, float4 &r2) {
-            const uint32_t e = sh.cand[i], j = t_begin + (e & 0x7FFFu);
-            const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, o = sh.ctab[slot] - v_begin;
-            item = (j + sh.cdelta[slot]) | ((e & 0x8000u) ? ITEM_STRADDLE : 0u);   // the original triangle index is the order key
-            r0 = sh.rv[o + (w & 255u)]; r1 = sh.rv[o + ((w >> 8) & 255u)]; r2 = sh.rv[o + ((w >> 16) & 255u)];
-        });
+// The direct walk over the front kernel's candidate queue: persistent CTAs take rounds of 256 records — always full but
+// the last — and run walk_round on them.  Nothing but the walk lives here, so the kernel's warps keep the reduction path
+// (one red.global.max.u64 per covered pixel) busy back to back.
+__global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Frame f) {
+    __shared__ WalkShared wsh;
+    __shared__ uint32_t s_round;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x;
+    uint32_t *counters = f.counters + view * C_COUNT;
+    const uint32_t n_q = counters[C_WALKQ];
+    if (n_q > f.walk_cap) {   // the queue overflowed: the host regrows it and renders the frame again
+        if (blockIdx.x == 0 && tid == 0) { atomicOr(counters + C_OVERFLOW, 8u); atomicOr(f.sticky + 0, 8u); atomicMax(f.sticky + 4, n_q); }
+        return;
+    }
+    if (tid < 4) { wsh.stats[tid] = 0; }
+    FrontCounts n = {0u, 0u, 0u, 0u};
+    const WalkRecord *queue = f.walk_q + (size_t)view * f.walk_cap;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) { s_round = atomicAdd(counters + C_WALKHEAD, 1u); }
+        __syncthreads();
+        const uint32_t base = s_round * 256u;
+        if (base >= n_q) { break; }
+        const bool valid = base + tid < n_q;
+        uint32_t item = 0;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+        if (valid) {
+            const uint2 *q = reinterpret_cast<const uint2 *>(queue + base + tid);
+            const uint2 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+            r0 = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x), 0.f);
+            r1 = make_float4(__uint_as_float(b.y), __uint_as_float(c.x), __uint_as_float(c.y), 0.f);
+            r2 = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(e.x), 0.f);
+            item = e.y;
+        }
+        walk_round(f, view, wsh, n, valid, item, r0, r1, r2);
     }
     publish_front_counts(f, view, wsh, n);
 }
@@ -2051,9 +2126,9 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(tile_raster_queue, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
     // both keep ~40 KB of static shared memory per CTA: without the carve-out hint the driver may leave too little for 4-6 CTAs per SM
-    e = cudaFuncSetAttribute(cluster_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontShared));
-    if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(cluster_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(direct_walk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
     if (e != cudaSuccess) { return e; }
@@ -2075,7 +2150,8 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         cudaMemsetAsync(f.counters, 0, (size_t)f.n_views * C_COUNT * sizeof(uint32_t), s);
         cudaMemsetAsync(f.tile_count, 0, (size_t)f.n_views * f.tile_stride * sizeof(uint32_t), s);
         batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
-        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * 4u)), f.n_views), 256, sizeof(FrontShared), s>>>(f); launches++; mark(m, "cluster_front");
+        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * 5u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
+        direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");
     } else {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
         triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");

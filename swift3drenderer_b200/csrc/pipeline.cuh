@@ -67,6 +67,8 @@ enum Counter : uint32_t {
     C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
     C_BATCHES = 16,  // cluster front: batches of clusters that survived the batch-level rejection (batch_cull)
     C_BHEAD = 17,    // ... and how many of them the front kernel's persistent CTAs have taken
+    C_WALKQ = 18,    // cluster front: candidates queued for the direct-walk kernel
+    C_WALKHEAD = 19, // ... and how many rounds of 256 the walk kernel's persistent CTAs have taken
     C_COUNT = 20
 };
 
@@ -92,6 +94,8 @@ struct __align__(16) SetupShade {   // 128 bytes: everything shading needs
 };
 static_assert(sizeof(SetupShade) == 128, "SetupShade must be 128 bytes");
 
+struct WalkRecord;
+
 struct Frame {
     // scene
     const float *pos_x, *pos_y, *pos_z;
@@ -108,6 +112,8 @@ struct Frame {
     const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
     uint32_t *batch_list;         // [views][n_batches] batches that survived batch_cull, in list order
     uint32_t n_clusters, n_batches;
+    struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)
+    uint32_t walk_cap;
     int cluster_cull;             // 0: every cluster is processed per triangle (A/B and tests)
     // views
     const float *cams;  // n_views x 12
@@ -130,7 +136,7 @@ struct Frame {
     uint32_t *worklist;   // [views][T] classify -> setup work items
     uint32_t setup_cap;
     uint32_t *counters;
-    uint32_t *sticky;   // [4] across chunks: overflow bits (OR), max setups, max entries, max big
+    uint32_t *sticky;   // [8] across chunks: overflow bits (OR), max setups, max entries, max big, max walk-queue length
     uint32_t *tile_count;       // [views][tile_stride] entries binned per tile this frame
     uint32_t tile_stride;
     uint32_t *entries;          // per-tile lists of survivor slots (unordered)

@@ -81,6 +81,8 @@ struct S3RRenderer {
     DevBuf<uint32_t> cl_tri;
     DevBuf<float4> cl_batch;
     DevBuf<uint32_t> batch_list;
+    DevBuf<uint8_t> walk_q;            // candidate queue of the direct walk: 40-byte records (front kernel -> walk kernel)
+    uint32_t walk_cap = 0;
     uint32_t n_clusters = 0, n_batches = 0;
     int opt_clusters = 1, opt_cluster_cull = 1;
     Frame last_frame;   // parameter block of the last submission (raster-vertex dumps on the cluster path)
@@ -202,7 +204,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release();
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release(); r->walk_q.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release(); r->tile_count.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -301,6 +303,7 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
     r->V = V; r->Vpad = px.size(); r->I = I; r->T = T; r->A = A; r->n_texels = n_texels;
     r->has_scene = true;
     r->views_cap = 0;  // scratch is re-sized on the next render
+    r->walk_q.release(); r->walk_cap = 0;
     r->worklist.release(); r->setup_cap = 0; r->tile_cap = 0; r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release(); r->rowbase.release();
     return S3R_OK;
 }
@@ -505,9 +508,9 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
     CUDA_TRY(r->worklist.ensure(vc * std::max<uint64_t>(r->T, 1)));
     CUDA_TRY(r->counters.ensure(vc * C_COUNT));
     if (!r->sticky.p) {
-        CUDA_TRY(r->sticky.ensure(4)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 16));
-        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&r->sticky_host), 16));
-        memset(r->sticky_host, 0, 16);
+        CUDA_TRY(r->sticky.ensure(8)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 32));
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&r->sticky_host), 32));
+        memset(r->sticky_host, 0, 32);
     }
     CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
     // bin lists exist only for scenes that do not take the in-kernel collection path
@@ -675,6 +678,10 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
         CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
+        // candidates of the direct walk: a quarter of the triangles to begin with, regrown on overflow
+        if (r->walk_cap == 0) { r->walk_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r->T, 1), std::max<uint64_t>(4096, r->T / 4)); }
+        CUDA_TRY(r->walk_q.ensure((size_t)r->views_cap * r->walk_cap * 40u));
+        f.walk_q = reinterpret_cast<WalkRecord *>(r->walk_q.p); f.walk_cap = r->walk_cap;
         f.cl_batch = r->cl_batch.p; f.batch_list = r->batch_list.p; f.n_batches = r->n_batches;
         f.rv = nullptr;
     }
@@ -742,7 +749,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         // rendering stream would sit between post_setup and the raster kernels (10 us of every frame)
         CUDA_TRY(cudaEventRecord(r->ev_geometry, s));
         CUDA_TRY(cudaStreamWaitEvent(r->aux_stream, r->ev_geometry, 0));
-        CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 16, cudaMemcpyDeviceToHost, r->aux_stream));
+        CUDA_TRY(cudaMemcpyAsync(r->sticky_host, r->sticky.p, 32, cudaMemcpyDeviceToHost, r->aux_stream));
     }
     if (timed) { CUDA_TRY(cudaEventRecord(r->ev_t1[slot], s)); }
     // (general path: the tile kernel runs with the first band over the whole frame, the bands cut the shading pass)
@@ -824,9 +831,9 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(r->aux_stream));   // the overflow record's copy
     if (r->last_views == 0 || !r->sticky.p) { return S3R_OK; }
-    uint32_t sticky[4];
+    uint32_t sticky[8];
     memcpy(sticky, r->sticky_host, sizeof(sticky));   // copied after the geometry of the last submission; the sync above covers it
-    const uint32_t overflow = sticky[0], need_setups = sticky[1], need_entries = sticky[2], need_big = sticky[3];
+    const uint32_t overflow = sticky[0], need_setups = sticky[1], need_entries = sticky[2], need_big = sticky[3], need_walk = sticky[4];
     if (!overflow) { return S3R_OK; }
     CUDA_TRY(cudaMemset(r->sticky.p, 0, sizeof(sticky)));
     memset(r->sticky_host, 0, sizeof(sticky));
@@ -838,6 +845,10 @@ static int finish_on(S3RRenderer *r, cudaStream_t s) {
     }
     if (overflow & 2u) { r->tile_cap = std::max(r->tile_cap, need_entries + need_entries / 2 + 64); r->entries.release(); }
     if (overflow & 4u) { r->big_cap = std::max(r->big_cap, need_big + need_big / 2 + 64); r->big_list.release(); }
+    if (overflow & 8u) {
+        r->walk_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r->T, 1), (uint64_t)need_walk + need_walk / 4 + 1024);
+        r->walk_q.release();
+    }
     return 1;
 }
 
@@ -1226,7 +1237,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "setup_capacity")) {  // test hook: force the regrow path
         if (value < 1) { return fail(S3R_E_ARG, "setup_capacity < 1"); }
         cudaStreamSynchronize(r->stream);
-        r->setup_cap = (uint32_t)value; r->tile_cap = 4; r->big_cap = 4;
+        r->setup_cap = (uint32_t)value; r->tile_cap = 4; r->big_cap = 4; r->walk_cap = 8; r->walk_q.release();
         r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->entries.release(); r->big_list.release(); r->rowbase.release();
         return S3R_OK;
     }
