@@ -2146,9 +2146,8 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
     if (f.cl_hdr) {
         // spatial pre-partition: vertex stage + front + direct walk in one kernel over the clusters; the frame's counters
-        // and tile histograms (zeroed by vertex_stage on the other path) are cleared by two small memsets
-        cudaMemsetAsync(f.counters, 0, (size_t)f.n_views * C_COUNT * sizeof(uint32_t), s);
-        cudaMemsetAsync(f.tile_count, 0, (size_t)f.n_views * f.tile_stride * sizeof(uint32_t), s);
+        // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
+        cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
         cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * 5u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
         direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");

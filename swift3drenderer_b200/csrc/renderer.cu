@@ -104,7 +104,7 @@ struct S3RRenderer {
     DevBuf<uint32_t> sticky;
     uint32_t *sticky_host = nullptr;   // pinned mirror of `sticky`
     float factor_override = 0.f;   // drop-in path: the reference's stale-factor rule (render.cpp:276-279)
-    DevBuf<uint32_t> counters, tile_count, big_list;
+    DevBuf<uint32_t> counters, big_list;   // counters: [views_cap][C_COUNT] followed by the tile histograms [views_cap][tile_stride]
     DevBuf<uint32_t> entries;
     DevBuf<float> cams;
     DevBuf<uint32_t> frame;   // internal device framebuffer for host renders (u32 pixels, or 3 bytes/pixel when packed)
@@ -206,7 +206,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
     r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release(); r->walk_q.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
-    r->counters.release(); r->tile_count.release();
+    r->counters.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
     r->coltab.release(); r->span_slots.release(); r->rowtab.release(); r->rowbase.release();
     if (r->cams_pinned) { cudaFreeHost(r->cams_pinned); }
@@ -506,13 +506,14 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
         CUDA_TRY(r->slot_of.ensure(vc * 2ull * std::max<uint64_t>(r->T, 1)));
     }
     CUDA_TRY(r->worklist.ensure(vc * std::max<uint64_t>(r->T, 1)));
-    CUDA_TRY(r->counters.ensure(vc * C_COUNT));
+    // per-view counters and, right behind them, the per-tile histograms: the cluster path clears both with one memset
+    if (vc * (C_COUNT + (size_t)r->tile_stride) > r->counters.n) { CUDA_TRY(cudaStreamSynchronize(r->stream)); }
+    CUDA_TRY(r->counters.ensure(vc * (C_COUNT + (size_t)r->tile_stride)));
     if (!r->sticky.p) {
         CUDA_TRY(r->sticky.ensure(8)); CUDA_TRY(cudaMemset(r->sticky.p, 0, 32));
         CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&r->sticky_host), 32));
         memset(r->sticky_host, 0, 32);
     }
-    CUDA_TRY(r->tile_count.ensure(vc * r->tile_stride));
     // bin lists exist only for scenes that do not take the in-kernel collection path
     if (!uses_direct_bin(r)) {
         CUDA_TRY(r->entries.ensure(vc * (size_t)r->tile_stride * r->tile_cap));
@@ -689,7 +690,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.band_lo = (float)y0; f.band_hi = (float)y1;
     f.counters = r->counters.p;
     f.sticky = r->sticky.p;
-    f.tile_count = r->tile_count.p;
+    f.tile_count = r->counters.p + (size_t)r->views_cap * C_COUNT;
     f.tile_stride = r->tile_stride;
     f.entries = r->entries.p; f.tile_cap = r->tile_cap;
     f.raster_items = r->raster_items.p; f.items_cap = r->items_cap;
