@@ -814,6 +814,7 @@ struct FrontShared {
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
     uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
     uint32_t batch, first_alive, last_alive;
+    uint32_t wsum[8], base_walk, base_work;   // queue-space allocation: per-warp partial sums, the batch's reserved ranges
     uint32_t stats[4];
 };
 
@@ -992,48 +993,68 @@ __global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- 3. front tests and routing, one thread per triangle word (four words in flight per thread) ----------------
-        for (uint32_t jb = t_begin; jb < t_end; jb += 1024u) {
-            uint32_t w[4];
+        // ---- 3. front tests and routing, one thread per triangle word.  Pass A decides where every triangle goes (2 bits
+        // each, kept in a register); one block-wide scan and ONE global atomic per counter and batch reserve the queue
+        // space (a warp-level atomic per iteration made the two counters the hottest addresses of the frame); pass B
+        // gathers the corners again from shared memory and writes the records.
+        constexpr int TU = (CL_BATCH * CL_MAX_TRIS) / 256;
+        uint32_t codes = 0, c_walk = 0, c_work = 0;   // code: 1 larger box -> K2b, 2 straddler -> K2b, 3 direct walk
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t j = jb + 256u * k + tid; w[k] = j < t_end ? __ldg(f.cl_tri + j) : 0xFFFFFFFFu; }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t j = jb + 256u * k + tid;
-                if (jb + 256u * k >= t_end) { break; }   // (uniform)
-                uint32_t route = 0, item = 0;   // 1: work item for K2b (straddler or larger box), 3: direct walk
-                float4 r0, r1, r2;
-                if (j < t_end) {
-                    const uint32_t slot = w[k] >> 24, base = sh.ctab[slot];
-                    if (base != CL_DEAD) {
-                        const uint32_t o = base - v_begin;
-                        r0 = sh.rv[o + (w[k] & 255u)]; r1 = sh.rv[o + ((w[k] >> 8) & 255u)]; r2 = sh.rv[o + ((w[k] >> 16) & 255u)];
-                        const uint32_t cand = front_test(f, r0, r1, r2, n);
-                        item = j + sh.cdelta[slot];   // the original triangle index is the order key
-                        if (cand == 2u) { route = 1; item |= ITEM_STRADDLE; }
-                        else if (cand == 1u) {
-                            route = route_candidate(f, r0, r1, r2).route;
-                            if (route == 0u) { n.n_cull++; }
-                        }
+        for (int k = 0; k < TU; k++) {
+            const uint32_t j = t_begin + 256u * k + tid;
+            if (j < t_end) {
+                const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
+                if (base != CL_DEAD) {
+                    const uint32_t o = base - v_begin;
+                    const float4 r0 = sh.rv[o + (w & 255u)], r1 = sh.rv[o + ((w >> 8) & 255u)], r2 = sh.rv[o + ((w >> 16) & 255u)];
+                    const uint32_t cand = front_test(f, r0, r1, r2, n);
+                    uint32_t code = 0;
+                    if (cand == 2u) { code = 2u; }
+                    else if (cand == 1u) {
+                        code = route_candidate(f, r0, r1, r2).route;
+                        if (code == 0u) { n.n_cull++; }
                     }
+                    codes |= code << (2 * k);
+                    c_walk += code == 3u ? 1u : 0u; c_work += (code == 1u || code == 2u) ? 1u : 0u;
                 }
-                const uint32_t m_walk = __ballot_sync(0xFFFFFFFFu, route == 3u), m_work = __ballot_sync(0xFFFFFFFFu, route == 1u);
-                uint32_t base_walk = 0, base_work = 0;
-                if (lane == 0) {
-                    if (m_walk) { base_walk = atomicAdd(counters + C_WALKQ, __popc(m_walk)); }
-                    if (m_work) { base_work = atomicAdd(counters + C_WORK, __popc(m_work)); }
-                }
-                base_walk = __shfl_sync(0xFFFFFFFFu, base_walk, 0); base_work = __shfl_sync(0xFFFFFFFFu, base_work, 0);
-                if (route == 3u) {
-                    const uint32_t at = base_walk + __popc(m_walk & ((1u << lane) - 1u));
-                    if (at < f.walk_cap) {
-                        uint2 *q = reinterpret_cast<uint2 *>(queue + at);
+            }
+        }
+        uint32_t incl = c_walk | (c_work << 16);   // both counts in one word (at most 2048 each per batch)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
+        if (lane == 31) { sh.wsum[tid >> 5] = incl; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int wv = 0; wv < 8; wv++) { const uint32_t c = sh.wsum[wv]; sh.wsum[wv] = run; run += c; }
+            const uint32_t n_walk = run & 0xFFFFu, n_work = run >> 16;
+            sh.base_walk = n_walk ? atomicAdd(counters + C_WALKQ, n_walk) : 0u;
+            sh.base_work = n_work ? atomicAdd(counters + C_WORK, n_work) : 0u;
+        }
+        __syncthreads();
+        if (codes) {
+            const uint32_t excl = sh.wsum[tid >> 5] + incl - (c_walk | (c_work << 16));
+            uint32_t at_walk = sh.base_walk + (excl & 0xFFFFu), at_work = sh.base_work + (excl >> 16);
+#pragma unroll
+            for (int k = 0; k < TU; k++) {
+                const uint32_t code = (codes >> (2 * k)) & 3u;
+                if (code == 0u) { continue; }
+                const uint32_t j = t_begin + 256u * k + tid;
+                const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24;
+                const uint32_t item = j + sh.cdelta[slot];   // the original triangle index is the order key
+                if (code == 3u) {
+                    if (at_walk < f.walk_cap) {
+                        const uint32_t o = sh.ctab[slot] - v_begin;
+                        const float4 r0 = sh.rv[o + (w & 255u)], r1 = sh.rv[o + ((w >> 8) & 255u)], r2 = sh.rv[o + ((w >> 16) & 255u)];
+                        uint2 *q = reinterpret_cast<uint2 *>(queue + at_walk);
                         q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
                         q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
                         q[4] = make_uint2(__float_as_uint(r2.z), item);
                     }
-                } else if (route == 1u) {
-                    f.worklist[(size_t)view * f.T + base_work + __popc(m_work & ((1u << lane) - 1u))] = item;
+                    at_walk++;
+                } else {
+                    f.worklist[(size_t)view * f.T + at_work++] = item | (code == 2u ? ITEM_STRADDLE : 0u);
                 }
             }
         }
