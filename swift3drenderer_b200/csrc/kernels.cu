@@ -63,7 +63,12 @@ __device__ __forceinline__ float3 xform(const Cam &c, float x, float y, float z,
 // render.cpp:288 — (v.x, -v.y, 0) * factor / -v.z + (W/2, H/2, -v.z)
 __device__ __forceinline__ float3 project(float3 cv, float factor, float half_w, float half_h) {
     const float nz = -cv.z;
-    return make_float3(cv.x * factor / nz + half_w, -cv.y * factor / nz + half_h, 0.f * factor / nz + nz);
+    // the two quotients share one reciprocal refinement (exact_math.cuh: bit-identical to the `/` operator, checked on
+    // the device); the third component, 0 * factor / nz + nz, IS nz unless nz is zero (0 / 0): +-0 / nz is a zero for
+    // every other nz, infinities included, and x + (+-0) == x
+    float qx, qy;
+    div2_rn_signed(cv.x * factor, -cv.y * factor, nz, qx, qy);
+    return make_float3(qx + half_w, qy + half_h, nz != 0.f ? nz : 0.f * factor / nz + nz);
 }
 
 __device__ __forceinline__ float3 add3(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -716,15 +721,16 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
         // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
         // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
         // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
-        uint32_t x = 0;
-        while (x <= bw && !(w0 >= 0 && w1 >= 0 && w2 >= 0)) {
-            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);
-            x++;
-        }
-        for (; x <= bw && (w0 >= 0 && w1 >= 0 && w2 >= 0); x++) {
+        // (One loop for both parts: a warp's lanes are in different parts of their rows, and two loops cost it the longest
+        // lead-in plus the longest run.)
+        bool entered = false;
+        for (uint32_t x = 0; x <= bw; x++) {
+            const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+            if (entered && !inside) { break; }                                    // left the run: the rest of the row is outside
+            entered = inside;
             const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
             // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-            if (ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+            if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
             w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
         }
     }
@@ -814,7 +820,9 @@ struct FrontShared {
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
     uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
     uint32_t batch, first_alive, last_alive;
-    uint32_t wsum[8], base_walk, base_work;   // queue-space allocation: per-warp partial sums, the batch's reserved ranges
+    uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // triangles that passed the front tests: position in the batch's span | 0x8000 for a straddler
+    uint32_t n_cand;
+    uint32_t wsum[8], base_walk, base_work;   // queue-space allocation: per-warp partial sums, the round's reserved ranges
     uint32_t stats[4];
 };
 
@@ -993,70 +1001,83 @@ __global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- 3. front tests and routing, one thread per triangle word.  Pass A decides where every triangle goes (2 bits
-        // each, kept in a register); one block-wide scan and ONE global atomic per counter and batch reserve the queue
-        // space (a warp-level atomic per iteration made the two counters the hottest addresses of the frame); pass B
-        // gathers the corners again from shared memory and writes the records.
+        // ---- 3. front tests, one thread per triangle word; the ~20 % that pass are compacted into a shared-memory list ------
         constexpr int TU = (CL_BATCH * CL_MAX_TRIS) / 256;
-        uint32_t codes = 0, c_walk = 0, c_work = 0;   // code: 1 larger box -> K2b, 2 straddler -> K2b, 3 direct walk
-#pragma unroll
-        for (int k = 0; k < TU; k++) {
-            const uint32_t j = t_begin + 256u * k + tid;
-            if (j < t_end) {
-                const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
-                if (base != CL_DEAD) {
-                    const uint32_t o = base - v_begin;
-                    const float4 r0 = sh.rv[o + (w & 255u)], r1 = sh.rv[o + ((w >> 8) & 255u)], r2 = sh.rv[o + ((w >> 16) & 255u)];
-                    const uint32_t cand = front_test(f, r0, r1, r2, n);
-                    uint32_t code = 0;
-                    if (cand == 2u) { code = 2u; }
-                    else if (cand == 1u) {
-                        code = route_candidate(f, r0, r1, r2).route;
-                        if (code == 0u) { n.n_cull++; }
-                    }
-                    codes |= code << (2 * k);
-                    c_walk += code == 3u ? 1u : 0u; c_work += (code == 1u || code == 2u) ? 1u : 0u;
-                }
-            }
-        }
-        uint32_t incl = c_walk | (c_work << 16);   // both counts in one word (at most 2048 each per batch)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
-        if (lane == 31) { sh.wsum[tid >> 5] = incl; }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int wv = 0; wv < 8; wv++) { const uint32_t c = sh.wsum[wv]; sh.wsum[wv] = run; run += c; }
-            const uint32_t n_walk = run & 0xFFFFu, n_work = run >> 16;
-            sh.base_walk = n_walk ? atomicAdd(counters + C_WALKQ, n_walk) : 0u;
-            sh.base_work = n_work ? atomicAdd(counters + C_WORK, n_work) : 0u;
-        }
-        __syncthreads();
-        if (codes) {
-            const uint32_t excl = sh.wsum[tid >> 5] + incl - (c_walk | (c_work << 16));
-            uint32_t at_walk = sh.base_walk + (excl & 0xFFFFu), at_work = sh.base_work + (excl >> 16);
+        {
+            uint32_t flags = 0, mine = 0;   // 2 bits per triangle: 1 candidate, 2 candidate that straddles the near plane
 #pragma unroll
             for (int k = 0; k < TU; k++) {
-                const uint32_t code = (codes >> (2 * k)) & 3u;
-                if (code == 0u) { continue; }
                 const uint32_t j = t_begin + 256u * k + tid;
-                const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24;
-                const uint32_t item = j + sh.cdelta[slot];   // the original triangle index is the order key
-                if (code == 3u) {
-                    if (at_walk < f.walk_cap) {
-                        const uint32_t o = sh.ctab[slot] - v_begin;
-                        const float4 r0 = sh.rv[o + (w & 255u)], r1 = sh.rv[o + ((w >> 8) & 255u)], r2 = sh.rv[o + ((w >> 16) & 255u)];
-                        uint2 *q = reinterpret_cast<uint2 *>(queue + at_walk);
-                        q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
-                        q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
-                        q[4] = make_uint2(__float_as_uint(r2.z), item);
+                if (j < t_end) {
+                    const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
+                    if (base != CL_DEAD) {
+                        const uint32_t o = base - v_begin;
+                        const uint32_t cand = front_test(f, sh.rv[o + (w & 255u)], sh.rv[o + ((w >> 8) & 255u)], sh.rv[o + ((w >> 16) & 255u)], n);
+                        flags |= cand << (2 * k);
+                        mine += cand != 0u ? 1u : 0u;
                     }
-                    at_walk++;
-                } else {
-                    f.worklist[(size_t)view * f.T + at_work++] = item | (code == 2u ? ITEM_STRADDLE : 0u);
                 }
             }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
+            if (lane == 31) { sh.wsum[tid >> 5] = incl; }
+            __syncthreads();
+            uint32_t at = incl - mine;
+#pragma unroll
+            for (int wv = 0; wv < 8; wv++) { if ((uint32_t)wv < (tid >> 5)) { at += sh.wsum[wv]; } }
+            if (tid == 255) { sh.n_cand = at + mine; }
+#pragma unroll
+            for (int k = 0; k < TU; k++) {
+                const uint32_t c = (flags >> (2 * k)) & 3u;
+                if (c) { sh.cand[at++] = (uint16_t)((256u * k + tid) | (c == 2u ? 0x8000u : 0u)); }
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. routing of the candidates, densely packed: exact box, row ownership; one block scan and ONE global atomic per
+        // counter and batch reserve the queue space (a warp-level atomic per iteration made the two counters the hottest
+        // addresses of the frame); then the records (direct walk) and work items (K2b) are written ---------------------------
+        const uint32_t n_cand = sh.n_cand;
+        for (uint32_t cb = 0; cb < n_cand; cb += 256u) {
+            uint32_t code = 0, item = 0;   // code: 1 work item for K2b, 3 direct walk
+            float4 r0, r1, r2;
+            if (cb + tid < n_cand) {
+                const uint32_t e = sh.cand[cb + tid], j = t_begin + (e & 0x7FFFu);
+                const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, o = sh.ctab[slot] - v_begin;
+                item = j + sh.cdelta[slot];   // the original triangle index is the order key
+                if (e & 0x8000u) { code = 1u; item |= ITEM_STRADDLE; }
+                else {
+                    r0 = sh.rv[o + (w & 255u)]; r1 = sh.rv[o + ((w >> 8) & 255u)]; r2 = sh.rv[o + ((w >> 16) & 255u)];
+                    code = route_candidate(f, r0, r1, r2).route;
+                    if (code == 0u) { n.n_cull++; }
+                }
+            }
+            const uint32_t m_walk = __ballot_sync(0xFFFFFFFFu, code == 3u), m_work = __ballot_sync(0xFFFFFFFFu, code == 1u);
+            if (lane == 0) { sh.wsum[tid >> 5] = (uint32_t)__popc(m_walk) | ((uint32_t)__popc(m_work) << 16); }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int wv = 0; wv < 8; wv++) { const uint32_t c = sh.wsum[wv]; sh.wsum[wv] = run; run += c; }
+                const uint32_t n_walk = run & 0xFFFFu, n_work = run >> 16;
+                sh.base_walk = n_walk ? atomicAdd(counters + C_WALKQ, n_walk) : 0u;
+                sh.base_work = n_work ? atomicAdd(counters + C_WORK, n_work) : 0u;
+            }
+            __syncthreads();
+            const uint32_t wbase = sh.wsum[tid >> 5];
+            if (code == 3u) {
+                const uint32_t at = sh.base_walk + (wbase & 0xFFFFu) + (uint32_t)__popc(m_walk & ((1u << lane) - 1u));
+                if (at < f.walk_cap) {
+                    uint2 *q = reinterpret_cast<uint2 *>(queue + at);
+                    q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
+                    q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
+                    q[4] = make_uint2(__float_as_uint(r2.z), item);
+                }
+            } else if (code == 1u) {
+                f.worklist[(size_t)view * f.T + sh.base_work + (wbase >> 16) + (uint32_t)__popc(m_work & ((1u << lane) - 1u))] = item;
+            }
+            __syncthreads();   // wsum / base_* are rewritten by the next round
         }
     }
     // statistics: one shared-memory atomic per warp, one global atomic per CTA and counter
@@ -2241,6 +2262,28 @@ __global__ void exact_math_kernel(uint32_t mode, unsigned long long lo, unsigned
             const uint32_t got = __float_as_uint(inv_sqrt_rn(x)), want = __float_as_uint(__frcp_rn(__fsqrt_rn(x)));
             if (got != want && !(got > 0x7f800000u && want > 0x7f800000u)) {
                 if (atomicAdd(result, 1ull) == 0ull) { result[1] = __float_as_uint(x); result[2] = got; result[3] = want; }
+            }
+        } else if (mode == 2) {
+            // div2_rn_signed: operands of either sign, zeros, extreme mantissas, exponents beyond the guarded range
+            uint32_t h = mix32((uint32_t)i ^ seed), g = mix32((uint32_t)(i >> 32) + h + 0x9e3779b9u);
+            uint32_t op[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                g = mix32(g + 0x85ebca6bu * (k + 1)); h = mix32(h ^ g);
+                uint32_t mant = g & 0x7FFFFFu;
+                const uint32_t sel = (h >> 8) & 15u;
+                if (sel == 0) { mant = 0x7FFFFFu; } else if (sel == 1) { mant = 0u; } else if (sel == 2) { mant = 0x7FFFFEu; } else if (sel == 3) { mant = 1u; }
+                const uint32_t e = 127u - 62u + (h >> 24) % 124u;
+                op[k] = (e << 23) | mant | ((h & 1u) << 31);
+            }
+            if (((h >> 3) & 63u) == 0u) { op[(h >> 12) % 3u] &= 0x80000000u; }     // signed zeros take the fallback
+            const float a0 = __uint_as_float(op[0]), a1 = __uint_as_float(op[1]), b = __uint_as_float(op[2]);
+            float q0, q1;
+            div2_rn_signed(a0, a1, b, q0, q1);
+            const float w0 = a0 / b, w1 = a1 / b;
+            const bool ok = (__float_as_uint(q0) == __float_as_uint(w0) || (q0 != q0 && w0 != w0)) && (__float_as_uint(q1) == __float_as_uint(w1) || (q1 != q1 && w1 != w1));
+            if (!ok) {
+                if (atomicAdd(result, 1ull) == 0ull) { result[1] = op[0]; result[2] = op[2]; result[3] = __float_as_uint(q0); result[4] = __float_as_uint(w0); }
             }
         } else {
             uint32_t h = mix32((uint32_t)i ^ seed) , g = mix32((uint32_t)(i >> 32) + h + 0x9e3779b9u);

@@ -530,6 +530,9 @@ def test_exact_math_equals_ieee_operators(gpu_renderer):
     for seed in (1, 2):
         assert lib.s3r_debug_exact_math(h, 1, 0, 1 << 32, seed, res) == 0
         assert res[0] == 0, f"div: {res[0]} mismatches, first a={res[1]:08x} b={res[2]:08x} got={res[3]:08x} want={res[4]:08x}"
+    for seed in (3, 4):   # the vertex stage's two projections by one depth: operands of either sign, signed zeros
+        assert lib.s3r_debug_exact_math(h, 2, 0, 1 << 32, seed, res) == 0
+        assert res[0] == 0, f"signed div: {res[0]} mismatches, first a={res[1]:08x} b={res[2]:08x} got={res[3]:08x} want={res[4]:08x}"
 
 
 def _i420_reference(px):
