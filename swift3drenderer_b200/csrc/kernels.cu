@@ -819,10 +819,10 @@ struct FrontShared {
     uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in the cluster-vertex arrays, CL_DEAD = cluster skipped
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
     uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
-    uint32_t batch, first_alive, last_alive;
+    uint32_t first_alive, last_alive;
     uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // triangles that passed the front tests: position in the batch's span | 0x8000 for a straddler
     uint32_t n_cand;
-    uint32_t wsum[8], base_walk, base_work;   // queue-space allocation: per-warp partial sums, the round's reserved ranges
+    uint32_t wsum[8], base_walk;   // candidate compaction: per-warp partial sums; the batch's reserved range of the walk queue
     uint32_t stats[4];
 };
 
@@ -925,38 +925,54 @@ __global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame 
     }
 }
 
-__global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ Frame f) {
+#ifndef S3R_FRONT_CTAS
+#define S3R_FRONT_CTAS 4
+#endif
+constexpr uint32_t WALK_HOLE = 0xFFFFFFFFu;   // order key of a queue slot that holds no candidate
+
+// The front kernel is a chain of dependent memory round trips per batch (list entry -> headers -> vertices -> triangle
+// words -> queue space), so it is written to keep as few of them on the critical path as it can: batches are dealt
+// statically (no counter), the NEXT batch's headers are fetched while this one is processed, vertex positions, slot bytes
+// and the first triangle words are requested together, and the queue space for all of a batch's candidates is reserved by
+// one atomic whose result is only needed after the candidates have been packed.
+__global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __grid_constant__ Frame f) {
     __shared__ FrontShared sh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
     const Cam cam = load_cam(f, view);
     const ViewBounds vb = view_bounds(cam);
     uint32_t *counters = f.counters + view * C_COUNT;
     const uint32_t n_alive = counters[C_BATCHES];   // written by batch_cull
+    const uint32_t *list = f.batch_list + (size_t)view * f.n_batches;
     if (tid < 4) { sh.stats[tid] = 0; }
     FrontCounts n = {0u, 0u, 0u, 0u};
     WalkRecord *queue = f.walk_q + (size_t)view * f.walk_cap;
 
-    // persistent CTAs: batches are handed out by a counter
-    while (true) {
-        __syncthreads();   // the previous batch's shared-memory state is dead
-        if (tid == 0) {
-            const uint32_t i = atomicAdd(counters + C_BHEAD, 1u);
-            sh.batch = i < n_alive ? f.batch_list[(size_t)view * f.n_batches + i] : CL_DEAD;
-            sh.first_alive = CL_BATCH; sh.last_alive = 0;
+    // headers of the batch about to be processed (threads 0 .. CL_BATCH hold one cluster each; entry nc is the end marker)
+    uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0;
+    uint32_t h_next_toff = 0, c0 = 0, nc = 0;
+    auto fetch_headers = [&](uint32_t i) {
+        nc = 0;
+        if (i < n_alive) {
+            c0 = __ldg(list + i) * CL_BATCH; nc = min(CL_BATCH, f.n_clusters - c0);
+            if (tid <= nc) {
+                h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
+                if (tid < nc) { h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid)); h_next_toff = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w; }
+            }
         }
-        __syncthreads();
-        if (sh.batch == CL_DEAD) { break; }
-        const uint32_t c0 = sh.batch * CL_BATCH, nc = min(CL_BATCH, f.n_clusters - c0);
+    };
+    fetch_headers(blockIdx.x);
 
-        // ---- 1. cluster verdicts -----------------------------------------------------------------------------------
+    for (uint32_t i = blockIdx.x; i < n_alive; i += gridDim.x) {
+        // ---- 1. cluster verdicts (from the prefetched headers) -------------------------------------------------------
+        if (tid == 0) { sh.first_alive = CL_BATCH; sh.last_alive = 0; }
+        __syncthreads();   // (also: the previous batch's shared-memory state is dead)
+        const uint32_t my_nc = nc;
         if (tid <= CL_BATCH) {
             uint32_t alive = 0;
-            if (tid <= nc) {
-                const uint4 h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
+            if (tid <= my_nc) {
                 sh.voff[tid] = h1.z; sh.toff[tid] = h1.w;
-                if (tid < nc) {
-                    const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid));
-                    const uint32_t n_tris = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w - h1.w;
+                if (tid < my_nc) {
+                    const uint32_t n_tris = h_next_toff - h1.w;
                     const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
                                                                               __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
                     if (verdict == 0u) { alive = 1; }
@@ -975,44 +991,47 @@ __global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ 
             }
         }
         __syncthreads();
-        if (sh.first_alive == CL_BATCH) { continue; }   // nothing of this batch survives
+        fetch_headers(i + gridDim.x);   // the next batch's headers travel while this batch is processed
+        if (sh.first_alive == CL_BATCH) { continue; }   // nothing of this batch survives (uniform)
         // only the span of the surviving clusters is streamed
         const uint32_t v_begin = sh.voff[sh.first_alive], v_end = sh.voff[sh.last_alive + 1u];
         const uint32_t t_begin = sh.toff[sh.first_alive], t_end = sh.toff[sh.last_alive + 1u];
 
-        // ---- 2. vertex stage of the surviving clusters, into shared memory (loads first, then arithmetic) --------------
+        // ---- 2. vertex stage of the surviving clusters, into shared memory: every load of the span is requested at once
+        // (positions do not wait for the slot bytes), then the arithmetic ---------------------------------------------
+        constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256, TU = (CL_BATCH * CL_MAX_TRIS) / 256;
         {
-            constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256;
             float px[VU], py[VU], pz[VU];
-            bool live[VU];
+            uint32_t vs[VU];
 #pragma unroll
             for (int k = 0; k < VU; k++) {
                 const uint32_t j = v_begin + tid + 256u * k;
-                live[k] = j < v_end && sh.ctab[__ldg(f.cl_vslot + j)] != CL_DEAD;
-                if (live[k]) { px[k] = __ldg(f.cl_px + j); py[k] = __ldg(f.cl_py + j); pz[k] = __ldg(f.cl_pz + j); }
+                vs[k] = 0xFFFFFFFFu;
+                if (j < v_end) { vs[k] = __ldg(f.cl_vslot + j); px[k] = __ldg(f.cl_px + j); py[k] = __ldg(f.cl_py + j); pz[k] = __ldg(f.cl_pz + j); }
             }
 #pragma unroll
             for (int k = 0; k < VU; k++) {
-                if (live[k]) {
+                if (vs[k] != 0xFFFFFFFFu && sh.ctab[vs[k]] != CL_DEAD) {
                     const float3 r = project(xform(cam, px[k], py[k], pz[k], 1.0f), f.factor, f.half_w, f.half_h);
                     sh.rv[tid + 256u * k] = make_float4(r.x, r.y, r.z, 0.f);
                 }
             }
         }
+        uint32_t w[TU];   // this thread's triangle words: requested before the barrier, used after it
+#pragma unroll
+        for (int k = 0; k < TU; k++) { const uint32_t j = t_begin + 256u * k + tid; w[k] = j < t_end ? __ldg(f.cl_tri + j) : 0xFFFFFFFFu; }
         __syncthreads();
 
         // ---- 3. front tests, one thread per triangle word; the ~20 % that pass are compacted into a shared-memory list ------
-        constexpr int TU = (CL_BATCH * CL_MAX_TRIS) / 256;
         {
             uint32_t flags = 0, mine = 0;   // 2 bits per triangle: 1 candidate, 2 candidate that straddles the near plane
 #pragma unroll
             for (int k = 0; k < TU; k++) {
-                const uint32_t j = t_begin + 256u * k + tid;
-                if (j < t_end) {
-                    const uint32_t w = __ldg(f.cl_tri + j), base = sh.ctab[w >> 24];
+                if (t_begin + 256u * k + tid < t_end) {
+                    const uint32_t base = sh.ctab[w[k] >> 24];
                     if (base != CL_DEAD) {
                         const uint32_t o = base - v_begin;
-                        const uint32_t cand = front_test(f, sh.rv[o + (w & 255u)], sh.rv[o + ((w >> 8) & 255u)], sh.rv[o + ((w >> 16) & 255u)], n);
+                        const uint32_t cand = front_test(f, sh.rv[o + (w[k] & 255u)], sh.rv[o + ((w[k] >> 8) & 255u)], sh.rv[o + ((w[k] >> 16) & 255u)], n);
                         flags |= cand << (2 * k);
                         mine += cand != 0u ? 1u : 0u;
                     }
@@ -1026,7 +1045,14 @@ __global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ 
             uint32_t at = incl - mine;
 #pragma unroll
             for (int wv = 0; wv < 8; wv++) { if ((uint32_t)wv < (tid >> 5)) { at += sh.wsum[wv]; } }
-            if (tid == 255) { sh.n_cand = at + mine; }
+            if (tid == 255) {
+                // queue space for ALL of the batch's candidates in one go: the few that turn out to be work items of K2b, or
+                // to own no row here, leave a hole (a record with the order key WALK_HOLE) — the reply is needed after the
+                // next barrier only
+                const uint32_t total = at + mine;
+                sh.n_cand = total;
+                sh.base_walk = total ? atomicAdd(counters + C_WALKQ, total) : 0u;
+            }
 #pragma unroll
             for (int k = 0; k < TU; k++) {
                 const uint32_t c = (flags >> (2 * k)) & 3u;
@@ -1035,49 +1061,36 @@ __global__ void __launch_bounds__(256, 5) cluster_front(const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- 4. routing of the candidates, densely packed: exact box, row ownership; one block scan and ONE global atomic per
-        // counter and batch reserve the queue space (a warp-level atomic per iteration made the two counters the hottest
-        // addresses of the frame); then the records (direct walk) and work items (K2b) are written ---------------------------
-        const uint32_t n_cand = sh.n_cand;
-        for (uint32_t cb = 0; cb < n_cand; cb += 256u) {
+        // ---- 4. routing of the candidates, densely packed: exact box, row ownership, then the record (direct walk) or the
+        // work item (K2b: straddlers and larger boxes, one warp-level atomic when a warp has any) ------------------------
+        const uint32_t n_cand = sh.n_cand, base_walk = sh.base_walk;
+        for (uint32_t cb = tid; cb < ((n_cand + 31u) & ~31u); cb += 256u) {   // (whole warps: the ballot below)
             uint32_t code = 0, item = 0;   // code: 1 work item for K2b, 3 direct walk
-            float4 r0, r1, r2;
-            if (cb + tid < n_cand) {
-                const uint32_t e = sh.cand[cb + tid], j = t_begin + (e & 0x7FFFu);
-                const uint32_t w = __ldg(f.cl_tri + j), slot = w >> 24, o = sh.ctab[slot] - v_begin;
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+            if (cb < n_cand) {
+                const uint32_t e = sh.cand[cb], j = t_begin + (e & 0x7FFFu);
+                const uint32_t tw = __ldg(f.cl_tri + j), slot = tw >> 24, o = sh.ctab[slot] - v_begin;
                 item = j + sh.cdelta[slot];   // the original triangle index is the order key
                 if (e & 0x8000u) { code = 1u; item |= ITEM_STRADDLE; }
                 else {
-                    r0 = sh.rv[o + (w & 255u)]; r1 = sh.rv[o + ((w >> 8) & 255u)]; r2 = sh.rv[o + ((w >> 16) & 255u)];
+                    r0 = sh.rv[o + (tw & 255u)]; r1 = sh.rv[o + ((tw >> 8) & 255u)]; r2 = sh.rv[o + ((tw >> 16) & 255u)];
                     code = route_candidate(f, r0, r1, r2).route;
                     if (code == 0u) { n.n_cull++; }
                 }
-            }
-            const uint32_t m_walk = __ballot_sync(0xFFFFFFFFu, code == 3u), m_work = __ballot_sync(0xFFFFFFFFu, code == 1u);
-            if (lane == 0) { sh.wsum[tid >> 5] = (uint32_t)__popc(m_walk) | ((uint32_t)__popc(m_work) << 16); }
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t run = 0;
-#pragma unroll
-                for (int wv = 0; wv < 8; wv++) { const uint32_t c = sh.wsum[wv]; sh.wsum[wv] = run; run += c; }
-                const uint32_t n_walk = run & 0xFFFFu, n_work = run >> 16;
-                sh.base_walk = n_walk ? atomicAdd(counters + C_WALKQ, n_walk) : 0u;
-                sh.base_work = n_work ? atomicAdd(counters + C_WORK, n_work) : 0u;
-            }
-            __syncthreads();
-            const uint32_t wbase = sh.wsum[tid >> 5];
-            if (code == 3u) {
-                const uint32_t at = sh.base_walk + (wbase & 0xFFFFu) + (uint32_t)__popc(m_walk & ((1u << lane) - 1u));
-                if (at < f.walk_cap) {
-                    uint2 *q = reinterpret_cast<uint2 *>(queue + at);
+                if (base_walk + cb < f.walk_cap) {
+                    uint2 *q = reinterpret_cast<uint2 *>(queue + base_walk + cb);
                     q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
                     q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
-                    q[4] = make_uint2(__float_as_uint(r2.z), item);
+                    q[4] = make_uint2(__float_as_uint(r2.z), code == 3u ? item : WALK_HOLE);
                 }
-            } else if (code == 1u) {
-                f.worklist[(size_t)view * f.T + sh.base_work + (wbase >> 16) + (uint32_t)__popc(m_work & ((1u << lane) - 1u))] = item;
             }
-            __syncthreads();   // wsum / base_* are rewritten by the next round
+            const uint32_t m_work = __ballot_sync(0xFFFFFFFFu, code == 1u);
+            if (m_work) {
+                uint32_t base_work = 0;
+                if (lane == 0) { base_work = atomicAdd(counters + C_WORK, __popc(m_work)); }
+                base_work = __shfl_sync(0xFFFFFFFFu, base_work, 0);
+                if (code == 1u) { f.worklist[(size_t)view * f.T + base_work + (uint32_t)__popc(m_work & ((1u << lane) - 1u))] = item; }
+            }
         }
     }
     // statistics: one shared-memory atomic per warp, one global atomic per CTA and counter
@@ -1113,7 +1126,7 @@ __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Fr
         __syncthreads();
         const uint32_t base = s_round * 256u;
         if (base >= n_q) { break; }
-        const bool valid = base + tid < n_q;
+        bool valid = base + tid < n_q;
         uint32_t item = 0;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
         if (valid) {
@@ -1123,6 +1136,7 @@ __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Fr
             r1 = make_float4(__uint_as_float(b.y), __uint_as_float(c.x), __uint_as_float(c.y), 0.f);
             r2 = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(e.x), 0.f);
             item = e.y;
+            valid = item != WALK_HOLE;   // a slot reserved for a candidate that went elsewhere
         }
         walk_round(f, view, wsh, n, valid, item, r0, r1, r2);
     }
@@ -2191,7 +2205,7 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
-        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * 5u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
+        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
         direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");
     } else {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
