@@ -819,7 +819,8 @@ struct FrontShared {
     uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in the cluster-vertex arrays, CL_DEAD = cluster skipped
     uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
     uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
-    uint32_t first_alive, last_alive;
+    uint32_t first_alive, last_alive, n_alive_cl;
+    uint8_t alive_list[CL_BATCH];            // slots of the surviving clusters
     uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // triangles that passed the front tests: position in the batch's span | 0x8000 for a straddler
     uint32_t n_cand;
     uint32_t wsum[8], base_walk;   // candidate compaction: per-warp partial sums; the batch's reserved range of the walk queue
@@ -964,7 +965,7 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
 
     for (uint32_t i = blockIdx.x; i < n_alive; i += gridDim.x) {
         // ---- 1. cluster verdicts (from the prefetched headers) -------------------------------------------------------
-        if (tid == 0) { sh.first_alive = CL_BATCH; sh.last_alive = 0; }
+        if (tid == 0) { sh.first_alive = CL_BATCH; sh.last_alive = 0; sh.n_alive_cl = 0; sh.n_cand = 0; }
         __syncthreads();   // (also: the previous batch's shared-memory state is dead)
         const uint32_t my_nc = nc;
         if (tid <= CL_BATCH) {
@@ -982,12 +983,16 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
                     sh.cdelta[tid] = h1.y - h1.w;   // t0 - tri_off (mod 2^32)
                 }
             }
-            if (tid < CL_BATCH) {   // (warps 0 and 1: the alive clusters' slot range)
+            if (tid < CL_BATCH) {   // (warps 0 and 1: the alive clusters' slot range and their list)
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive != 0u);
+                uint32_t at = 0;
                 if (lane == 0 && m) {
                     atomicMin(&sh.first_alive, (tid & ~31u) + (uint32_t)__ffs((int)m) - 1u);
                     atomicMax(&sh.last_alive, (tid & ~31u) + 31u - (uint32_t)__clz((int)m));
+                    at = atomicAdd(&sh.n_alive_cl, (uint32_t)__popc(m));
                 }
+                at = __shfl_sync(0xFFFFFFFFu, at, 0);
+                if (alive) { sh.alive_list[at + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid; }
             }
         }
         __syncthreads();
@@ -997,9 +1002,42 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
         const uint32_t v_begin = sh.voff[sh.first_alive], v_end = sh.voff[sh.last_alive + 1u];
         const uint32_t t_begin = sh.toff[sh.first_alive], t_end = sh.toff[sh.last_alive + 1u];
 
+        constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256, TU = (CL_BATCH * CL_MAX_TRIS) / 256;
+        const uint32_t n_alive_cl = sh.n_alive_cl;
+        if (2u * n_alive_cl < sh.last_alive - sh.first_alive + 1u) {
+            // ---- SPARSE batch (a rank of a screen partition keeps a cluster here and there): nothing of the dead clusters is
+            // touched.  2'. vertex stage: half a warp per surviving cluster; 3'. front tests: a warp per surviving cluster,
+            // candidates appended to the list by one shared-memory atomic per warp ---------------------------------------
+            for (uint32_t a = tid >> 4; a < n_alive_cl; a += 16u) {
+                const uint32_t slot = sh.alive_list[a], v = tid & 15u, vo = sh.voff[slot];
+                if (v < sh.voff[slot + 1u] - vo) {
+                    const float3 r = project(xform(cam, __ldg(f.cl_px + vo + v), __ldg(f.cl_py + vo + v), __ldg(f.cl_pz + vo + v), 1.0f), f.factor, f.half_w, f.half_h);
+                    sh.rv[vo - v_begin + v] = make_float4(r.x, r.y, r.z, 0.f);
+                }
+            }
+            __syncthreads();
+            for (uint32_t a = tid >> 5; a < ((n_alive_cl + 7u) & ~7u); a += 8u) {
+                uint32_t cand = 0, pos_in_span = 0;
+                if (a < n_alive_cl) {
+                    const uint32_t slot = sh.alive_list[a], to = sh.toff[slot];
+                    if (lane < sh.toff[slot + 1u] - to) {
+                        const uint32_t tw = __ldg(f.cl_tri + to + lane), o = sh.voff[slot] - v_begin;
+                        cand = front_test(f, sh.rv[o + (tw & 255u)], sh.rv[o + ((tw >> 8) & 255u)], sh.rv[o + ((tw >> 16) & 255u)], n);
+                        pos_in_span = to - t_begin + lane;
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0u);
+                uint32_t at = 0;
+                if (lane == 0 && m) { at = atomicAdd(&sh.n_cand, (uint32_t)__popc(m)); }
+                at = __shfl_sync(0xFFFFFFFFu, at, 0);
+                if (cand) { sh.cand[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(pos_in_span | (cand == 2u ? 0x8000u : 0u)); }
+            }
+            __syncthreads();
+            if (tid == 255) { const uint32_t total = sh.n_cand; sh.base_walk = total ? atomicAdd(counters + C_WALKQ, total) : 0u; }
+            __syncthreads();
+        } else {
         // ---- 2. vertex stage of the surviving clusters, into shared memory: every load of the span is requested at once
         // (positions do not wait for the slot bytes), then the arithmetic ---------------------------------------------
-        constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256, TU = (CL_BATCH * CL_MAX_TRIS) / 256;
         {
             float px[VU], py[VU], pz[VU];
             uint32_t vs[VU];
@@ -1060,6 +1098,7 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
             }
         }
         __syncthreads();
+        }   // dense batch
 
         // ---- 4. routing of the candidates, densely packed: exact box, row ownership, then the record (direct walk) or the
         // work item (K2b: straddlers and larger boxes, one warp-level atomic when a warp has any) ------------------------

@@ -17,14 +17,25 @@ for opt in os.environ.get("S3R_OPTS", "").split(","):   # e.g. S3R_OPTS=clusters
 W, H = 3840, 2160
 world, phase = int(os.environ.get("C3_WORLD", "8")), int(os.environ.get("C3_PHASE", "3"))
 rows, _, _ = R.rows_layout(H, world, phase)
-out = torch.zeros((rows, W), dtype=torch.int32, device="cuda:0")
+out = torch.zeros((max(rows, H // world + 1), W), dtype=torch.int32, device="cuda:0")
+band = os.environ.get("C3_MODE", "rows") == "band"   # contiguous band [H * phase / world, H * (phase + 1) / world) instead of interleaved tile rows
+
+
+def frame(f):
+    if band:
+        r.render_device(mats[f], W, H, out.data_ptr(), y0=H * phase // world, y1=H * (phase + 1) // world)
+    else:
+        r.render_device_rows(mats[f], W, H, world, phase, out.data_ptr())
+
+
 for rep in range(3):
     for f in range(4):
-        r.render_device_rows(mats[f], W, H, world, phase, out.data_ptr())
+        frame(f)
     while r.finish():
         pass
 r.set_option("timing", 1); r.timing()
 for f in range(4):
-    r.render_device_rows(mats[f], W, H, world, phase, out.data_ptr())
+    frame(f)
 r.finish()
-print(r.timing(), r.stats())
+kt = r.kernel_timing()
+print({k: round(v["ms"] * 1e3 / max(v["launches"], 1), 1) for k, v in kt.items()}, r.timing(), r.stats())
