@@ -213,6 +213,9 @@ S3R_API void s3r_dropin_reset(void);
  * straight into the caller's buffer (registered on first sight; S3R_PIN_HOST=0: through pinned staging).  The call stays
  * synchronous and its result bit-identical.  S3R_DEVICE=<k> selects the GPU of the single-GPU drop-in. */
 S3R_API int s3r_dropin_devices(void);
+/* Harness-only: unregisters every caller buffer the drop-in has registered with CUDA (call before freeing frame buffers
+ * whose addresses the allocator may hand out again; the reference's main loop never frees its double buffer). */
+S3R_API void s3r_dropin_release_pins(void);
 
 #ifdef __cplusplus
 }

@@ -1470,6 +1470,20 @@ extern "C" void s3r_dropin_reset(void) {
     s3r_camera_reset(&g_camera);
 }
 
+// Harness-only: drops every registration of caller memory the drop-in holds (a harness that frees its frame buffers and
+// lets the allocator recycle their addresses must not leave them registered: the next registration of that range fails,
+// and a DMA through the stale one would land in pages nobody sees).  The next call registers again.
+extern "C" void s3r_dropin_release_pins(void) {
+    if (g_multi) {
+        cudaSetDevice(g_multi->w[0].r->device);
+        for (auto &p : g_multi->pins) { cudaHostUnregister(const_cast<void *>(p.ptr)); }
+        g_multi->pins.clear();
+    } else if (g_renderer) {
+        cudaSetDevice(g_renderer->device);
+        unpin_all(g_renderer);
+    }
+}
+
 // Harness-only: how many GPUs the drop-in renders on (0 before the first updateAndRender call).
 extern "C" int s3r_dropin_devices(void) {
     return g_multi ? (int)g_multi->w.size() : (g_renderer ? 1 : 0);

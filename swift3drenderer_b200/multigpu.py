@@ -153,7 +153,8 @@ class PeerFrames:
         if guard is not None:
             ext.wait_event(guard)
         self.r.set_peer_frames(self.destinations(slot))
-        self.r.render_device_rows(camera, self.width, self.height, self.world, self.rank, 0, stream=ext.cuda_stream)
+        # (handle 0 would mean "the renderer's own stream" to the C ABI: torch's default stream is CUDA's legacy stream, handle 1)
+        self.r.render_device_rows(camera, self.width, self.height, self.world, self.rank, 0, stream=ext.cuda_stream or 1)
         self.r.set_peer_frames([])
         self._rendered.record(ext)
         self._pending = True

@@ -72,7 +72,7 @@ EXPORTS = [
     "s3r_dump_setups", "s3r_kernel_launches", "s3r_set_option", "s3r_get_timing",
     "s3r_dropin_reset", "s3r_debug_walk", "s3r_debug_exact_math", "s3r_render_device_rows", "s3r_tile_height",
     "s3r_peer_frame_alloc", "s3r_peer_frame_open", "s3r_peer_frame_release", "s3r_set_peer_frames", "s3r_copy_from_device",
-    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing", "s3r_debug_clusters", "s3r_dropin_devices",
+    "s3r_sink_open", "s3r_sink_submit", "s3r_sink_close", "s3r_debug_band_edges", "s3r_get_kernel_timing", "s3r_debug_clusters", "s3r_dropin_devices", "s3r_dropin_release_pins",
 ]
 
 
@@ -448,4 +448,9 @@ class DropIn:
         self._lib.s3r_dropin_reset()
 
     def close(self) -> None:
+        """Releases the library's registrations of caller memory (the library itself stays loaded, like the reference)."""
+        try:
+            self._lib.s3r_dropin_release_pins()
+        except AttributeError:
+            pass
         shutil.rmtree(self._dir, ignore_errors=True)
