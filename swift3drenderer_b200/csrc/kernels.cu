@@ -812,19 +812,13 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
 //   4. the candidates' coverage setup and direct walk (walk_candidates), exactly as in triangle_classify.
 // Every skipped triangle is proven rejected by the reference's own per-triangle tests, so the frame cannot change.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t CL_DEAD = 0xFFFFFFFFu;
+constexpr uint32_t FRONT_GROUP = 4;                                  // clusters a warp of the front kernel takes at a time
+constexpr uint32_t FRONT_VERTS = FRONT_GROUP * CL_MAX_VERTS;         // <= 64 vertices ...
+constexpr uint32_t FRONT_TRIS = FRONT_GROUP * CL_MAX_TRIS;           // ... and <= 128 triangles per group
 
-struct FrontShared {
-    float4 rv[CL_BATCH * CL_MAX_VERTS];      // raster-space vertices of the batch's surviving clusters
-    uint32_t ctab[CL_BATCH];                 // first vertex of the cluster in the cluster-vertex arrays, CL_DEAD = cluster skipped
-    uint32_t cdelta[CL_BATCH];               // original triangle index minus position in the triangle-word array
-    uint32_t voff[CL_BATCH + 1], toff[CL_BATCH + 1];   // the batch's header offsets (entry nc: the end)
-    uint32_t first_alive, last_alive, n_alive_cl;
-    uint8_t alive_list[CL_BATCH];            // slots of the surviving clusters
-    uint16_t cand[CL_BATCH * CL_MAX_TRIS];   // triangles that passed the front tests: position in the batch's span | 0x8000 for a straddler
-    uint32_t n_cand;
-    uint32_t wsum[8], base_walk;   // candidate compaction: per-warp partial sums; the batch's reserved range of the walk queue
-    uint32_t stats[4];
+struct FrontWarp {                       // a warp's private staging: nothing in the front kernel crosses warps
+    float4 rv[FRONT_VERTS];              // raster-space vertices of the group's clusters
+    uint16_t cand[FRONT_TRIS];           // triangles that passed the front tests: position in the group | 0x8000 for a straddler
 };
 
 // One candidate of the direct walk as the front kernel hands it to the walk kernel through HBM: the three raster-space
@@ -930,200 +924,190 @@ __global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame 
 #define S3R_FRONT_CTAS 4
 #endif
 constexpr uint32_t WALK_HOLE = 0xFFFFFFFFu;   // order key of a queue slot that holds no candidate
+constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front kernel reserves at a time
 
-// The front kernel is a chain of dependent memory round trips per batch (list entry -> headers -> vertices -> triangle
-// words -> queue space), so it is written to keep as few of them on the critical path as it can: batches are dealt
-// statically (no counter), the NEXT batch's headers are fetched while this one is processed, vertex positions, slot bytes
-// and the first triangle words are requested together, and the queue space for all of a batch's candidates is reserved by
-// one atomic whose result is only needed after the candidates have been packed.
-__global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __grid_constant__ Frame f) {
-    __shared__ FrontShared sh;
-    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+// Cluster-level rejection: one thread per cluster of the batches that survived batch_cull.  Surviving clusters are appended
+// to a compact list as {first vertex, first triangle word, original index of the first triangle, vertices | triangles << 16}
+// — everything the front kernel needs, so it never reads a header; the triangles of rejected clusters are accounted for
+// here (near-rejected or culled, what the reference's per-triangle tests would have said).  The front kernel's work is
+// then proportional to what may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.
+__global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
+    __shared__ uint32_t s_wsum[8], s_base;
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Cam cam = load_cam(f, view);
     const ViewBounds vb = view_bounds(cam);
     uint32_t *counters = f.counters + view * C_COUNT;
-    const uint32_t n_alive = counters[C_BATCHES];   // written by batch_cull
-    const uint32_t *list = f.batch_list + (size_t)view * f.n_batches;
-    if (tid < 4) { sh.stats[tid] = 0; }
-    FrontCounts n = {0u, 0u, 0u, 0u};
+    const uint32_t n_alive_b = counters[C_BATCHES];   // written by batch_cull
+    const uint32_t bi = blockIdx.x * 4u + (tid >> 6);   // four batches of CL_BATCH = 64 clusters per CTA
+    static_assert(CL_BATCH == 64, "cluster_cull maps 64 threads to a batch");
+    uint32_t verdict = 3u, n_tris = 0;   // 3: no cluster
+    uint4 entry = make_uint4(0u, 0u, 0u, 0u);
+    if (bi < n_alive_b) {
+        const uint32_t c = __ldg(f.batch_list + (size_t)view * f.n_batches + bi) * CL_BATCH + (tid & 63u);
+        if (c < f.n_clusters) {
+            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)c), h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1), nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3);
+            n_tris = nx.w - h1.w;
+            entry = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
+            verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
+                                                       __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
+    if (lane == 0) { s_wsum[warp] = (uint32_t)__popc(m); }
+    const uint32_t near = __reduce_add_sync(0xFFFFFFFFu, verdict == 1u ? n_tris : 0u), cull = __reduce_add_sync(0xFFFFFFFFu, verdict == 2u ? n_tris : 0u);
+    if (lane == 0) {
+        if (near) { atomicAdd(counters + C_NEAR, near); }
+        if (cull) { atomicAdd(counters + C_CULLED, cull); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_wsum[w]; s_wsum[w] = run; run += c; }
+        s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;
+    }
+    __syncthreads();
+    if (verdict == 0u) { f.cluster_list[(size_t)view * f.n_clusters + s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = entry; }
+}
+
+// K1 + the front of K2a over the surviving clusters, one WARP per group of FRONT_GROUP clusters and no block-wide step
+// anywhere: a warp's chain of dependent loads (list entries -> vertices and triangle words -> queue space) overlaps with
+// those of the 31 other warps of its SM partition, and the next group's list entries are fetched while this one is processed.
+//   1. the group's vertices, densely over the lanes (the owner of a flat index is found with three compares): vertex stage
+//      (render.cpp:285-289) into the warp's shared-memory staging — raster-space vertices never travel to HBM;
+//   2. the front tests (render.cpp:306-317), densely over the group's triangle words; candidates are packed into a list;
+//   3. the candidates, densely: exact box and row ownership; a 40-byte record for the direct walk into queue space the warp
+//      reserves WALK_CHUNK slots at a time (one global atomic per chunk; what is left of a chunk is padded with holes),
+//      or a work item for K2b (straddlers and larger boxes).
+__global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __grid_constant__ Frame f) {
+    __shared__ FrontWarp sh_all[8];
+    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    FrontWarp &sh = sh_all[tid >> 5];
+    const Cam cam = load_cam(f, view);
+    uint32_t *counters = f.counters + view * C_COUNT;
+    const uint32_t n_cl = counters[C_CLUSTERS];   // written by cluster_cull
+    const uint4 *list = f.cluster_list + (size_t)view * f.n_clusters;
     WalkRecord *queue = f.walk_q + (size_t)view * f.walk_cap;
+    FrontCounts n = {0u, 0u, 0u, 0u};
+    uint32_t q_pos = 0, q_end = 0;   // the warp's reserved queue range [q_pos, q_end) (uniform over the lanes)
+    const uint32_t n_groups = (n_cl + FRONT_GROUP - 1u) / FRONT_GROUP, warps = gridDim.x * 8u;
+    uint32_t g = blockIdx.x * 8u + (tid >> 5);
+    // lanes 0 .. FRONT_GROUP - 1 hold the list entries of the group's clusters
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (g < n_groups && lane < FRONT_GROUP && g * FRONT_GROUP + lane < n_cl) { e = __ldg(list + g * FRONT_GROUP + lane); }
 
-    // headers of the batch about to be processed (threads 0 .. CL_BATCH hold one cluster each; entry nc is the end marker)
-    uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0;
-    uint32_t h_next_toff = 0, c0 = 0, nc = 0;
-    auto fetch_headers = [&](uint32_t i) {
-        nc = 0;
-        if (i < n_alive) {
-            c0 = __ldg(list + i) * CL_BATCH; nc = min(CL_BATCH, f.n_clusters - c0);
-            if (tid <= nc) {
-                h1 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid) + 1);
-                if (tid < nc) { h0 = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid)); h_next_toff = __ldg(f.cl_hdr + 2 * (size_t)(c0 + tid + 1) + 1).w; }
+    for (; g < n_groups; g += warps) {
+        // the group's layout: exclusive prefix sums of the clusters' vertex and triangle counts (lanes >= FRONT_GROUP hold zeros)
+        const uint32_t nv = e.w & 0xFFFFu, nt = e.w >> 16;
+        uint32_t vpre = nv, tpre = nt;
+#pragma unroll
+        for (int d = 1; d < (int)FRONT_GROUP; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, vpre, d), b = __shfl_up_sync(0xFFFFFFFFu, tpre, d);
+            if (lane >= (uint32_t)d) { vpre += a; tpre += b; }
+        }
+        const uint32_t v_tot = __shfl_sync(0xFFFFFFFFu, vpre, FRONT_GROUP - 1), t_tot = __shfl_sync(0xFFFFFFFFu, tpre, FRONT_GROUP - 1);
+        vpre -= nv; tpre -= nt;   // exclusive
+        uint32_t vstart[FRONT_GROUP], tstart[FRONT_GROUP], voff[FRONT_GROUP], toff[FRONT_GROUP], t0[FRONT_GROUP];
+#pragma unroll
+        for (int k = 0; k < (int)FRONT_GROUP; k++) {
+            vstart[k] = __shfl_sync(0xFFFFFFFFu, vpre, k); tstart[k] = __shfl_sync(0xFFFFFFFFu, tpre, k);
+            voff[k] = __shfl_sync(0xFFFFFFFFu, e.x, k); toff[k] = __shfl_sync(0xFFFFFFFFu, e.y, k); t0[k] = __shfl_sync(0xFFFFFFFFu, e.z, k);
+        }
+        // the next group's entries travel while this one is processed
+        const uint32_t g_next = g + warps;
+        e = make_uint4(0u, 0u, 0u, 0u);
+        if (g_next < n_groups && lane < FRONT_GROUP && g_next * FRONT_GROUP + lane < n_cl) { e = __ldg(list + g_next * FRONT_GROUP + lane); }
+
+        // owner of a flat index: three compares against the starts
+        auto owner = [&](uint32_t j, const uint32_t (&start)[FRONT_GROUP]) {
+            uint32_t k = 0;
+#pragma unroll
+            for (int q = 1; q < (int)FRONT_GROUP; q++) { k += j >= start[q] ? 1u : 0u; }
+            return k;
+        };
+        auto pick = [&](const uint32_t (&a)[FRONT_GROUP], uint32_t k) {
+            uint32_t r = a[0];
+#pragma unroll
+            for (int q = 1; q < (int)FRONT_GROUP; q++) { r = k == (uint32_t)q ? a[q] : r; }
+            return r;
+        };
+
+        // ---- 1. vertex stage, and the triangle words requested alongside -----------------------------------------------
+        constexpr int VP = FRONT_VERTS / 32, TP = FRONT_TRIS / 32;
+        float px[VP], py[VP], pz[VP];
+#pragma unroll
+        for (int p = 0; p < VP; p++) {
+            const uint32_t j = lane + 32u * p;
+            if (j < v_tot) { const uint32_t k = owner(j, vstart), at = pick(voff, k) + (j - pick(vstart, k)); px[p] = __ldg(f.cl_px + at); py[p] = __ldg(f.cl_py + at); pz[p] = __ldg(f.cl_pz + at); }
+        }
+        uint32_t tw[TP], tk[TP];
+#pragma unroll
+        for (int p = 0; p < TP; p++) {
+            const uint32_t j = lane + 32u * p;
+            tw[p] = 0u; tk[p] = 0u;
+            if (j < t_tot) { tk[p] = owner(j, tstart); tw[p] = __ldg(f.cl_tri + pick(toff, tk[p]) + (j - pick(tstart, tk[p]))); }
+        }
+#pragma unroll
+        for (int p = 0; p < VP; p++) {
+            const uint32_t j = lane + 32u * p;
+            if (j < v_tot) {
+                const float3 r = project(xform(cam, px[p], py[p], pz[p], 1.0f), f.factor, f.half_w, f.half_h);
+                sh.rv[j] = make_float4(r.x, r.y, r.z, 0.f);
             }
         }
-    };
-    fetch_headers(blockIdx.x);
+        __syncwarp();
 
-    for (uint32_t i = blockIdx.x; i < n_alive; i += gridDim.x) {
-        // ---- 1. cluster verdicts (from the prefetched headers) -------------------------------------------------------
-        if (tid == 0) { sh.first_alive = CL_BATCH; sh.last_alive = 0; sh.n_alive_cl = 0; sh.n_cand = 0; }
-        __syncthreads();   // (also: the previous batch's shared-memory state is dead)
-        const uint32_t my_nc = nc;
-        if (tid <= CL_BATCH) {
-            uint32_t alive = 0;
-            if (tid <= my_nc) {
-                sh.voff[tid] = h1.z; sh.toff[tid] = h1.w;
-                if (tid < my_nc) {
-                    const uint32_t n_tris = h_next_toff - h1.w;
-                    const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
-                                                                              __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
-                    if (verdict == 0u) { alive = 1; }
-                    else if (verdict == 1u) { n.n_near += n_tris; }
-                    else { n.n_cull += n_tris; }
-                    sh.ctab[tid] = alive ? h1.z : CL_DEAD;
-                    sh.cdelta[tid] = h1.y - h1.w;   // t0 - tri_off (mod 2^32)
-                }
+        // ---- 2. front tests; candidates packed into the warp's list ---------------------------------------------------------
+        uint32_t n_cand = 0;
+#pragma unroll
+        for (int p = 0; p < TP; p++) {
+            const uint32_t j = lane + 32u * p;
+            uint32_t cand = 0;
+            if (j < t_tot) {
+                const uint32_t o = pick(vstart, tk[p]);
+                cand = front_test(f, sh.rv[o + (tw[p] & 255u)], sh.rv[o + ((tw[p] >> 8) & 255u)], sh.rv[o + ((tw[p] >> 16) & 255u)], n);
             }
-            if (tid < CL_BATCH) {   // (warps 0 and 1: the alive clusters' slot range and their list)
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive != 0u);
-                uint32_t at = 0;
-                if (lane == 0 && m) {
-                    atomicMin(&sh.first_alive, (tid & ~31u) + (uint32_t)__ffs((int)m) - 1u);
-                    atomicMax(&sh.last_alive, (tid & ~31u) + 31u - (uint32_t)__clz((int)m));
-                    at = atomicAdd(&sh.n_alive_cl, (uint32_t)__popc(m));
-                }
-                at = __shfl_sync(0xFFFFFFFFu, at, 0);
-                if (alive) { sh.alive_list[at + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid; }
-            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0u);
+            if (cand) { sh.cand[n_cand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j | (cand == 2u ? 0x8000u : 0u)); }
+            n_cand += (uint32_t)__popc(m);
         }
-        __syncthreads();
-        fetch_headers(i + gridDim.x);   // the next batch's headers travel while this batch is processed
-        if (sh.first_alive == CL_BATCH) { continue; }   // nothing of this batch survives (uniform)
-        // only the span of the surviving clusters is streamed
-        const uint32_t v_begin = sh.voff[sh.first_alive], v_end = sh.voff[sh.last_alive + 1u];
-        const uint32_t t_begin = sh.toff[sh.first_alive], t_end = sh.toff[sh.last_alive + 1u];
+        __syncwarp();
 
-        constexpr int VU = (CL_BATCH * CL_MAX_VERTS) / 256, TU = (CL_BATCH * CL_MAX_TRIS) / 256;
-        const uint32_t n_alive_cl = sh.n_alive_cl;
-        if (2u * n_alive_cl < sh.last_alive - sh.first_alive + 1u) {
-            // ---- SPARSE batch (a rank of a screen partition keeps a cluster here and there): nothing of the dead clusters is
-            // touched.  2'. vertex stage: half a warp per surviving cluster; 3'. front tests: a warp per surviving cluster,
-            // candidates appended to the list by one shared-memory atomic per warp ---------------------------------------
-            for (uint32_t a = tid >> 4; a < n_alive_cl; a += 16u) {
-                const uint32_t slot = sh.alive_list[a], v = tid & 15u, vo = sh.voff[slot];
-                if (v < sh.voff[slot + 1u] - vo) {
-                    const float3 r = project(xform(cam, __ldg(f.cl_px + vo + v), __ldg(f.cl_py + vo + v), __ldg(f.cl_pz + vo + v), 1.0f), f.factor, f.half_w, f.half_h);
-                    sh.rv[vo - v_begin + v] = make_float4(r.x, r.y, r.z, 0.f);
-                }
-            }
-            __syncthreads();
-            for (uint32_t a = tid >> 5; a < ((n_alive_cl + 7u) & ~7u); a += 8u) {
-                uint32_t cand = 0, pos_in_span = 0;
-                if (a < n_alive_cl) {
-                    const uint32_t slot = sh.alive_list[a], to = sh.toff[slot];
-                    if (lane < sh.toff[slot + 1u] - to) {
-                        const uint32_t tw = __ldg(f.cl_tri + to + lane), o = sh.voff[slot] - v_begin;
-                        cand = front_test(f, sh.rv[o + (tw & 255u)], sh.rv[o + ((tw >> 8) & 255u)], sh.rv[o + ((tw >> 16) & 255u)], n);
-                        pos_in_span = to - t_begin + lane;
-                    }
-                }
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand != 0u);
-                uint32_t at = 0;
-                if (lane == 0 && m) { at = atomicAdd(&sh.n_cand, (uint32_t)__popc(m)); }
-                at = __shfl_sync(0xFFFFFFFFu, at, 0);
-                if (cand) { sh.cand[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(pos_in_span | (cand == 2u ? 0x8000u : 0u)); }
-            }
-            __syncthreads();
-            if (tid == 255) { const uint32_t total = sh.n_cand; sh.base_walk = total ? atomicAdd(counters + C_WALKQ, total) : 0u; }
-            __syncthreads();
-        } else {
-        // ---- 2. vertex stage of the surviving clusters, into shared memory: every load of the span is requested at once
-        // (positions do not wait for the slot bytes), then the arithmetic ---------------------------------------------
-        {
-            float px[VU], py[VU], pz[VU];
-            uint32_t vs[VU];
-#pragma unroll
-            for (int k = 0; k < VU; k++) {
-                const uint32_t j = v_begin + tid + 256u * k;
-                vs[k] = 0xFFFFFFFFu;
-                if (j < v_end) { vs[k] = __ldg(f.cl_vslot + j); px[k] = __ldg(f.cl_px + j); py[k] = __ldg(f.cl_py + j); pz[k] = __ldg(f.cl_pz + j); }
-            }
-#pragma unroll
-            for (int k = 0; k < VU; k++) {
-                if (vs[k] != 0xFFFFFFFFu && sh.ctab[vs[k]] != CL_DEAD) {
-                    const float3 r = project(xform(cam, px[k], py[k], pz[k], 1.0f), f.factor, f.half_w, f.half_h);
-                    sh.rv[tid + 256u * k] = make_float4(r.x, r.y, r.z, 0.f);
-                }
-            }
-        }
-        uint32_t w[TU];   // this thread's triangle words: requested before the barrier, used after it
-#pragma unroll
-        for (int k = 0; k < TU; k++) { const uint32_t j = t_begin + 256u * k + tid; w[k] = j < t_end ? __ldg(f.cl_tri + j) : 0xFFFFFFFFu; }
-        __syncthreads();
-
-        // ---- 3. front tests, one thread per triangle word; the ~20 % that pass are compacted into a shared-memory list ------
-        {
-            uint32_t flags = 0, mine = 0;   // 2 bits per triangle: 1 candidate, 2 candidate that straddles the near plane
-#pragma unroll
-            for (int k = 0; k < TU; k++) {
-                if (t_begin + 256u * k + tid < t_end) {
-                    const uint32_t base = sh.ctab[w[k] >> 24];
-                    if (base != CL_DEAD) {
-                        const uint32_t o = base - v_begin;
-                        const uint32_t cand = front_test(f, sh.rv[o + (w[k] & 255u)], sh.rv[o + ((w[k] >> 8) & 255u)], sh.rv[o + ((w[k] >> 16) & 255u)], n);
-                        flags |= cand << (2 * k);
-                        mine += cand != 0u ? 1u : 0u;
-                    }
-                }
-            }
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
-            if (lane == 31) { sh.wsum[tid >> 5] = incl; }
-            __syncthreads();
-            uint32_t at = incl - mine;
-#pragma unroll
-            for (int wv = 0; wv < 8; wv++) { if ((uint32_t)wv < (tid >> 5)) { at += sh.wsum[wv]; } }
-            if (tid == 255) {
-                // queue space for ALL of the batch's candidates in one go: the few that turn out to be work items of K2b, or
-                // to own no row here, leave a hole (a record with the order key WALK_HOLE) — the reply is needed after the
-                // next barrier only
-                const uint32_t total = at + mine;
-                sh.n_cand = total;
-                sh.base_walk = total ? atomicAdd(counters + C_WALKQ, total) : 0u;
-            }
-#pragma unroll
-            for (int k = 0; k < TU; k++) {
-                const uint32_t c = (flags >> (2 * k)) & 3u;
-                if (c) { sh.cand[at++] = (uint16_t)((256u * k + tid) | (c == 2u ? 0x8000u : 0u)); }
-            }
-        }
-        __syncthreads();
-        }   // dense batch
-
-        // ---- 4. routing of the candidates, densely packed: exact box, row ownership, then the record (direct walk) or the
-        // work item (K2b: straddlers and larger boxes, one warp-level atomic when a warp has any) ------------------------
-        const uint32_t n_cand = sh.n_cand, base_walk = sh.base_walk;
-        for (uint32_t cb = tid; cb < ((n_cand + 31u) & ~31u); cb += 256u) {   // (whole warps: the ballot below)
+        // ---- 3. routing of the candidates, densely ---------------------------------------------------------------------------
+        for (uint32_t cb = 0; cb < n_cand; cb += 32u) {
             uint32_t code = 0, item = 0;   // code: 1 work item for K2b, 3 direct walk
             float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-            if (cb < n_cand) {
-                const uint32_t e = sh.cand[cb], j = t_begin + (e & 0x7FFFu);
-                const uint32_t tw = __ldg(f.cl_tri + j), slot = tw >> 24, o = sh.ctab[slot] - v_begin;
-                item = j + sh.cdelta[slot];   // the original triangle index is the order key
-                if (e & 0x8000u) { code = 1u; item |= ITEM_STRADDLE; }
+            if (cb + lane < n_cand) {
+                const uint32_t c = sh.cand[cb + lane], j = c & 0x7FFFu, k = owner(j, tstart);
+                const uint32_t local = j - pick(tstart, k), w = __ldg(f.cl_tri + pick(toff, k) + local), o = pick(vstart, k);
+                item = pick(t0, k) + local;   // the original triangle index is the order key
+                if (c & 0x8000u) { code = 1u; item |= ITEM_STRADDLE; }
                 else {
-                    r0 = sh.rv[o + (tw & 255u)]; r1 = sh.rv[o + ((tw >> 8) & 255u)]; r2 = sh.rv[o + ((tw >> 16) & 255u)];
+                    r0 = sh.rv[o + (w & 255u)]; r1 = sh.rv[o + ((w >> 8) & 255u)]; r2 = sh.rv[o + ((w >> 16) & 255u)];
                     code = route_candidate(f, r0, r1, r2).route;
                     if (code == 0u) { n.n_cull++; }
                 }
-                if (base_walk + cb < f.walk_cap) {
-                    uint2 *q = reinterpret_cast<uint2 *>(queue + base_walk + cb);
-                    q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
-                    q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
-                    q[4] = make_uint2(__float_as_uint(r2.z), code == 3u ? item : WALK_HOLE);
-                }
             }
-            const uint32_t m_work = __ballot_sync(0xFFFFFFFFu, code == 1u);
+            const uint32_t m_walk = __ballot_sync(0xFFFFFFFFu, code == 3u), m_work = __ballot_sync(0xFFFFFFFFu, code == 1u);
+            const uint32_t n_walk = (uint32_t)__popc(m_walk);
+            if (n_walk) {
+                if (q_pos + n_walk > q_end) {   // (uniform) the chunk cannot take them: pad it with holes, reserve the next one
+                    for (uint32_t h = q_pos + lane; h < q_end; h += 32u) { if (h < f.walk_cap) { queue[h].order = WALK_HOLE; } }
+                    if (lane == 0) { q_pos = atomicAdd(counters + C_WALKQ, WALK_CHUNK); }
+                    q_pos = __shfl_sync(0xFFFFFFFFu, q_pos, 0);
+                    q_end = q_pos + WALK_CHUNK;
+                }
+                if (code == 3u) {
+                    const uint32_t at = q_pos + (uint32_t)__popc(m_walk & ((1u << lane) - 1u));
+                    if (at < f.walk_cap) {
+                        uint2 *q = reinterpret_cast<uint2 *>(queue + at);
+                        q[0] = make_uint2(__float_as_uint(r0.x), __float_as_uint(r0.y)); q[1] = make_uint2(__float_as_uint(r0.z), __float_as_uint(r1.x));
+                        q[2] = make_uint2(__float_as_uint(r1.y), __float_as_uint(r1.z)); q[3] = make_uint2(__float_as_uint(r2.x), __float_as_uint(r2.y));
+                        q[4] = make_uint2(__float_as_uint(r2.z), item);
+                    }
+                }
+                q_pos += n_walk;
+            }
             if (m_work) {
                 uint32_t base_work = 0;
                 if (lane == 0) { base_work = atomicAdd(counters + C_WORK, __popc(m_work)); }
@@ -1131,16 +1115,16 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
                 if (code == 1u) { f.worklist[(size_t)view * f.T + base_work + (uint32_t)__popc(m_work & ((1u << lane) - 1u))] = item; }
             }
         }
+        __syncwarp();   // the staging is rewritten by the next group
     }
-    // statistics: one shared-memory atomic per warp, one global atomic per CTA and counter
+    for (uint32_t h = q_pos + lane; h < q_end; h += 32u) { if (h < f.walk_cap) { queue[h].order = WALK_HOLE; } }   // the last chunk's rest
+    // statistics: one global atomic per warp and counter
     n.n_near = __reduce_add_sync(0xFFFFFFFFu, n.n_near); n.n_clip = __reduce_add_sync(0xFFFFFFFFu, n.n_clip); n.n_cull = __reduce_add_sync(0xFFFFFFFFu, n.n_cull);
     if (lane == 0) {
-        if (n.n_near) { atomicAdd(&sh.stats[0], n.n_near); }
-        if (n.n_clip) { atomicAdd(&sh.stats[1], n.n_clip); }
-        if (n.n_cull) { atomicAdd(&sh.stats[3], n.n_cull); }
+        if (n.n_near) { atomicAdd(counters + C_NEAR, n.n_near); }
+        if (n.n_clip) { atomicAdd(counters + C_CLIPPED, n.n_clip); }
+        if (n.n_cull) { atomicAdd(counters + C_CULLED, n.n_cull); }
     }
-    __syncthreads();
-    if (tid < 4 && tid != 2u && sh.stats[tid]) { atomicAdd(counters + C_NEAR + tid, sh.stats[tid]); }   // C_NEAR, C_CLIPPED, (-), C_CULLED
 }
 
 // The direct walk over the front kernel's candidate queue: persistent CTAs take rounds of 256 records — always full but
@@ -2244,7 +2228,8 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
-        cluster_front<<<dim3(max(1u, min(f.n_batches, (uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
+        cluster_cull<<<dim3(max(1u, ceil_div(f.n_batches, 4u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_cull");
+        cluster_front<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
         direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");
     } else {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");

@@ -69,7 +69,8 @@ enum Counter : uint32_t {
     C_BHEAD = 17,    // ... and how many of them the front kernel's persistent CTAs have taken
     C_WALKQ = 18,    // cluster front: candidates queued for the direct-walk kernel
     C_WALKHEAD = 19, // ... and how many rounds of 256 the walk kernel's persistent CTAs have taken
-    C_COUNT = 20
+    C_CLUSTERS = 20, // cluster front: clusters that survived the cluster-level rejection (cluster_cull)
+    C_COUNT = 24
 };
 
 struct __align__(16) SetupVis {     // 64 bytes: everything the coverage/depth walk needs
@@ -111,6 +112,7 @@ struct Frame {
     const uint32_t *cl_tri;
     const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
     uint32_t *batch_list;         // [views][n_batches] batches that survived batch_cull, in list order
+    uint4 *cluster_list;          // [views][n_clusters] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}
     uint32_t n_clusters, n_batches;
     struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)
     uint32_t walk_cap;

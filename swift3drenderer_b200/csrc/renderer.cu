@@ -81,6 +81,7 @@ struct S3RRenderer {
     DevBuf<uint32_t> cl_tri;
     DevBuf<float4> cl_batch;
     DevBuf<uint32_t> batch_list;
+    DevBuf<uint4> cluster_list;
     DevBuf<uint8_t> walk_q;            // candidate queue of the direct walk: 40-byte records (front kernel -> walk kernel)
     uint32_t walk_cap = 0;
     uint32_t n_clusters = 0, n_batches = 0;
@@ -204,7 +205,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release(); r->walk_q.release();
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release(); r->cluster_list.release(); r->walk_q.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -679,6 +680,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
         CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
+        CUDA_TRY(r->cluster_list.ensure((size_t)r->views_cap * r->n_clusters));
+        f.cluster_list = r->cluster_list.p;
         // candidates of the direct walk: a quarter of the triangles to begin with, regrown on overflow
         if (r->walk_cap == 0) { r->walk_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r->T, 1), std::max<uint64_t>(4096, r->T / 4)); }
         CUDA_TRY(r->walk_q.ensure((size_t)r->views_cap * r->walk_cap * 40u));
