@@ -161,8 +161,10 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
  *          "pack24" (1 = 24-bit pixel transport over PCIe for host renders, default), "host_bands" (raster/
  *          copy pipeline depth of host renders, default 8), "copy_threads" (staging -> caller copy workers),
  *          "setup_capacity" (test hook: shrink the survivor buffers to exercise regrowth),
- *          "clusters" (1 = general path: vertex stage + front tests + direct walk in one kernel over the load-time clusters,
- *          raster-space vertices in shared memory only, default; 0 = vertex_stage + triangle_classify over the raw stream),
+ *          "clusters" (general path front: 1 = over the load-time clusters — batch / cluster rejection, per-warp vertex stage and
+ *          front tests with raster-space vertices in shared memory only, direct walk from a candidate queue; 0 = vertex_stage +
+ *          triangle_classify over the raw stream; 2 (default) = clusters for partitioned submissions — bands, interleaved rows —
+ *          and the raw stream for whole frames),
  *          "cluster_cull" (1 = whole clusters are rejected by their bounds, default; 0 = every triangle is tested) */
 
 /* Test hook: out[i] = the device build of walk_jump(start[i], delta[i], steps[i]) — the exact result of

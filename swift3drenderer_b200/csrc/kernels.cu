@@ -579,7 +579,7 @@ struct WalkShared {
     uint32_t xy[256];                  // xmin | ymin << 16
     uint32_t bwrows[256];              // xmax - xmin | owned-row mask << 16
     uint32_t tri[256];                 // order key of the box's triangle
-    uint16_t items[256 * SMALL_MAX];   // parked slot | row << 8, grouped by box-width class
+    uint16_t items[256 * SMALL_MAX / 2]; // parked slot | pair number << 8 (a pair: owned rows i and i + half), grouped by box width
     uint32_t n_cand;
     uint32_t cls_count[SMALL_MAX];     // row items per box width (1 .. 16 pixels): a warp's items are equally wide
     uint32_t stats[4];                 // near-rejected, clipped, walked here, culled
@@ -678,9 +678,9 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
                     w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
                     if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
                 }
-                my_rows = b.rows;
+                my_rows = ((uint32_t)__popc(b.rows) + 1u) >> 1;   // work items: the owned rows in pairs (row i with row i + half)
                 my_cls = b.xmax - b.xmin;
-                my_off = atomicAdd(&wsh.cls_count[my_cls], (uint32_t)__popc(b.rows));
+                my_off = atomicAdd(&wsh.cls_count[my_cls], my_rows);
             }
         }
     }
@@ -697,41 +697,43 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
     for (uint32_t c = 0; c < SMALL_MAX; c++) { const uint32_t k = wsh.cls_count[c]; if (c < my_cls) { cls_base += k; } n_items += k; }
     if (route == 3) {
         uint32_t pos = my_off + cls_base;
-        while (my_rows) {   // one work item per owned box row
-            const uint32_t r = (uint32_t)__ffs((int)my_rows) - 1u;
-            my_rows &= my_rows - 1u;
-            wsh.items[pos++] = (uint16_t)(tid | (r << 8));
-        }
+        for (uint32_t i = 0; i < my_rows; i++) { wsh.items[pos++] = (uint16_t)(tid | (i << 8)); }
     }
     __syncthreads();
-    // the direct walk: one (triangle, row) item per thread and pass
+    // The direct walk: one work item per thread and pass.  An item is a PAIR of owned rows of one box, row i and row
+    // i + half: a triangle's rows are short at its tips and long in the middle, so the pairs' lengths are far more alike than
+    // the rows' (the lanes of a warp run in lockstep), and the box's parameters are fetched once for two rows.  The owned
+    // rows of a box are always one contiguous range (a box under 16 rows meets at most two tile rows).
     for (uint32_t i = tid; i < n_items; i += 256u) {
-        const uint32_t it = wsh.items[i], ow = it & 255u, r = it >> 8, g = r >> 2;
-        float w0, w1, w2;
-        if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
-        else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
+        const uint32_t it = wsh.items[i], ow = it & 255u;
+        const uint32_t br = wsh.bwrows[ow], bw = br & 0xFFFFu, mask = br >> 16;
+        const uint32_t r_lo = (uint32_t)__ffs((int)mask) - 1u, n_rows = (uint32_t)__popc(mask), half = (n_rows + 1u) >> 1;
         const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
-        for (uint32_t k = 0; k < (r & 3u); k++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
         const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
         const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
-        const uint32_t xy = wsh.xy[ow], y = (xy >> 16) + r, a = y / TILE_H;
-        unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+        const uint32_t xy = wsh.xy[ow];
         const unsigned long long key_lo = (unsigned long long)(~wsh.tri[ow]);
-        const uint32_t bw = wsh.bwrows[ow] & 0xFFFFu;
-        // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
-        // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
-        // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
-        // (One loop for both parts: a warp's lanes are in different parts of their rows, and two loops cost it the longest
-        // lead-in plus the longest run.)
-        bool entered = false;
-        for (uint32_t x = 0; x <= bw; x++) {
-            const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
-            if (entered && !inside) { break; }                                    // left the run: the rest of the row is outside
-            entered = inside;
-            const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
-            // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-            if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
-            w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+        for (uint32_t k = it >> 8; k < n_rows; k += half) {   // at most two rows
+            const uint32_t r = r_lo + k, g = r >> 2;
+            float w0, w1, w2;
+            if (g == 0u) { w0 = wsh.par[0][ow]; w1 = wsh.par[1][ow]; w2 = wsh.par[2][ow]; }
+            else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
+            for (uint32_t q = 0; q < (r & 3u); q++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
+            const uint32_t y = (xy >> 16) + r, a = y / TILE_H;
+            unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+            // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
+            // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
+            // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
+            bool entered = false;
+            for (uint32_t x = 0; x <= bw; x++) {
+                const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
+                if (entered && !inside) { break; }                                    // left the run: the rest of the row is outside
+                entered = inside;
+                const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
+                // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
+            }
         }
     }
     __syncthreads();   // parked boxes and items are rewritten by the next round

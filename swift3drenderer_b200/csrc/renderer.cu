@@ -85,7 +85,7 @@ struct S3RRenderer {
     DevBuf<uint8_t> walk_q;            // candidate queue of the direct walk: 40-byte records (front kernel -> walk kernel)
     uint32_t walk_cap = 0;
     uint32_t n_clusters = 0, n_batches = 0;
-    int opt_clusters = 1, opt_cluster_cull = 1;
+    int opt_clusters = 2, opt_cluster_cull = 1;   // clusters: 0 off, 1 on, 2 on for partitioned submissions
     Frame last_frame;   // parameter block of the last submission (raster-vertex dumps on the cluster path)
     // per-view scratch
     uint32_t views_cap = 0, tile_stride = 0;
@@ -477,9 +477,15 @@ static bool uses_direct_bin(const S3RRenderer *r) {
     return r->opt_fused_small && 2ull * r->T <= (uint64_t)SORT_CAP && r->setup_cap >= 2ull * r->T;
 }
 
-static bool uses_clusters(const S3RRenderer *r) { return r->opt_clusters && r->n_clusters > 0; }
+// The cluster front (batch_cull, cluster_cull, cluster_front, direct_walk) pays for itself when much of the scene can be
+// rejected wholesale — above all on a screen partition, where a rank keeps 1/n of the clusters.  opt_clusters: 0 never,
+// 1 always, 2 (default) for partitioned submissions only: on a whole frame of the benchmark field it rejects a quarter of
+// the clusters and costs more than the raw-stream classify kernel it replaces.
+static bool uses_clusters(const S3RRenderer *r, bool partitioned) {
+    return r->n_clusters > 0 && (r->opt_clusters == 1 || (r->opt_clusters == 2 && partitioned));
+}
 
-static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
+static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles, bool partitioned) {
     const uint32_t T = (uint32_t)r->T;
     if (r->setup_cap == 0) {
         // survivors are usually a small share of 2T; start at T/4 (min 4096) and regrow on demand
@@ -499,7 +505,7 @@ static int ensure_scratch(S3RRenderer *r, uint32_t views, uint32_t n_tiles) {
         r->tile_stride = std::max(tile_stride, r->tile_stride);
     }
     const size_t vc = r->views_cap;
-    if (uses_direct_bin(r) || !uses_clusters(r)) { CUDA_TRY(r->rv.ensure(vc * r->Vpad)); }   // the cluster front keeps raster-space vertices on chip
+    if (uses_direct_bin(r) || !uses_clusters(r, partitioned)) { CUDA_TRY(r->rv.ensure(vc * r->Vpad)); }   // the cluster front keeps raster-space vertices on chip
     CUDA_TRY(r->vis.ensure(vc * r->setup_cap));
     CUDA_TRY(r->shade.ensure(vc * r->setup_cap));
     CUDA_TRY(r->head.ensure(vc * r->setup_cap));
@@ -637,7 +643,8 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         f.tiles_y = rows > row_phase ? (rows - row_phase + row_stride - 1) / row_stride : 0;
     }
     f.n_tiles = f.tiles_x * f.tiles_y;
-    int rc = ensure_scratch(r, n_views, f.n_tiles);
+    const bool partitioned = row_stride > 1 || y0 > 0 || y1 < H;
+    int rc = ensure_scratch(r, n_views, f.n_tiles, partitioned);
     if (rc) { return rc; }
     const int slot = (int)(r->chunk_counter++ % S3RRenderer::RING);
     if (r->slot_used[slot]) {  // the chunk that used this slot RING submissions ago
@@ -676,7 +683,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.fw = (float)W; f.fh = (float)H; f.half_w = f.fw / 2; f.half_h = f.fh / 2;  // screen_size / 2, render.cpp:284,288
     f.factor = r->factor_override != 0.f ? r->factor_override : s3r_factor(H);
     f.rv = r->rv.p;
-    if (!uses_direct_bin(r) && uses_clusters(r)) {
+    if (!uses_direct_bin(r) && uses_clusters(r, partitioned)) {
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
         CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
@@ -1216,7 +1223,10 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
     if (!strcmp(name, "fused_small")) { r->opt_fused_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "direct_small")) { r->opt_direct_small = value != 0; return S3R_OK; }
     if (!strcmp(name, "spans")) { r->opt_spans = value != 0; return S3R_OK; }
-    if (!strcmp(name, "clusters")) { cudaStreamSynchronize(r->stream); r->opt_clusters = value != 0; return S3R_OK; }
+    if (!strcmp(name, "clusters")) {
+        if (value < 0 || value > 2) { return fail(S3R_E_ARG, "clusters: 0 off, 1 on, 2 on for partitioned submissions"); }
+        cudaStreamSynchronize(r->stream); r->opt_clusters = (int)value; return S3R_OK;
+    }
     if (!strcmp(name, "cluster_cull")) { r->opt_cluster_cull = value != 0; return S3R_OK; }
     if (!strcmp(name, "tensor_store")) { r->opt_tmap = value != 0; return S3R_OK; }
     if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
