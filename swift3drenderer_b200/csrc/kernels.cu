@@ -730,13 +730,8 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
                 if (entered && !inside) { break; }                                    // left the run: the rest of the row is outside
                 entered = inside;
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
-                // depth starts at 0, strict '>' (render.cpp:364).  Keys only ever grow, so a key that does not beat the value
-                // read here (however stale) cannot win: the reduction — the direct walk's scarce resource, one per covered
-                // pixel otherwise — is issued only for keys that may; it is fire-and-forget, nothing waits for it.
-                if (inside && ooz > 0.f) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo;
-                    if (key > __ldcg(krow + x)) { red_max_u64(krow + x, key); }
-                }
+                // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
+                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
@@ -919,64 +914,12 @@ __global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame 
     uint32_t pos = 0;
     if (lane == 0 && m) { pos = atomicAdd(c + C_BATCHES, __popc(m)); }
     pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    if (verdict == 0u) {
-        // unsorted list + the depth of the batch's centre: batch_sort orders the list front to back
-        const size_t at = (size_t)view * f.n_batches + pos + __popc(m & ((1u << lane) - 1u)), third = (size_t)f.n_views * f.n_batches;
-        const float4 h = __ldg(f.cl_batch + b);
-        f.batch_list[third + at] = b;
-        f.batch_list[2 * third + at] = __float_as_uint(-xform(cam, h.x, h.y, h.z, 1.0f).z);
-    }
+    if (verdict == 0u) { f.batch_list[(size_t)view * f.n_batches + pos + __popc(m & ((1u << lane) - 1u))] = b; }
     const uint32_t near = __reduce_add_sync(0xFFFFFFFFu, verdict == 1u ? n_tris : 0u), cull = __reduce_add_sync(0xFFFFFFFFu, verdict == 2u ? n_tris : 0u);
     if (lane == 0) {
         if (near) { atomicAdd(c + C_NEAR, near); }
         if (cull) { atomicAdd(c + C_CULLED, cull); }
     }
-}
-
-// Orders the surviving batches front to back (one CTA per view: min / max of the centre depths, a 1024-bucket counting sort).
-// Batches are small in space, so the order carries through cluster_cull, the front kernel and the candidate queue to the
-// direct walk: near triangles publish their keys first, and most of what lies behind them is dropped by the walk's look at
-// the key before it issues a reduction.  Only the order of work changes — keys are maxima, the frame cannot.
-__global__ void __launch_bounds__(1024) batch_sort(const __grid_constant__ Frame f) {
-    __shared__ float s_lo[32], s_hi[32];
-    __shared__ uint32_t s_hist[1024], s_warp[32];
-    const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const uint32_t n = f.counters[view * C_COUNT + C_BATCHES];
-    const size_t third = (size_t)f.n_views * f.n_batches;
-    uint32_t *out = f.batch_list + (size_t)view * f.n_batches;
-    const uint32_t *raw = out + third;
-    const float *depth = reinterpret_cast<const float *>(out + 2 * third);
-    float lo = INFINITY, hi = -INFINITY;
-    for (uint32_t i = tid; i < n; i += 1024u) { const float d = depth[i]; if (d == d) { lo = fminf(lo, d); hi = fmaxf(hi, d); } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
-    if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
-    s_hist[tid] = 0;
-    __syncthreads();
-    lo = s_lo[lane]; hi = s_hi[lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
-    const float scale = hi > lo ? 1023.0f / (hi - lo) : 0.f;
-    auto bucket = [&](float d) { const float q = (d - lo) * scale; return q >= 0.f ? min(1023u, (uint32_t)q) : 0u; };   // (NaN -> 0)
-    for (uint32_t i = tid; i < n; i += 1024u) { atomicAdd(&s_hist[bucket(depth[i])], 1u); }
-    __syncthreads();
-    // exclusive scan of the 1024 bucket counts
-    const uint32_t mine = s_hist[tid];
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
-    if (lane == 31) { s_warp[warp] = incl; }
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, d); if (lane >= (uint32_t)d) { w += v; } }
-        s_warp[lane] = w - s_warp[lane];
-    }
-    __syncthreads();
-    s_hist[tid] = s_warp[warp] + incl - mine;
-    __syncthreads();
-    for (uint32_t i = tid; i < n; i += 1024u) { out[atomicAdd(&s_hist[bucket(depth[i])], 1u)] = raw[i]; }
 }
 
 #ifndef S3R_FRONT_CTAS
@@ -2287,7 +2230,6 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
-        batch_sort<<<dim3(1u, f.n_views), 1024, 0, s>>>(f); launches++; mark(m, "batch_sort");
         cluster_cull<<<dim3(max(1u, ceil_div(f.n_batches, 4u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_cull");
         cluster_front<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
         direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");

@@ -111,7 +111,7 @@ struct Frame {
     const uint8_t *cl_vslot;
     const uint32_t *cl_tri;
     const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
-    uint32_t *batch_list;         // 3 x [n_views][n_batches]: surviving batches front to back (batch_sort) | as batch_cull found them | their centre depths
+    uint32_t *batch_list;         // [views][n_batches] batches that survived batch_cull, in list order
     uint4 *cluster_list;          // [views][n_clusters] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}
     uint32_t n_clusters, n_batches;
     struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)

@@ -686,7 +686,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     if (!uses_direct_bin(r) && uses_clusters(r, partitioned)) {
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
-        CUDA_TRY(r->batch_list.ensure(3u * (size_t)r->views_cap * r->n_batches));   // sorted list | unsorted list | centre depths
+        CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
         CUDA_TRY(r->cluster_list.ensure((size_t)r->views_cap * r->n_clusters));
         f.cluster_list = r->cluster_list.p;
         // candidates of the direct walk: a quarter of the triangles to begin with, regrown on overflow
