@@ -430,10 +430,13 @@ __device__ __forceinline__ void emit_block(bool valid, const Corner &d0, const C
     }
 }
 
+// HAS_RV: the vertex stage left raster-space vertices in HBM (raw-stream front, small scenes); otherwise (cluster front,
+// which keeps them on chip) the vertex stage's own expression is evaluated again — the same bits.
+template <bool HAS_RV>
 __device__ __forceinline__ Corner gather_corner(const Frame &f, const Cam &cam, uint32_t view, uint32_t vi, uint32_t ai) {
     Corner c;
     c.cv = xform(cam, __ldg(f.pos_x + vi), __ldg(f.pos_y + vi), __ldg(f.pos_z + vi), 1.0f);
-    if (f.rv) {
+    if (HAS_RV) {
         const float4 r = f.rv[(size_t)view * f.Vpad + vi];
         c.rv = make_float3(r.x, r.y, r.z);
     } else {   // cluster front: raster-space vertices never reach HBM; the vertex stage's own expression gives the same bits
@@ -535,6 +538,7 @@ __device__ __forceinline__ void classify_body(const Frame &f, uint32_t view, uin
 }
 
 // Phase 2 of K2: dense full setup of up to 256 work items held in sh.list (all 256 threads call).
+template <bool HAS_RV>
 __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, uint32_t view, SetupShared &sh) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
     const uint32_t count = sh.count;
@@ -545,9 +549,9 @@ __device__ __forceinline__ void process_items(const Frame &f, const Cam &cam, ui
     if (valid) {
         const uint32_t item = sh.list[tid];
         tri = item & ~ITEM_STRADDLE;
-        d0 = gather_corner(f, cam, view, __ldg(f.vi0 + tri), __ldg(f.ai0 + tri));
-        d1 = gather_corner(f, cam, view, __ldg(f.vi1 + tri), __ldg(f.ai1 + tri));
-        d2 = gather_corner(f, cam, view, __ldg(f.vi2 + tri), __ldg(f.ai2 + tri));
+        d0 = gather_corner<HAS_RV>(f, cam, view, __ldg(f.vi0 + tri), __ldg(f.ai0 + tri));
+        d1 = gather_corner<HAS_RV>(f, cam, view, __ldg(f.vi1 + tri), __ldg(f.ai1 + tri));
+        d2 = gather_corner<HAS_RV>(f, cam, view, __ldg(f.vi2 + tri), __ldg(f.ai2 + tri));
         if (item & ITEM_STRADDLE) { spawn = clip_near(d0, d1, d2, s0, s1, s2, f); }
     }
     if (count) { emit_block(valid, d0, d1, d2, tri, f, view, sh, /*count_culled=*/true); }
@@ -579,7 +583,7 @@ struct WalkShared {
     uint32_t xy[256];                  // xmin | ymin << 16
     uint32_t bwrows[256];              // xmax - xmin | owned-row mask << 16
     uint32_t tri[256];                 // order key of the box's triangle
-    uint16_t items[256 * SMALL_MAX / 2]; // parked slot | pair number << 8 (a pair: owned rows i and i + half), grouped by box width
+    uint16_t items[256 * SMALL_MAX];   // parked slot | row (or pair: owned rows i and i + half) << 8, grouped by box width
     uint32_t n_cand;
     uint32_t cls_count[SMALL_MAX];     // row items per box width (1 .. 16 pixels): a warp's items are equally wide
     uint32_t stats[4];                 // near-rejected, clipped, walked here, culled
@@ -645,6 +649,12 @@ __device__ __forceinline__ BoxRoute route_candidate(const Frame &f, const float4
 // direct walk of the boxes under 16 x 16 pixels — one (triangle, owned row) work item per lane, grouped by box width,
 // row starts from checkpoints every 4 rows, true additions along the row (render.cpp:374-379), keys published with
 // fire-and-forget 64-bit red.max.  Everything else becomes a work item of K2b.  All 256 threads call.
+// PAIR: a work item is a pair of owned rows of one box, row i and row i + half — a triangle's rows are short at its tips and
+// long in the middle, so the pairs' lengths are more alike than the rows' (the lanes of a warp run in lockstep) and the box's
+// parameters are fetched once for two rows.  Measured on the benchmark field (profiles/r02_experiments.md): pairs win in the
+// walk-only kernel (direct_walk 332 -> 316 us), single rows in the fused classify kernel (509 -> 452 us), where the walk
+// shares its warps with the front tests.
+template <bool PAIR>
 __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkShared &wsh, FrontCounts &n, bool valid, uint32_t item,
                                            const float4 &r0, const float4 &r1, const float4 &r2) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
@@ -678,7 +688,7 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
                     w0 = add_rn(w0, vc.dy[0]); w1 = add_rn(w1, vc.dy[1]); w2 = add_rn(w2, vc.dy[2]);
                     if ((r & 3u) == 0u) { const uint32_t g = (r >> 2) - 1u; wsh.ck[3 * g][tid] = w0; wsh.ck[3 * g + 1][tid] = w1; wsh.ck[3 * g + 2][tid] = w2; }
                 }
-                my_rows = ((uint32_t)__popc(b.rows) + 1u) >> 1;   // work items: the owned rows in pairs (row i with row i + half)
+                my_rows = PAIR ? ((uint32_t)__popc(b.rows) + 1u) >> 1 : (uint32_t)__popc(b.rows);   // work items: the owned rows, one by one or in pairs
                 my_cls = b.xmax - b.xmin;
                 my_off = atomicAdd(&wsh.cls_count[my_cls], my_rows);
             }
@@ -700,14 +710,12 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
         for (uint32_t i = 0; i < my_rows; i++) { wsh.items[pos++] = (uint16_t)(tid | (i << 8)); }
     }
     __syncthreads();
-    // The direct walk: one work item per thread and pass.  An item is a PAIR of owned rows of one box, row i and row
-    // i + half: a triangle's rows are short at its tips and long in the middle, so the pairs' lengths are far more alike than
-    // the rows' (the lanes of a warp run in lockstep), and the box's parameters are fetched once for two rows.  The owned
-    // rows of a box are always one contiguous range (a box under 16 rows meets at most two tile rows).
+    // The direct walk: one work item per thread and pass.  The owned rows of a box are always one contiguous range (a box
+    // under 16 rows meets at most two tile rows), so row k of an item is r_lo + k.
     for (uint32_t i = tid; i < n_items; i += 256u) {
         const uint32_t it = wsh.items[i], ow = it & 255u;
         const uint32_t br = wsh.bwrows[ow], bw = br & 0xFFFFu, mask = br >> 16;
-        const uint32_t r_lo = (uint32_t)__ffs((int)mask) - 1u, n_rows = (uint32_t)__popc(mask), half = (n_rows + 1u) >> 1;
+        const uint32_t r_lo = (uint32_t)__ffs((int)mask) - 1u, n_rows = (uint32_t)__popc(mask), half = PAIR ? (n_rows + 1u) >> 1 : n_rows;
         const float dy0 = wsh.par[6][ow], dy1 = wsh.par[7][ow], dy2 = wsh.par[8][ow];
         const float dx0 = wsh.par[3][ow], dx1 = wsh.par[4][ow], dx2 = wsh.par[5][ow];
         const float rz0 = wsh.par[9][ow], rz1 = wsh.par[10][ow], rz2 = wsh.par[11][ow];
@@ -721,14 +729,10 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
             for (uint32_t q = 0; q < (r & 3u); q++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
             const uint32_t y = (xy >> 16) + r, a = y / TILE_H;
             unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
-            // Along a row every weight is a monotone sequence (w += dx with a fixed dx, rounded monotonically), so the
-            // pixels that pass the inside test (render.cpp:362) are one contiguous run: walk up to it with nothing but
-            // the reference's own additions (render.cpp:374), publish the run, and stop — no later pixel can be inside.
-            bool entered = false;
+            // (leaving the row once it has left its run of inside pixels — the weights are monotone along a row — was
+            // measured and does not pay: the warp's longest row decides, and the test costs every lane)
             for (uint32_t x = 0; x <= bw; x++) {
                 const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
-                if (entered && !inside) { break; }                                    // left the run: the rest of the row is outside
-                entered = inside;
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
                 if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
             item = csh.cand[cbase + tid];
             if (!(item & ITEM_STRADDLE)) { r0 = rv[__ldg(f.vi0 + item)]; r1 = rv[__ldg(f.vi1 + item)]; r2 = rv[__ldg(f.vi2 + item)]; }
         }
-        walk_round(f, view, wsh, n, valid, item, r0, r1, r2);
+        walk_round<false>(f, view, wsh, n, valid, item, r0, r1, r2);
     }
     publish_front_counts(f, view, wsh, n);
 }
@@ -1163,13 +1167,14 @@ __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Fr
             item = e.y;
             valid = item != WALK_HOLE;   // a slot reserved for a candidate that went elsewhere
         }
-        walk_round(f, view, wsh, n, valid, item, r0, r1, r2);
+        walk_round<true>(f, view, wsh, n, valid, item, r0, r1, r2);
     }
     publish_front_counts(f, view, wsh, n);
 }
 
 // K2b: dense setup over the compacted work list (persistent grid-stride; every lane has a survivor
 // candidate, so the register-heavy gather/clip/setup code runs at full lane efficiency).
+template <bool HAS_RV>
 __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__ Frame f) {
     __shared__ SetupShared sh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x;
@@ -1180,7 +1185,7 @@ __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__
         if (tid < 4) { sh.stats[tid] = 0; }
         if (base + tid < n_work) { sh.list[tid] = f.worklist[(size_t)view * f.T + base + tid]; }
         __syncthreads();
-        process_items(f, cam, view, sh);
+        process_items<HAS_RV>(f, cam, view, sh);
     }
 }
 
@@ -1264,7 +1269,7 @@ __global__ void __launch_bounds__(256) geometry_small(const __grid_constant__ Fr
     __syncthreads();
     for (uint32_t chunk = 0; chunk * 256u < f.T; chunk++) {
         classify_body(f, view, chunk, sh);
-        process_items(f, cam, view, sh);
+        process_items<true>(f, cam, view, sh);
     }
     __syncthreads();
     if (tid == 0) {
@@ -1992,6 +1997,7 @@ struct ShadeShared {
     uint32_t count, n_tri;
 };
 
+template <bool HAS_RV>
 __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ShadeShared &sh = *reinterpret_cast<ShadeShared *>(smem_raw);
@@ -2069,7 +2075,7 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
                     // (indices, then vertices + attributes) instead of three
                     const uint32_t i0 = __ldg(f.vi0 + order), i1 = __ldg(f.vi1 + order), i2 = __ldg(f.vi2 + order);
                     const uint32_t a0 = __ldg(f.ai0 + order), a1 = __ldg(f.ai1 + order), a2 = __ldg(f.ai2 + order);
-                    d0 = gather_corner(f, cam, view, i0, a0); d1 = gather_corner(f, cam, view, i1, a1); d2 = gather_corner(f, cam, view, i2, a2);
+                    d0 = gather_corner<HAS_RV>(f, cam, view, i0, a0); d1 = gather_corner<HAS_RV>(f, cam, view, i1, a1); d2 = gather_corner<HAS_RV>(f, cam, view, i2, a2);
                     // the classify kernel's own routing rule: not straddling the near plane, screen box under 16 x 16
                     if (!(fminf(fminf(d0.rv.z, d1.rv.z), d2.rv.z) < kNear)) {
                         const float max_x = fmaxf(fmaxf(d0.rv.x, d1.rv.x), d2.rv.x), max_y = fmaxf(fmaxf(d0.rv.y, d1.rv.y), d2.rv.y);
@@ -2211,9 +2217,13 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) { return e; }
     e = cudaFuncSetAttribute(direct_walk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
-    e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
+    e = cudaFuncSetAttribute(shade_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
     if (e != cudaSuccess) { return e; }
-    e = cudaFuncSetAttribute(shade_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(shade_tiles<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(shade_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
+    if (e != cudaSuccess) { return e; }
+    e = cudaFuncSetAttribute(shade_tiles<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { return e; }
     return cudaFuncSetAttribute(triangle_classify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
@@ -2237,7 +2247,9 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
         triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");
     }
-    triangle_setup<<<dim3(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_setup");
+    const dim3 setup_grid(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views);
+    if (f.rv) { triangle_setup<true><<<setup_grid, 256, 0, s>>>(f); } else { triangle_setup<false><<<setup_grid, 256, 0, s>>>(f); }
+    launches++; mark(m, "triangle_setup");
     // cooperative binning of the big triangles, flat visibility pass over the recorded small ones (clipped or spawned),
     // and — by the last CTA to finish — the frame's tile statistics and overflow record
     post_setup<<<dim3(persistent, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "post_setup");
@@ -2265,7 +2277,10 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
     }
     if (nrows) {
-        shade_tiles<<<dim3(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views), 256, sizeof(ShadeShared), s>>>(f, row0, nrows); mark(m, "shade_tiles");
+        const dim3 grid(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views);
+        if (f.rv) { shade_tiles<true><<<grid, 256, sizeof(ShadeShared), s>>>(f, row0, nrows); }
+        else { shade_tiles<false><<<grid, 256, sizeof(ShadeShared), s>>>(f, row0, nrows); }
+        mark(m, "shade_tiles");
         launches++;
     }
     return launches;
