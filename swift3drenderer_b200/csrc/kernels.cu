@@ -84,6 +84,11 @@ __device__ __forceinline__ float edge_fn(float ax, float ay, float bx, float by,
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch: the general path's kernels are launched with programmatic stream serialization, so a
+// kernel's CTAs are placed while its predecessor drains and wait here — before they touch anything the predecessor wrote —
+// until it has completed and flushed.  Without the launch attribute this is a no-op.
+__device__ __forceinline__ void wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // fire-and-forget 64-bit max on a visibility key: always the reduction form (REDG.E.MAX.64).  atomicMax() with an unused
 // result is sometimes compiled to the returning ATOMG form instead, and a walk loop then waits for each atomic to
 // come back before it may reuse the address registers (45 % of post_setup's warp time on the clipping-stress scene).
@@ -766,6 +771,7 @@ struct ClassifyShared {
 };
 
 __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     __shared__ ClassifyShared csh;
     WalkShared &wsh = csh.w;
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
@@ -832,6 +838,12 @@ struct FrontWarp {                       // a warp's private staging: nothing in
 struct __align__(8) WalkRecord { float v[9]; uint32_t order; };
 static_assert(sizeof(WalkRecord) == 40, "WalkRecord must be 40 bytes");
 
+// The rejection tests only have to err on the safe side, so they use the approximate units (MUFU, a few ulps) with a margin
+// instead of the correctly rounded operators this translation unit is compiled with (-prec-div / -prec-sqrt: ten times the
+// instructions).  fast_sqrt_up(x) >= sqrt(x), fast_div_up(a, b) >= a / b for a >= 0, b > 0.
+__device__ __forceinline__ float fast_sqrt_up(float x) { return x > 0.f ? x * mufu_rsq(x) * 1.00001f : 0.f; }
+__device__ __forceinline__ float fast_div_up(float a, float b) { return a * mufu_rcp(b) * 1.00001f; }
+
 // What the rejection tests need from the view's matrix: the norms of its rows and a bound of its largest singular value
 // (Gershgorin on the Gram matrix; 1 for a camera's orthonormal rows).
 struct ViewBounds { float norm[3], sigma; };
@@ -842,13 +854,13 @@ __device__ __forceinline__ ViewBounds view_bounds(const Cam &cam) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const float m0 = cam.m[4 * i], m1 = cam.m[4 * i + 1], m2 = cam.m[4 * i + 2];
-        vb.norm[i] = sqrtf(m0 * m0 + m1 * m1 + m2 * m2) * 1.000001f;
+        vb.norm[i] = fast_sqrt_up(m0 * m0 + m1 * m1 + m2 * m2);
         float row = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; j++) { row += fabsf(m0 * cam.m[4 * j] + m1 * cam.m[4 * j + 1] + m2 * cam.m[4 * j + 2]); }
         gram = fmaxf(gram, row);
     }
-    vb.sigma = sqrtf(gram) * 1.000001f;
+    vb.sigma = fast_sqrt_up(gram);
     return vb;
 }
 
@@ -876,7 +888,9 @@ __device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &c
     if (!(d_min > kNear * 1.000001f)) { return 0u; }   // may touch the near plane (or bounds are not finite): per triangle
     // every vertex strictly in front: raster coordinates by interval arithmetic over the box [cc - rho, cc + rho]
     const float x_lo = cc.x - rho[0], x_hi = cc.x + rho[0], y_lo = -cc.y - rho[1], y_hi = -cc.y + rho[1];   // raster y grows downwards (-cv.y)
-    const float inv_min = f.factor / d_min, inv_max = f.factor / d_max;   // d_min < d_max, both positive
+    // factor / d_min rounded up, factor / d_max rounded down (d_min < d_max, both positive): an upper bound takes the
+    // larger scale for a positive coordinate and the smaller one for a negative coordinate, a lower bound the other way round
+    const float inv_min = fast_div_up(f.factor, d_min), inv_max = f.factor * mufu_rcp(d_max) * 0.99999f;
     const float qx_hi = x_hi * (x_hi >= 0.f ? inv_min : inv_max), qx_lo = x_lo * (x_lo >= 0.f ? inv_max : inv_min);
     const float qy_hi = y_hi * (y_hi >= 0.f ? inv_min : inv_max), qy_lo = y_lo * (y_lo >= 0.f ? inv_max : inv_min);
     // slack: rounding of the vertices' own projections and of this evaluation (a few 2^-24 of the magnitudes)
@@ -892,38 +906,11 @@ __device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &c
     // depth >= d_min whose endpoints project at tangents (tu, tv) is at most factor / d_min * L * sqrt(1 + tu^2 + tv^2)
     // pixels long.  L: the longest object-space edge through the matrix plus the endpoints' rounding.
     const float len = vb.sigma * max_edge + 4.f * err;
-    const float tu = fmaxf(fabsf(x_lo), fabsf(x_hi)) / d_min, tv = fmaxf(fabsf(y_lo), fabsf(y_hi)) / d_min;
-    const float pixels = inv_min * len * sqrtf(1.f + tu * tu + tv * tv) * 1.00001f + 2.f * (sx + sy);
+    const float rcp_min = mufu_rcp(d_min) * 1.00001f;
+    const float tu = fmaxf(fabsf(x_lo), fabsf(x_hi)) * rcp_min, tv = fmaxf(fabsf(y_lo), fabsf(y_hi)) * rcp_min;
+    const float pixels = inv_min * len * fast_sqrt_up(1.f + tu * tu + tv * tv) * 1.00001f + 2.f * (sx + sy);
     if (pixels <= 3.09f) { return 2u; }   // (3.09 + rounding)^2 < 10
     return 0u;
-}
-
-// Batch-level rejection: one thread per batch of CL_BATCH clusters tests the sphere around the batch's spheres.  Batches
-// that may show something are appended to the front kernel's work list; the triangles of the others are accounted for here
-// (near-rejected or culled, exactly what the reference's per-triangle tests would have said).  On a screen partition most
-// batches miss a rank's rows: they cost 16 bytes each.
-__global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame f) {
-    const uint32_t view = blockIdx.y, b = blockIdx.x * 256u + threadIdx.x, lane = lane_id();
-    const Cam cam = load_cam(f, view);
-    const ViewBounds vb = view_bounds(cam);
-    uint32_t verdict = 3u, n_tris = 0;   // 3: no batch
-    if (b < f.n_batches) {
-        const float4 h = __ldg(f.cl_batch + b);
-        const uint32_t c0 = b * CL_BATCH, c1 = min(c0 + CL_BATCH, f.n_clusters);
-        n_tris = __ldg(f.cl_hdr + 2 * (size_t)c1 + 1).w - __ldg(f.cl_hdr + 2 * (size_t)c0 + 1).w;
-        verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, h.x, h.y, h.z, h.w, INFINITY) : 0u;
-    }
-    uint32_t *c = f.counters + view * C_COUNT;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
-    uint32_t pos = 0;
-    if (lane == 0 && m) { pos = atomicAdd(c + C_BATCHES, __popc(m)); }
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    if (verdict == 0u) { f.batch_list[(size_t)view * f.n_batches + pos + __popc(m & ((1u << lane) - 1u))] = b; }
-    const uint32_t near = __reduce_add_sync(0xFFFFFFFFu, verdict == 1u ? n_tris : 0u), cull = __reduce_add_sync(0xFFFFFFFFu, verdict == 2u ? n_tris : 0u);
-    if (lane == 0) {
-        if (near) { atomicAdd(c + C_NEAR, near); }
-        if (cull) { atomicAdd(c + C_CULLED, cull); }
-    }
 }
 
 #ifndef S3R_FRONT_CTAS
@@ -932,30 +919,44 @@ __global__ void __launch_bounds__(256) batch_cull(const __grid_constant__ Frame 
 constexpr uint32_t WALK_HOLE = 0xFFFFFFFFu;   // order key of a queue slot that holds no candidate
 constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front kernel reserves at a time
 
-// Cluster-level rejection: one thread per cluster of the batches that survived batch_cull.  Surviving clusters are appended
-// to a compact list as {first vertex, first triangle word, original index of the first triangle, vertices | triangles << 16}
-// — everything the front kernel needs, so it never reads a header; the triangles of rejected clusters are accounted for
-// here (near-rejected or culled, what the reference's per-triangle tests would have said).  The front kernel's work is
-// then proportional to what may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.
+// Rejection of whole batches and clusters by their bounds, one thread per cluster, four batches of CL_BATCH = 64 clusters
+// per CTA.  First the sphere around the batch (lane 0 of each warp, broadcast): a batch that cannot show anything — most of
+// them for a rank of a screen partition — ends there.  Then the cluster's own sphere and longest edge.  Surviving
+// clusters are appended to a compact list as {first vertex, first triangle word, original index of the first triangle,
+// vertices | triangles << 16} — everything the front kernel needs, so it never reads a header; the triangles of what is
+// rejected are accounted for here (near-rejected or culled, exactly what the reference's per-triangle tests would have said).
+// The front kernel's work is then proportional to what may actually be visible to this submission: on an n-GPU screen
+// partition, 1/n of it.
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     __shared__ uint32_t s_wsum[8], s_base;
+    static_assert(CL_BATCH == 64, "cluster_cull maps 64 threads to a batch");
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Cam cam = load_cam(f, view);
-    const ViewBounds vb = view_bounds(cam);
     uint32_t *counters = f.counters + view * C_COUNT;
-    const uint32_t n_alive_b = counters[C_BATCHES];   // written by batch_cull
-    const uint32_t bi = blockIdx.x * 4u + (tid >> 6);   // four batches of CL_BATCH = 64 clusters per CTA
-    static_assert(CL_BATCH == 64, "cluster_cull maps 64 threads to a batch");
-    uint32_t verdict = 3u, n_tris = 0;   // 3: no cluster
-    uint4 entry = make_uint4(0u, 0u, 0u, 0u);
-    if (bi < n_alive_b) {
-        const uint32_t c = __ldg(f.batch_list + (size_t)view * f.n_batches + bi) * CL_BATCH + (tid & 63u);
-        if (c < f.n_clusters) {
-            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)c), h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1), nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3);
-            n_tris = nx.w - h1.w;
-            entry = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
-            verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z),
-                                                       __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+    const uint32_t b = blockIdx.x * 4u + (tid >> 6), c = b * CL_BATCH + (tid & 63u);
+    // the cluster's header travels while lane 0 judges the batch
+    const bool have = c < f.n_clusters;
+    uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, nx = h0;
+    if (have) { h0 = __ldg(f.cl_hdr + 2 * (size_t)c); h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1); nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3); }
+    ViewBounds vb = {{0.f, 0.f, 0.f}, 0.f};
+    uint32_t batch_verdict = 3u;   // 3: no such batch
+    if (lane == 0) {
+        vb = view_bounds(cam);
+        if (b < f.n_batches) {
+            const float4 hb = __ldg(f.cl_batch + b);
+            batch_verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, hb.x, hb.y, hb.z, hb.w, INFINITY) : 0u;
+        }
+    }
+    batch_verdict = __shfl_sync(0xFFFFFFFFu, batch_verdict, 0);
+    vb.norm[0] = __shfl_sync(0xFFFFFFFFu, vb.norm[0], 0); vb.norm[1] = __shfl_sync(0xFFFFFFFFu, vb.norm[1], 0);
+    vb.norm[2] = __shfl_sync(0xFFFFFFFFu, vb.norm[2], 0); vb.sigma = __shfl_sync(0xFFFFFFFFu, vb.sigma, 0);
+    const uint32_t n_tris = nx.w - h1.w;
+    uint32_t verdict = 3u;   // 3: no cluster
+    if (have) {
+        verdict = batch_verdict;
+        if (batch_verdict == 0u && f.cluster_cull) {
+            verdict = cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x));
         }
     }
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
@@ -969,11 +970,13 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
     if (tid == 0) {
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) { const uint32_t c = s_wsum[w]; s_wsum[w] = run; run += c; }
+        for (int w = 0; w < 8; w++) { const uint32_t k = s_wsum[w]; s_wsum[w] = run; run += k; }
         s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;
     }
     __syncthreads();
-    if (verdict == 0u) { f.cluster_list[(size_t)view * f.n_clusters + s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = entry; }
+    if (verdict == 0u) {
+        f.cluster_list[(size_t)view * f.n_clusters + s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
+    }
 }
 
 // K1 + the front of K2a over the surviving clusters, one WARP per group of FRONT_GROUP clusters and no block-wide step
@@ -986,6 +989,7 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
 //      reserves WALK_CHUNK slots at a time (one global atomic per chunk; what is left of a chunk is padded with holes),
 //      or a work item for K2b (straddlers and larger boxes).
 __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     __shared__ FrontWarp sh_all[8];
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id();
     FrontWarp &sh = sh_all[tid >> 5];
@@ -1137,6 +1141,7 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
 // the last — and run walk_round on them.  Nothing but the walk lives here, so the kernel's warps keep the reduction path
 // (one red.global.max.u64 per covered pixel) busy back to back.
 __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     __shared__ WalkShared wsh;
     __shared__ uint32_t s_round;
     const uint32_t view = blockIdx.y, tid = threadIdx.x;
@@ -1176,6 +1181,7 @@ __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Fr
 // candidate, so the register-heavy gather/clip/setup code runs at full lane efficiency).
 template <bool HAS_RV>
 __global__ void __launch_bounds__(256, 2) triangle_setup(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     __shared__ SetupShared sh;
     const uint32_t view = blockIdx.y, tid = threadIdx.x;
     const Cam cam = load_cam(f, view);
@@ -1817,6 +1823,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS) tile_raster(const
 #define S3R_QUEUE_CTAS 4
 #endif
 __global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_queue(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterShared &sh = *reinterpret_cast<RasterShared *>(smem_raw);
     const uint32_t view = blockIdx.y;
@@ -1842,6 +1849,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_qu
 // with atomicMax in global memory (L2-resident), exactly like walk_small does in shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame f) {
+    wait_for_predecessor();
     constexpr uint32_t FLAT_ROUND = 64, FLAT_CK = 16;   // survivors per round; row-start checkpoints per survivor, one every 8 rows
     __shared__ uint32_t s_sum, s_max, s_last, s_round, s_warp[8], s_pref[257];
     __shared__ float s_ck[FLAT_ROUND][FLAT_CK][3];
@@ -1999,6 +2007,7 @@ struct ShadeShared {
 
 template <bool HAS_RV>
 __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+    wait_for_predecessor();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ShadeShared &sh = *reinterpret_cast<ShadeShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tid = threadIdx.x, lane = lane_id();
@@ -2232,6 +2241,21 @@ static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b
 
 static inline void mark(const LaunchMarks *m, const char *kernel) { if (m) { m->fn(m->ctx, kernel); } }
 
+// Launch with programmatic stream serialization (see wait_for_predecessor): `after_kernel` = the previous operation in the
+// stream is one of this path's kernels.
+static int g_pdl = 1;
+template <typename... KArgs, typename... Args>
+static void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool after_kernel, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (g_pdl && after_kernel) ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+void set_dependent_launch(int on) { g_pdl = on; }
+
 int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     int launches = 0;
     const uint32_t persistent = (uint32_t)g_sm_count * 4u;
@@ -2239,20 +2263,21 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // spatial pre-partition: vertex stage + front + direct walk in one kernel over the clusters; the frame's counters
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
-        batch_cull<<<dim3(max(1u, ceil_div(f.n_batches, 256u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "batch_cull");
-        cluster_cull<<<dim3(max(1u, ceil_div(f.n_batches, 4u)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_cull");
-        cluster_front<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "cluster_front");
-        direct_walk<<<dim3((uint32_t)g_sm_count * 6u, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "direct_walk");
+        const bool chain = true;
+        launch_chain(cluster_cull, dim3(max(1u, ceil_div(f.n_batches, 4u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
+        launch_chain(cluster_front, dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "cluster_front");
+        launch_chain(direct_walk, dim3((uint32_t)g_sm_count * 6u, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "direct_walk");
     } else {
         vertex_stage<<<dim3(max(1u, ceil_div(f.Vpad / 4, 256)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "vertex_stage");
         triangle_classify<<<dim3(max(1u, ceil_div(f.T, CLS_PER_CTA)), f.n_views), 256, 0, s>>>(f); launches++; mark(m, "triangle_classify");
     }
     const dim3 setup_grid(min((uint32_t)g_sm_count * 2u, max(1u, ceil_div(f.T, 256))), f.n_views);
-    if (f.rv) { triangle_setup<true><<<setup_grid, 256, 0, s>>>(f); } else { triangle_setup<false><<<setup_grid, 256, 0, s>>>(f); }
+    const bool chain2 = true;
+    if (f.rv) { launch_chain(triangle_setup<true>, setup_grid, dim3(256), 0, s, chain2, f); } else { launch_chain(triangle_setup<false>, setup_grid, dim3(256), 0, s, chain2, f); }
     launches++; mark(m, "triangle_setup");
     // cooperative binning of the big triangles, flat visibility pass over the recorded small ones (clipped or spawned),
     // and — by the last CTA to finish — the frame's tile statistics and overflow record
-    post_setup<<<dim3(persistent, f.n_views), 256, 0, s>>>(f); launches++; mark(m, "post_setup");
+    launch_chain(post_setup, dim3(persistent, f.n_views), dim3(256), 0, s, chain2, f); launches++; mark(m, "post_setup");
     return launches;
 }
 
@@ -2265,7 +2290,7 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     // the first band; the bands only cut the shading pass (the host path copies band k while band k + 1 is shaded)
     int launches = 0;
     if (f.raster_row0 == 0u) {
-        tile_raster_queue<<<dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), RASTER_THREADS, sizeof(RasterShared), s>>>(f); mark(m, "tile_raster_queue");
+        launch_chain(tile_raster_queue, dim3((uint32_t)g_sm_count * (uint32_t)S3R_QUEUE_CTAS, f.n_views), dim3(RASTER_THREADS), sizeof(RasterShared), s, true, f); mark(m, "tile_raster_queue");
         launches++;
     }
     uint32_t row0, nrows;
@@ -2278,8 +2303,8 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
     }
     if (nrows) {
         const dim3 grid(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views);
-        if (f.rv) { shade_tiles<true><<<grid, 256, sizeof(ShadeShared), s>>>(f, row0, nrows); }
-        else { shade_tiles<false><<<grid, 256, sizeof(ShadeShared), s>>>(f, row0, nrows); }
+        if (f.rv) { launch_chain(shade_tiles<true>, grid, dim3(256), sizeof(ShadeShared), s, true, f, row0, nrows); }
+        else { launch_chain(shade_tiles<false>, grid, dim3(256), sizeof(ShadeShared), s, true, f, row0, nrows); }
         mark(m, "shade_tiles");
         launches++;
     }

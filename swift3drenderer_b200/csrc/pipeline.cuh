@@ -65,8 +65,6 @@ enum Counter : uint32_t {
     C_ROWTAB = 15,   // general path: floats of row-start tables allocated so far (post_setup)
     C_FLATQ = 14,    // general path: rounds of the flat walk handed out so far (post_setup)
     C_SPANS = 13,    // small scenes: survivors with a checkpoint table this frame (<= SPAN_MAX)
-    C_BATCHES = 16,  // cluster front: batches of clusters that survived the batch-level rejection (batch_cull)
-    C_BHEAD = 17,    // ... and how many of them the front kernel's persistent CTAs have taken
     C_WALKQ = 18,    // cluster front: candidates queued for the direct-walk kernel
     C_WALKHEAD = 19, // ... and how many rounds of 256 the walk kernel's persistent CTAs have taken
     C_CLUSTERS = 20, // cluster front: clusters that survived the cluster-level rejection (cluster_cull)
@@ -111,7 +109,6 @@ struct Frame {
     const uint8_t *cl_vslot;
     const uint32_t *cl_tri;
     const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
-    uint32_t *batch_list;         // [views][n_batches] batches that survived batch_cull, in list order
     uint4 *cluster_list;          // [views][n_clusters] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}
     uint32_t n_clusters, n_batches;
     struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)
@@ -185,6 +182,7 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *marks = n
 int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);     // per-tile visibility + shading + write-out
 int launch_geometry_small(const Frame &f, cudaStream_t s, const LaunchMarks *marks = nullptr);  // single-CTA-per-view fused geometry (+ span_walk when f.coltab is set)
 void launch_vertex_stage(const Frame &f, cudaStream_t s);   // vertex stage alone into f.rv (raster-vertex dumps)
+void set_dependent_launch(int on);   // programmatic dependent launch between the general path's kernels (default on)
 cudaError_t configure_kernels();
 void launch_exact_math(uint32_t mode, unsigned long long lo, unsigned long long count, uint32_t seed, unsigned long long *result,
                        cudaStream_t st);

@@ -80,7 +80,6 @@ struct S3RRenderer {
     DevBuf<uint8_t> cl_vslot;
     DevBuf<uint32_t> cl_tri;
     DevBuf<float4> cl_batch;
-    DevBuf<uint32_t> batch_list;
     DevBuf<uint4> cluster_list;
     DevBuf<uint8_t> walk_q;            // candidate queue of the direct walk: 40-byte records (front kernel -> walk kernel)
     uint32_t walk_cap = 0;
@@ -205,7 +204,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->batch_list.release(); r->cluster_list.release(); r->walk_q.release();
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->cluster_list.release(); r->walk_q.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -686,14 +685,13 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     if (!uses_direct_bin(r) && uses_clusters(r, partitioned)) {
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
-        CUDA_TRY(r->batch_list.ensure((size_t)r->views_cap * r->n_batches));
         CUDA_TRY(r->cluster_list.ensure((size_t)r->views_cap * r->n_clusters));
         f.cluster_list = r->cluster_list.p;
         // candidates of the direct walk: a quarter of the triangles to begin with, regrown on overflow
         if (r->walk_cap == 0) { r->walk_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r->T, 1), std::max<uint64_t>(4096, r->T / 4)); }
         CUDA_TRY(r->walk_q.ensure((size_t)r->views_cap * r->walk_cap * 40u));
         f.walk_q = reinterpret_cast<WalkRecord *>(r->walk_q.p); f.walk_cap = r->walk_cap;
-        f.cl_batch = r->cl_batch.p; f.batch_list = r->batch_list.p; f.n_batches = r->n_batches;
+        f.cl_batch = r->cl_batch.p; f.n_batches = r->n_batches;
         f.rv = nullptr;
     }
     f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;
@@ -1228,6 +1226,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
         cudaStreamSynchronize(r->stream); r->opt_clusters = (int)value; return S3R_OK;
     }
     if (!strcmp(name, "cluster_cull")) { r->opt_cluster_cull = value != 0; return S3R_OK; }
+    if (!strcmp(name, "dependent_launch")) { set_dependent_launch(value != 0); return S3R_OK; }   // (process-wide)
     if (!strcmp(name, "tensor_store")) { r->opt_tmap = value != 0; return S3R_OK; }
     if (!strcmp(name, "flat_max")) {   // >= 16: the record-free direct walk handles boxes under 16 x 16 whatever this says
         if (value < 16 || value > 65536) { return fail(S3R_E_ARG, "flat_max out of range"); }
@@ -1318,11 +1317,19 @@ int multi_worker_frame(MultiGpu *mg, int k) {
         int rc = render_chunk(r, j.matrix, 1, j.W, j.H, 0, j.H, r->frame.p, r->stream, 1, nullptr, false, n, (uint32_t)k);
         if (rc) { return rc; }
         r->last_views = 1; r->last_W = j.W; r->last_H = j.H; r->last_stream = r->stream;
-        for (uint32_t l = 0; l < owned; l++) {   // owned tile row l = frame tile row l * n + k: 32 contiguous pixel rows
-            const uint32_t y = (l * n + (uint32_t)k) * TILE_H, rows = std::min<uint32_t>(TILE_H, j.H - y);
-            const uint32_t *src = r->frame.p + (size_t)l * TILE_H * j.W;
-            void *dst = j.pinned ? static_cast<void *>(j.host_out + (size_t)y * j.W) : static_cast<void *>(me.staging + (size_t)l * TILE_H * j.W * 4);
-            CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)rows * j.W * 4, cudaMemcpyDeviceToHost, r->stream));
+        {
+            // owned tile row l = frame tile row l * n + k: TILE_H contiguous pixel rows, i.e. one "row" of a 2-D copy whose
+            // destination pitch is n tile rows — one DMA descriptor for all full tile rows, one more for a cut last one
+            const size_t tile_bytes = (size_t)TILE_H * j.W * 4;
+            const uint32_t last_y = ((owned - 1u) * n + (uint32_t)k) * TILE_H, last_rows = std::min<uint32_t>(TILE_H, j.H - last_y);
+            const uint32_t full = last_rows == (uint32_t)TILE_H ? owned : owned - 1u;
+            uint8_t *dst0 = j.pinned ? reinterpret_cast<uint8_t *>(j.host_out + (size_t)k * TILE_H * j.W) : me.staging;
+            const size_t dpitch = j.pinned ? tile_bytes * n : tile_bytes;
+            if (full) { CUDA_TRY(cudaMemcpy2DAsync(dst0, dpitch, r->frame.p, tile_bytes, tile_bytes, full, cudaMemcpyDeviceToHost, r->stream)); }
+            if (full < owned) {
+                CUDA_TRY(cudaMemcpyAsync(dst0 + dpitch * full, reinterpret_cast<const uint8_t *>(r->frame.p) + tile_bytes * full,
+                                         (size_t)last_rows * j.W * 4, cudaMemcpyDeviceToHost, r->stream));
+            }
         }
         rc = finish_on(r, r->stream);   // waits for the launches and the copies; 1 = a capacity was regrown, render again
         if (rc < 0) { return rc; }
