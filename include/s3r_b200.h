@@ -196,10 +196,10 @@ S3R_API int s3r_debug_exact_math(S3RRenderer *r, uint32_t mode, uint64_t first, 
  * path's front kernel rejects wholesale when they lie behind the near plane, off screen, outside the rows a GPU owns or
  * are too small to pass `area >= 10` (render-cpp/render.cpp:306-317).  counts_out = {clusters, cluster vertices, triangles};
  * hdr_out: (clusters + 1) x 32 bytes {cx, cy, cz, radius, max_edge, t0, v_off, tri_off}; pos_out: three planes of v_cap
- * floats; tri_out: one word per triangle (v0 | v1 << 8 | v2 << 16 | batch slot << 24), needs room for index_count / 3. */
+ * floats; tri_out: one word per triangle (v0 | v1 << 8 | v2 << 16, cluster-local vertex numbers), room for index_count / 3. */
 S3R_API int s3r_debug_clusters(const float *vertices_xyzw, uint64_t vertex_count, const uint64_t *vertex_indices,
-                               uint64_t index_count, void *hdr_out, uint64_t hdr_cap, float *pos_out, uint8_t *vslot_out,
-                               uint64_t v_cap, uint32_t *tri_out, uint64_t counts_out[3]);
+                               uint64_t index_count, void *hdr_out, uint64_t hdr_cap, float *pos_out, uint64_t v_cap,
+                               uint32_t *tri_out, uint64_t counts_out[3]);
 
 /* Test hook, callable without a GPU: the tile-row band edges of a host render (s3r_render_host pipelines raster launches
  * with device-to-host copies band by band; the last band is tapered).  Returns the number of edges written (bands + 1),

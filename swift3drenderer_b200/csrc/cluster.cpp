@@ -143,12 +143,11 @@ void build_clusters(const float *px, const float *py, const float *pz, const uin
     out.n_clusters = (uint32_t)raw.size();
     out.hdr.resize(raw.size() + 1);
     out.tri.resize((size_t)T);
-    out.px.clear(); out.py.clear(); out.pz.clear(); out.vslot.clear();
-    out.px.reserve((size_t)T); out.py.reserve((size_t)T); out.pz.reserve((size_t)T); out.vslot.reserve((size_t)T);
+    out.px.clear(); out.py.clear(); out.pz.clear();
+    out.px.reserve((size_t)T); out.py.reserve((size_t)T); out.pz.reserve((size_t)T);
     uint32_t tri_off = 0;
     for (size_t k = 0; k < order.size(); k++) {
         const Raw &r = raw[order[k]];
-        const uint32_t slot = (uint32_t)(k % CL_BATCH);
         ClusterHeader &h = out.hdr[k];
         h.cx = r.cx; h.cy = r.cy; h.cz = r.cz; h.radius = r.radius; h.max_edge = r.max_edge;
         h.t0 = r.t0; h.v_off = (uint32_t)out.px.size(); h.tri_off = tri_off;
@@ -163,36 +162,11 @@ void build_clusters(const float *px, const float *py, const float *pz, const uin
                 if (at == n_verts) {
                     verts[n_verts++] = id[c];
                     out.px.push_back(px[id[c]]); out.py.push_back(py[id[c]]); out.pz.push_back(pz[id[c]]);
-                    out.vslot.push_back((uint8_t)slot);
                 }
                 local[c] = at;
             }
-            out.tri[tri_off++] = local[0] | (local[1] << 8) | (local[2] << 16) | (slot << 24);
+            out.tri[tri_off++] = local[0] | (local[1] << 8) | (local[2] << 16);
         }
-    }
-    // batch bounds: a sphere around the spheres of the batch's clusters (a whole batch that misses the view costs 16 bytes)
-    const size_t n_batches = (raw.size() + CL_BATCH - 1) / CL_BATCH;
-    out.batch.assign(4 * n_batches, 0.f);
-    for (size_t b = 0; b < n_batches; b++) {
-        const size_t k0 = b * CL_BATCH, k1 = std::min(raw.size(), k0 + CL_BATCH);
-        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        bool finite = true;
-        for (size_t k = k0; k < k1; k++) {
-            const ClusterHeader &h = out.hdr[k];
-            finite = finite && std::isfinite(h.radius);
-            const double c[3] = {h.cx, h.cy, h.cz};
-            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[a] - h.radius); hi[a] = std::max(hi[a], c[a] + h.radius); }
-        }
-        float *o = &out.batch[4 * b];
-        if (!finite) { o[0] = o[1] = o[2] = 0.f; o[3] = INFINITY; continue; }   // never rejected
-        const float c[3] = {(float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2]))};
-        double r = 0;
-        for (size_t k = k0; k < k1; k++) {
-            const ClusterHeader &h = out.hdr[k];
-            const double dx = (double)h.cx - c[0], dy = (double)h.cy - c[1], dz = (double)h.cz - c[2];
-            r = std::max(r, sqrt(dx * dx + dy * dy + dz * dz) + (double)h.radius);
-        }
-        o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = round_up(r * (1.0 + 1e-9));
     }
     ClusterHeader &end = out.hdr[raw.size()];
     memset(&end, 0, sizeof(end));

@@ -5,9 +5,9 @@
 // together (at most CL_MAX_VERTS distinct vertices, CL_MAX_TRIS triangles, bounding box no larger than a few of their
 // edges) — each with a bounding sphere and its longest edge, so that a whole cluster can be rejected by one
 // conservative test (behind the near plane, off screen, outside the rows a GPU owns, or too small to pass the
-// `area < 10` cull) before any of its vertices is transformed.  Clusters are stored in Morton order of their centres,
-// CL_BATCH of them per CTA of the front kernel; every cluster owns private copies of its vertices (streamed, coalesced)
-// and its triangles become one 32-bit word each (three cluster-local vertex numbers and the cluster's slot in its batch).
+// `area < 10` cull) before any of its vertices is transformed.  Clusters are stored in Morton order of their centres (what a
+// warp of the front kernel touches is close together in space and in memory); every cluster owns private copies of its
+// vertices (streamed, coalesced) and its triangles become one 32-bit word each (three cluster-local vertex numbers).
 // The reference's processing order survives as the order key: triangle j of a cluster is original triangle t0 + j.
 #pragma once
 #include <stdint.h>
@@ -18,7 +18,6 @@ namespace s3r {
 
 constexpr uint32_t CL_MAX_VERTS = 16;    // distinct vertices per cluster (an icosahedron has 12)
 constexpr uint32_t CL_MAX_TRIS = 32;     // triangles per cluster (an icosahedron has 20)
-constexpr uint32_t CL_BATCH = 64;        // clusters per CTA of the front kernel: <= 1024 vertices, <= 2048 triangles
 constexpr float CL_SPREAD = 4.0f;        // a cluster's bounding-box diagonal stays within CL_SPREAD of its longest edge
 
 struct ClusterHeader {                   // 32 bytes, two 16-byte loads
@@ -33,9 +32,7 @@ static_assert(sizeof(ClusterHeader) == 32, "ClusterHeader must be 32 bytes");
 struct ClusterSet {
     std::vector<ClusterHeader> hdr;      // n_clusters + 1: the last one is a sentinel that carries the end offsets
     std::vector<float> px, py, pz;       // cluster-private vertex copies, in cluster order
-    std::vector<uint8_t> vslot;          // per cluster vertex: its cluster's slot within the batch (0 .. CL_BATCH - 1)
-    std::vector<uint32_t> tri;           // v0 | v1 << 8 | v2 << 16 | slot << 24 (cluster-local vertex numbers)
-    std::vector<float> batch;            // per batch of CL_BATCH clusters: {cx, cy, cz, radius} enclosing its clusters' spheres
+    std::vector<uint32_t> tri;           // v0 | v1 << 8 | v2 << 16 (cluster-local vertex numbers), in cluster order
     uint32_t n_clusters = 0;
 };
 

@@ -812,16 +812,17 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 + K2a over the spatial pre-partition (cluster.hpp): one CTA per batch of CL_BATCH clusters.
-//   1. one thread per cluster: a conservative verdict from the bounding sphere — every vertex at or behind the near
-//      plane (all its triangles are near-rejected, render.cpp:306), or every triangle certainly culled: off screen, outside
-//      the rows this submission owns, or too small to reach `area >= 10` (render.cpp:311-317).  Such a cluster costs
-//      32 bytes; its vertices are never transformed.  On an n-GPU screen partition a rank skips what misses its rows,
-//      so the geometry work shrinks with n.
-//   2. the vertex stage (render.cpp:285-289) of the surviving clusters, streamed from the cluster-private position
-//      arrays into SHARED memory — raster-space vertices never travel to HBM;
-//   3. the front tests, one thread per triangle word, corners gathered from shared memory; warp-ballot compaction;
-//   4. the candidates' coverage setup and direct walk (walk_candidates), exactly as in triangle_classify.
+// K1 + K2a over the spatial pre-partition (cluster.hpp), three kernels:
+//   cluster_cull    one thread per cluster: a conservative verdict from the bounding sphere — every vertex at or behind the
+//                   near plane (all its triangles are near-rejected, render.cpp:306), or every triangle certainly culled: off
+//                   screen, outside the rows this submission owns, or too small to reach `area >= 10` (render.cpp:311-317).
+//                   Such a cluster costs 48 bytes of header; its vertices are never transformed.  On an n-GPU screen
+//                   partition a rank skips what misses its rows, so the geometry work shrinks with n.
+//   cluster_front   one warp per group of four surviving clusters: the vertex stage (render.cpp:285-289) streamed from the
+//                   cluster-private position arrays into SHARED memory — raster-space vertices never travel to HBM —, the
+//                   front tests with corners gathered from shared memory, routing, and a 40-byte record per candidate of
+//                   the direct walk into a queue in HBM;
+//   direct_walk     coverage setup and direct walk of the queue, 256 records per round (walk_round).
 // Every skipped triangle is proven rejected by the reference's own per-triangle tests, so the frame cannot change.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t FRONT_GROUP = 4;                                  // clusters a warp of the front kernel takes at a time
@@ -919,45 +920,31 @@ __device__ __forceinline__ uint32_t cluster_verdict(const Frame &f, const Cam &c
 constexpr uint32_t WALK_HOLE = 0xFFFFFFFFu;   // order key of a queue slot that holds no candidate
 constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front kernel reserves at a time
 
-// Rejection of whole batches and clusters by their bounds, one thread per cluster, four batches of CL_BATCH = 64 clusters
-// per CTA.  First the sphere around the batch (lane 0 of each warp, broadcast): a batch that cannot show anything — most of
-// them for a rank of a screen partition — ends there.  Then the cluster's own sphere and longest edge.  Surviving
-// clusters are appended to a compact list as {first vertex, first triangle word, original index of the first triangle,
-// vertices | triangles << 16} — everything the front kernel needs, so it never reads a header; the triangles of what is
-// rejected are accounted for here (near-rejected or culled, exactly what the reference's per-triangle tests would have said).
-// The front kernel's work is then proportional to what may actually be visible to this submission: on an n-GPU screen
-// partition, 1/n of it.
+// Rejection of whole clusters by their bounds, one thread per cluster: the sphere around the cluster's vertices and its
+// longest edge against the view (cluster_verdict).  Surviving clusters are appended to a compact list as {first vertex,
+// first triangle word, original index of the first triangle, vertices | triangles << 16} — everything the front kernel
+// needs, so it never reads a header; the triangles of what is rejected are accounted for here (near-rejected or culled,
+// exactly what the reference's per-triangle tests would have said).  The front kernel's work is then proportional to what
+// may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.  (A coarser test on spheres around
+// batches of 64 clusters in front of this one was measured: the 32-byte headers it saves cost less than its extra step.)
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
     wait_for_predecessor();
     __shared__ uint32_t s_wsum[8], s_base;
-    static_assert(CL_BATCH == 64, "cluster_cull maps 64 threads to a batch");
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Cam cam = load_cam(f, view);
     uint32_t *counters = f.counters + view * C_COUNT;
-    const uint32_t b = blockIdx.x * 4u + (tid >> 6), c = b * CL_BATCH + (tid & 63u);
-    // the cluster's header travels while lane 0 judges the batch
+    const uint32_t c = blockIdx.x * 256u + tid;
     const bool have = c < f.n_clusters;
     uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, nx = h0;
     if (have) { h0 = __ldg(f.cl_hdr + 2 * (size_t)c); h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1); nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3); }
     ViewBounds vb = {{0.f, 0.f, 0.f}, 0.f};
-    uint32_t batch_verdict = 3u;   // 3: no such batch
-    if (lane == 0) {
-        vb = view_bounds(cam);
-        if (b < f.n_batches) {
-            const float4 hb = __ldg(f.cl_batch + b);
-            batch_verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, hb.x, hb.y, hb.z, hb.w, INFINITY) : 0u;
-        }
-    }
-    batch_verdict = __shfl_sync(0xFFFFFFFFu, batch_verdict, 0);
+    if (lane == 0) { vb = view_bounds(cam); }   // (while the headers travel)
     vb.norm[0] = __shfl_sync(0xFFFFFFFFu, vb.norm[0], 0); vb.norm[1] = __shfl_sync(0xFFFFFFFFu, vb.norm[1], 0);
     vb.norm[2] = __shfl_sync(0xFFFFFFFFu, vb.norm[2], 0); vb.sigma = __shfl_sync(0xFFFFFFFFu, vb.sigma, 0);
     const uint32_t n_tris = nx.w - h1.w;
     uint32_t verdict = 3u;   // 3: no cluster
     if (have) {
-        verdict = batch_verdict;
-        if (batch_verdict == 0u && f.cluster_cull) {
-            verdict = cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x));
-        }
+        verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
     }
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
     if (lane == 0) { s_wsum[warp] = (uint32_t)__popc(m); }
@@ -2264,7 +2251,7 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         const bool chain = true;
-        launch_chain(cluster_cull, dim3(max(1u, ceil_div(f.n_batches, 4u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
+        launch_chain(cluster_cull, dim3(max(1u, ceil_div(f.n_clusters, 256u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
         launch_chain(cluster_front, dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "cluster_front");
         launch_chain(direct_walk, dim3((uint32_t)g_sm_count * 6u, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "direct_walk");
     } else {

@@ -106,11 +106,9 @@ struct Frame {
     // triangle_classify) runs instead
     const uint4 *cl_hdr;          // 2 x uint4 per cluster, n_clusters + 1 (sentinel)
     const float *cl_px, *cl_py, *cl_pz;
-    const uint8_t *cl_vslot;
     const uint32_t *cl_tri;
-    const float4 *cl_batch;       // per batch of CL_BATCH clusters: bounding sphere of its clusters' spheres
     uint4 *cluster_list;          // [views][n_clusters] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}
-    uint32_t n_clusters, n_batches;
+    uint32_t n_clusters;
     struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)
     uint32_t walk_cap;
     int cluster_cull;             // 0: every cluster is processed per triangle (A/B and tests)

@@ -77,13 +77,11 @@ struct S3RRenderer {
     // spatial pre-partition of the triangle stream (cluster.hpp), built at load
     DevBuf<uint4> cl_hdr;
     DevBuf<float> cl_px, cl_py, cl_pz;
-    DevBuf<uint8_t> cl_vslot;
     DevBuf<uint32_t> cl_tri;
-    DevBuf<float4> cl_batch;
     DevBuf<uint4> cluster_list;
     DevBuf<uint8_t> walk_q;            // candidate queue of the direct walk: 40-byte records (front kernel -> walk kernel)
     uint32_t walk_cap = 0;
-    uint32_t n_clusters = 0, n_batches = 0;
+    uint32_t n_clusters = 0;
     int opt_clusters = 2, opt_cluster_cull = 1;   // clusters: 0 off, 1 on, 2 on for partitioned submissions
     Frame last_frame;   // parameter block of the last submission (raster-vertex dumps on the cluster path)
     // per-view scratch
@@ -204,7 +202,7 @@ extern "C" void s3r_destroy(S3RRenderer *r) {
     unpin_all(r);
     r->pos_x.release(); r->pos_y.release(); r->pos_z.release();
     for (int k = 0; k < 3; k++) { r->vi[k].release(); r->ai[k].release(); }
-    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_vslot.release(); r->cl_tri.release(); r->cl_batch.release(); r->cluster_list.release(); r->walk_q.release();
+    r->cl_hdr.release(); r->cl_px.release(); r->cl_py.release(); r->cl_pz.release(); r->cl_tri.release(); r->cluster_list.release(); r->walk_q.release();
     r->attr.release(); r->texels.release(); r->rv.release(); r->vis.release(); r->shade.release(); r->head.release(); r->slot_of.release(); r->worklist.release(); r->keys.release(); r->raster_items.release(); r->pstate.release();
     r->counters.release();
     r->big_list.release(); r->entries.release(); r->cams.release(); r->frame.release(); r->sticky.release();
@@ -284,17 +282,13 @@ extern "C" int s3r_load_scene_arrays(S3RRenderer *r, const float *vertices, uint
         ClusterSet cs;
         build_clusters(px.data(), py.data(), pz.data(), v[0].data(), v[1].data(), v[2].data(), T, cs);
         CUDA_TRY(r->cl_hdr.ensure(cs.hdr.size() * 2)); CUDA_TRY(r->cl_px.ensure(cs.px.size())); CUDA_TRY(r->cl_py.ensure(cs.px.size()));
-        CUDA_TRY(r->cl_pz.ensure(cs.px.size())); CUDA_TRY(r->cl_vslot.ensure(cs.vslot.size())); CUDA_TRY(r->cl_tri.ensure(cs.tri.size()));
+        CUDA_TRY(r->cl_pz.ensure(cs.px.size())); CUDA_TRY(r->cl_tri.ensure(cs.tri.size()));
         CUDA_TRY(cudaMemcpy(r->cl_hdr.p, cs.hdr.data(), cs.hdr.size() * sizeof(ClusterHeader), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_px.p, cs.px.data(), cs.px.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_py.p, cs.py.data(), cs.py.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_pz.p, cs.pz.data(), cs.pz.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(r->cl_vslot.p, cs.vslot.data(), cs.vslot.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->cl_tri.p, cs.tri.data(), cs.tri.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(r->cl_batch.ensure(cs.batch.size() / 4));
-        CUDA_TRY(cudaMemcpy(r->cl_batch.p, cs.batch.data(), cs.batch.size() * 4, cudaMemcpyHostToDevice));
         r->n_clusters = cs.n_clusters;
-        r->n_batches = (uint32_t)(cs.batch.size() / 4);
     }
     CUDA_TRY(r->attr.ensure(at.size()));
     CUDA_TRY(cudaMemcpy(r->attr.p, at.data(), at.size() * sizeof(uint4), cudaMemcpyHostToDevice));
@@ -360,7 +354,7 @@ extern "C" int s3r_load_scene_file(S3RRenderer *r, const char *path) {
 // Test hook, callable without a GPU: the spatial pre-partition (cluster.hpp) of a triangle stream.  counts_out =
 // {clusters, cluster vertices, triangles}; the arrays are filled when they are non-null and large enough.
 extern "C" int s3r_debug_clusters(const float *vertices, uint64_t V, const uint64_t *vidx, uint64_t I, void *hdr_out, uint64_t hdr_cap,
-                                  float *pos_out, uint8_t *vslot_out, uint64_t v_cap, uint32_t *tri_out, uint64_t counts_out[3]) {
+                                  float *pos_out, uint64_t v_cap, uint32_t *tri_out, uint64_t counts_out[3]) {
     if (!vertices || !vidx || !counts_out || I % 3) { return fail(S3R_E_ARG, "bad cluster request"); }
     const uint64_t T = I / 3;
     try {
@@ -378,9 +372,9 @@ extern "C" int s3r_debug_clusters(const float *vertices, uint64_t V, const uint6
         build_clusters(px.data(), py.data(), pz.data(), v[0].data(), v[1].data(), v[2].data(), T, cs);
         counts_out[0] = cs.n_clusters; counts_out[1] = cs.px.size(); counts_out[2] = cs.tri.size();
         if (hdr_out && hdr_cap >= cs.hdr.size()) { memcpy(hdr_out, cs.hdr.data(), cs.hdr.size() * sizeof(ClusterHeader)); }
-        if (pos_out && vslot_out && v_cap >= cs.px.size()) {
+        if (pos_out && v_cap >= cs.px.size()) {
             memcpy(pos_out, cs.px.data(), cs.px.size() * 4); memcpy(pos_out + v_cap, cs.py.data(), cs.px.size() * 4);
-            memcpy(pos_out + 2 * v_cap, cs.pz.data(), cs.px.size() * 4); memcpy(vslot_out, cs.vslot.data(), cs.vslot.size());
+            memcpy(pos_out + 2 * v_cap, cs.pz.data(), cs.px.size() * 4);
         }
         if (tri_out) { memcpy(tri_out, cs.tri.data(), cs.tri.size() * 4); }
     } catch (const std::exception &e) {
@@ -683,7 +677,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     f.factor = r->factor_override != 0.f ? r->factor_override : s3r_factor(H);
     f.rv = r->rv.p;
     if (!uses_direct_bin(r) && uses_clusters(r, partitioned)) {
-        f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_vslot = r->cl_vslot.p; f.cl_tri = r->cl_tri.p;
+        f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
         CUDA_TRY(r->cluster_list.ensure((size_t)r->views_cap * r->n_clusters));
         f.cluster_list = r->cluster_list.p;
@@ -691,7 +685,6 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         if (r->walk_cap == 0) { r->walk_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r->T, 1), std::max<uint64_t>(4096, r->T / 4)); }
         CUDA_TRY(r->walk_q.ensure((size_t)r->views_cap * r->walk_cap * 40u));
         f.walk_q = reinterpret_cast<WalkRecord *>(r->walk_q.p); f.walk_cap = r->walk_cap;
-        f.cl_batch = r->cl_batch.p; f.n_batches = r->n_batches;
         f.rv = nullptr;
     }
     f.vis = r->vis.p; f.shade = r->shade.p; f.head = r->head.p; f.slot_of = r->slot_of.p; f.worklist = r->worklist.p; f.setup_cap = r->setup_cap;

@@ -148,7 +148,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.s3r_sink_submit.argtypes = [vp, vp, vp]
     lib.s3r_sink_close.argtypes = [vp, ctypes.POINTER(u64)]
     lib.s3r_debug_band_edges.argtypes = [u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u32), ctypes.c_int]
-    lib.s3r_debug_clusters.argtypes = [vp, u64, vp, u64, vp, u64, vp, vp, u64, vp, ctypes.POINTER(u64)]
+    lib.s3r_debug_clusters.argtypes = [vp, u64, vp, u64, vp, u64, vp, u64, vp, ctypes.POINTER(u64)]
     lib.s3r_get_kernel_timing.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     if path is None:
         _lib = lib
@@ -195,19 +195,18 @@ def debug_clusters(scene) -> dict:
     v = np.ascontiguousarray(scene.vertices, "<f4")
     vi = np.ascontiguousarray(scene.vertex_indices, "<u8")
     counts = (ctypes.c_uint64 * 3)()
-    rc = lib.s3r_debug_clusters(v.ctypes.data, v.shape[0], vi.ctypes.data, vi.shape[0], None, 0, None, None, 0, None, counts)
+    rc = lib.s3r_debug_clusters(v.ctypes.data, v.shape[0], vi.ctypes.data, vi.shape[0], None, 0, None, 0, None, counts)
     if rc < 0:
         raise RendererError(lib.s3r_last_error().decode())
     nc, nv, nt = int(counts[0]), int(counts[1]), int(counts[2])
     hdr = np.zeros(nc + 1, CLUSTER_HDR_DTYPE)
     pos = np.zeros((3, max(nv, 1)), np.float32)
-    vslot = np.zeros(max(nv, 1), np.uint8)
     tri = np.zeros(max(nt, 1), np.uint32)
     rc = lib.s3r_debug_clusters(v.ctypes.data, v.shape[0], vi.ctypes.data, vi.shape[0], hdr.ctypes.data, nc + 1, pos.ctypes.data,
-                                vslot.ctypes.data, max(nv, 1), tri.ctypes.data, counts)
+                                max(nv, 1), tri.ctypes.data, counts)
     if rc < 0:
         raise RendererError(lib.s3r_last_error().decode())
-    return {"hdr": hdr, "pos": pos[:, :nv], "vslot": vslot[:nv], "tri": tri[:nt]}
+    return {"hdr": hdr, "pos": pos[:, :nv], "tri": tri[:nt]}
 
 
 def tile_height() -> int:
