@@ -927,42 +927,63 @@ constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front
 // exactly what the reference's per-triangle tests would have said).  The front kernel's work is then proportional to what
 // may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.  (A coarser test on spheres around
 // batches of 64 clusters in front of this one was measured: the 32-byte headers it saves cost less than its extra step.)
+// (Persistent CTAs: the list is filled in chunks of CULL_CHUNK entries a CTA reserves with one atomic, and the statistics
+// leave with one atomic per CTA and counter — a global atomic per warp put tens of thousands of operations on three
+// addresses and made this kernel four times as long.  What is left of a CTA's last chunk is zeroed: an entry without
+// vertices or triangles is a cluster the front kernel does nothing for.)
+constexpr uint32_t CULL_CHUNK = 1024;
+
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
     wait_for_predecessor();
-    __shared__ uint32_t s_wsum[8], s_base;
+    __shared__ uint32_t s_wsum[8], s_pos, s_end, s_base, s_stats[2];
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Cam cam = load_cam(f, view);
     uint32_t *counters = f.counters + view * C_COUNT;
-    const uint32_t c = blockIdx.x * 256u + tid;
-    const bool have = c < f.n_clusters;
-    uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, nx = h0;
-    if (have) { h0 = __ldg(f.cl_hdr + 2 * (size_t)c); h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1); nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3); }
+    uint4 *list = f.cluster_list + (size_t)view * f.list_cap;
     ViewBounds vb = {{0.f, 0.f, 0.f}, 0.f};
-    if (lane == 0) { vb = view_bounds(cam); }   // (while the headers travel)
+    if (lane == 0) { vb = view_bounds(cam); }
     vb.norm[0] = __shfl_sync(0xFFFFFFFFu, vb.norm[0], 0); vb.norm[1] = __shfl_sync(0xFFFFFFFFu, vb.norm[1], 0);
     vb.norm[2] = __shfl_sync(0xFFFFFFFFu, vb.norm[2], 0); vb.sigma = __shfl_sync(0xFFFFFFFFu, vb.sigma, 0);
-    const uint32_t n_tris = nx.w - h1.w;
-    uint32_t verdict = 3u;   // 3: no cluster
-    if (have) {
-        verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+    if (tid == 0) { s_pos = 0; s_end = 0; s_stats[0] = 0; s_stats[1] = 0; }
+    uint32_t near = 0, cull = 0;
+    __syncthreads();
+    for (uint32_t c0 = blockIdx.x * 256u; c0 < f.n_clusters; c0 += gridDim.x * 256u) {
+        const uint32_t c = c0 + tid;
+        uint32_t verdict = 3u, n_tris = 0;   // 3: no cluster
+        uint4 entry = make_uint4(0u, 0u, 0u, 0u);
+        if (c < f.n_clusters) {
+            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)c), h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1), nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3);
+            n_tris = nx.w - h1.w;
+            entry = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
+            verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+        }
+        near += verdict == 1u ? n_tris : 0u; cull += verdict == 2u ? n_tris : 0u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
+        if (lane == 0) { s_wsum[warp] = (uint32_t)__popc(m); }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const uint32_t k = s_wsum[w]; s_wsum[w] = run; run += k; }
+            if (s_pos + run > s_end) {   // the chunk cannot take this round: its rest becomes empty entries, a new one is reserved
+                for (uint32_t h = s_pos; h < s_end; h++) { list[h] = make_uint4(0u, 0u, 0u, 0u); }
+                s_pos = atomicAdd(counters + C_CLUSTERS, CULL_CHUNK);
+                s_end = s_pos + CULL_CHUNK;
+            }
+            s_base = s_pos;   // this round's first slot
+            s_pos += run;
+        }
+        __syncthreads();
+        if (verdict == 0u) { list[s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = entry; }
+        __syncthreads();   // s_wsum / s_base are rewritten by the next round
     }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
-    if (lane == 0) { s_wsum[warp] = (uint32_t)__popc(m); }
-    const uint32_t near = __reduce_add_sync(0xFFFFFFFFu, verdict == 1u ? n_tris : 0u), cull = __reduce_add_sync(0xFFFFFFFFu, verdict == 2u ? n_tris : 0u);
-    if (lane == 0) {
-        if (near) { atomicAdd(counters + C_NEAR, near); }
-        if (cull) { atomicAdd(counters + C_CULLED, cull); }
-    }
+    if (tid == 0) { for (uint32_t h = s_pos; h < s_end; h++) { list[h] = make_uint4(0u, 0u, 0u, 0u); } }
+    near = __reduce_add_sync(0xFFFFFFFFu, near); cull = __reduce_add_sync(0xFFFFFFFFu, cull);
+    if (lane == 0) { if (near) { atomicAdd(&s_stats[0], near); } if (cull) { atomicAdd(&s_stats[1], cull); } }
     __syncthreads();
     if (tid == 0) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) { const uint32_t k = s_wsum[w]; s_wsum[w] = run; run += k; }
-        s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;
-    }
-    __syncthreads();
-    if (verdict == 0u) {
-        f.cluster_list[(size_t)view * f.n_clusters + s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
+        if (s_stats[0]) { atomicAdd(counters + C_NEAR, s_stats[0]); }
+        if (s_stats[1]) { atomicAdd(counters + C_CULLED, s_stats[1]); }
     }
 }
 
@@ -982,8 +1003,8 @@ __global__ void __launch_bounds__(256, S3R_FRONT_CTAS) cluster_front(const __gri
     FrontWarp &sh = sh_all[tid >> 5];
     const Cam cam = load_cam(f, view);
     uint32_t *counters = f.counters + view * C_COUNT;
-    const uint32_t n_cl = counters[C_CLUSTERS];   // written by cluster_cull
-    const uint4 *list = f.cluster_list + (size_t)view * f.n_clusters;
+    const uint32_t n_cl = min(counters[C_CLUSTERS], f.list_cap);   // list slots written by cluster_cull (empty ones included)
+    const uint4 *list = f.cluster_list + (size_t)view * f.list_cap;
     WalkRecord *queue = f.walk_q + (size_t)view * f.walk_cap;
     FrontCounts n = {0u, 0u, 0u, 0u};
     uint32_t q_pos = 0, q_end = 0;   // the warp's reserved queue range [q_pos, q_end) (uniform over the lanes)
@@ -2251,7 +2272,7 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         const bool chain = true;
-        launch_chain(cluster_cull, dim3(max(1u, ceil_div(f.n_clusters, 256u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
+        launch_chain(cluster_cull, dim3(max(1u, min(ceil_div(f.n_clusters, 256u), (uint32_t)g_sm_count * 4u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
         launch_chain(cluster_front, dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "cluster_front");
         launch_chain(direct_walk, dim3((uint32_t)g_sm_count * 6u, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "direct_walk");
     } else {

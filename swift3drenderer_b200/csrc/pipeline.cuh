@@ -107,7 +107,8 @@ struct Frame {
     const uint4 *cl_hdr;          // 2 x uint4 per cluster, n_clusters + 1 (sentinel)
     const float *cl_px, *cl_py, *cl_pz;
     const uint32_t *cl_tri;
-    uint4 *cluster_list;          // [views][n_clusters] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}
+    uint4 *cluster_list;          // [views][list_cap] clusters that survived cluster_cull: {v_off, tri_off, t0, n_verts | n_tris << 16}; zeros = empty slot
+    uint32_t list_cap;            // n_clusters + room for every CTA's partly used last chunk
     uint32_t n_clusters;
     struct WalkRecord *walk_q;    // [views][walk_cap] candidates of the direct walk (front kernel -> walk kernel)
     uint32_t walk_cap;
