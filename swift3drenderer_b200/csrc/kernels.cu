@@ -927,15 +927,14 @@ constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front
 // exactly what the reference's per-triangle tests would have said).  The front kernel's work is then proportional to what
 // may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.  (A coarser test on spheres around
 // batches of 64 clusters in front of this one was measured: the 32-byte headers it saves cost less than its extra step.)
-// (Persistent CTAs: the list is filled in chunks of CULL_CHUNK entries a CTA reserves with one atomic, and the statistics
-// leave with one atomic per CTA and counter — a global atomic per warp put tens of thousands of operations on three
-// addresses and made this kernel four times as long.  What is left of a CTA's last chunk is zeroed: an entry without
-// vertices or triangles is a cluster the front kernel does nothing for.)
-constexpr uint32_t CULL_CHUNK = 1024;
+// (Persistent CTAs: a round of 256 clusters reserves its list slots with one atomic, and the statistics leave with one
+// atomic per CTA and counter — a global atomic per warp put tens of thousands of operations on two addresses.  Reserving
+// the list in larger chunks per CTA was measured too: the empty slots it leaves cost the front kernel more than the
+// atomics it saves.)
 
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
     wait_for_predecessor();
-    __shared__ uint32_t s_wsum[8], s_pos, s_end, s_base, s_stats[2];
+    __shared__ uint32_t s_wsum[8], s_base, s_stats[2];
     const uint32_t view = blockIdx.y, tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Cam cam = load_cam(f, view);
     uint32_t *counters = f.counters + view * C_COUNT;
@@ -944,7 +943,7 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
     if (lane == 0) { vb = view_bounds(cam); }
     vb.norm[0] = __shfl_sync(0xFFFFFFFFu, vb.norm[0], 0); vb.norm[1] = __shfl_sync(0xFFFFFFFFu, vb.norm[1], 0);
     vb.norm[2] = __shfl_sync(0xFFFFFFFFu, vb.norm[2], 0); vb.sigma = __shfl_sync(0xFFFFFFFFu, vb.sigma, 0);
-    if (tid == 0) { s_pos = 0; s_end = 0; s_stats[0] = 0; s_stats[1] = 0; }
+    if (tid == 0) { s_stats[0] = 0; s_stats[1] = 0; }
     uint32_t near = 0, cull = 0;
     __syncthreads();
     for (uint32_t c0 = blockIdx.x * 256u; c0 < f.n_clusters; c0 += gridDim.x * 256u) {
@@ -965,19 +964,12 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
             uint32_t run = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) { const uint32_t k = s_wsum[w]; s_wsum[w] = run; run += k; }
-            if (s_pos + run > s_end) {   // the chunk cannot take this round: its rest becomes empty entries, a new one is reserved
-                for (uint32_t h = s_pos; h < s_end; h++) { list[h] = make_uint4(0u, 0u, 0u, 0u); }
-                s_pos = atomicAdd(counters + C_CLUSTERS, CULL_CHUNK);
-                s_end = s_pos + CULL_CHUNK;
-            }
-            s_base = s_pos;   // this round's first slot
-            s_pos += run;
+            s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;   // this round's first slot
         }
         __syncthreads();
         if (verdict == 0u) { list[s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = entry; }
         __syncthreads();   // s_wsum / s_base are rewritten by the next round
     }
-    if (tid == 0) { for (uint32_t h = s_pos; h < s_end; h++) { list[h] = make_uint4(0u, 0u, 0u, 0u); } }
     near = __reduce_add_sync(0xFFFFFFFFu, near); cull = __reduce_add_sync(0xFFFFFFFFu, cull);
     if (lane == 0) { if (near) { atomicAdd(&s_stats[0], near); } if (cull) { atomicAdd(&s_stats[1], cull); } }
     __syncthreads();

@@ -679,9 +679,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     if (!uses_direct_bin(r) && uses_clusters(r, partitioned)) {
         f.cl_hdr = r->cl_hdr.p; f.cl_px = r->cl_px.p; f.cl_py = r->cl_py.p; f.cl_pz = r->cl_pz.p; f.cl_tri = r->cl_tri.p;
         f.n_clusters = r->n_clusters; f.cluster_cull = r->opt_cluster_cull;
-        // cluster_cull fills the list in chunks of 1024 entries per CTA: a chunk is left when fewer than a round's 256 slots remain
-        // (so at least 3/4 of it is used), and each of its CTAs (at most 4 per SM) leaves one partly used at the end
-        f.list_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, (uint64_t)r->n_clusters + r->n_clusters / 2 + (2u << 20));
+        f.list_cap = r->n_clusters;
         CUDA_TRY(r->cluster_list.ensure((size_t)r->views_cap * f.list_cap));
         f.cluster_list = r->cluster_list.p;
         // candidates of the direct walk: a quarter of the triangles to begin with, regrown on overflow
