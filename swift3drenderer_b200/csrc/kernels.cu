@@ -1984,19 +1984,26 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
 //   3. one covered pixel per lane: small winners replay their own walk to the pixel (<= 15 + 15 true additions,
 //      render.cpp:374-379), winners of the tile path get there with the exact jump; shade (render.cpp:363-372);
 //   4. the colour block goes out in 16-byte (or 12-byte, 24-bit transport) pieces.
-constexpr uint32_t SHADE_B = 32;          // block edge in pixels
-constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_B;
-constexpr uint32_t SHADE_TAB = 2048;      // hash slots (load factor <= 0.5)
+#ifndef S3R_SHADE_ROWS
+#define S3R_SHADE_ROWS 16
+#endif
+constexpr uint32_t SHADE_B = 32;                              // block width in pixels
+constexpr uint32_t SHADE_BH = S3R_SHADE_ROWS;                 // block height: 32 (256 threads, 4 CTAs/SM) or 16 (128 threads, 8 CTAs/SM)
+static_assert(SHADE_BH == 32 || SHADE_BH == 16, "shade blocks are 32 x 32 or 32 x 16 pixels");
+constexpr uint32_t SHADE_THREADS = SHADE_B * SHADE_BH / 4;    // four pixels per thread when the keys are read
+constexpr uint32_t SHADE_PIX = SHADE_B * SHADE_BH;
+constexpr uint32_t SHADE_TAB = 2 * SHADE_PIX;                 // hash slots (load factor <= 0.5)
+constexpr uint32_t SHADE_TAB_SHIFT = SHADE_TAB == 2048 ? 21 : 22;
 #ifndef S3R_SHADE_CTAS
-#define S3R_SHADE_CTAS 4
+#define S3R_SHADE_CTAS (S3R_SHADE_ROWS == 32 ? 4 : 8)
 #endif
 constexpr int SHADE_CTAS = S3R_SHADE_CTAS;                  // shade_tiles CTAs per SM the launch bounds ask for
-constexpr uint32_t SHADE_TRIS = SHADE_CTAS >= 4 ? 192 : 256; // triangle setups staged per pass (one per thread; 192 keeps four CTAs within an SM's shared memory)
+constexpr uint32_t SHADE_TRIS = SHADE_BH == 16 ? 96 : (SHADE_CTAS >= 4 ? 192 : 256); // triangle setups staged per pass (one per thread; sized so that the CTAs fit an SM's shared memory)
 constexpr uint32_t SHADE_WORDS = 47;      // words per staged setup (odd: distinct triangles fall into distinct banks)
 constexpr uint32_t SHADE_EMPTY = 0xFFFFFFFFu;
 
 struct ShadeShared {
-    __align__(16) uint32_t colour[SHADE_B][SHADE_B];
+    __align__(16) uint32_t colour[SHADE_BH][SHADE_B];
     uint32_t tab[SHADE_TAB];              // hash set of orders; after numbering: slot -> triangle number
     uint32_t tri_order[SHADE_PIX];        // triangle number -> order
     uint16_t pix[SHADE_PIX];              // covered pixel list: position in the block ...
@@ -2006,12 +2013,12 @@ struct ShadeShared {
 };
 
 template <bool HAS_RV>
-__global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_CTAS) shade_tiles(const __grid_constant__ Frame f, uint32_t row0, uint32_t nrows) {
     wait_for_predecessor();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ShadeShared &sh = *reinterpret_cast<ShadeShared *>(smem_raw);
     const uint32_t view = blockIdx.z, tid = threadIdx.x, lane = lane_id();
-    const uint32_t bx0 = blockIdx.x * SHADE_B, br0 = blockIdx.y * SHADE_B;       // block origin: pixel column, row within [row0, row0 + nrows)
+    const uint32_t bx0 = blockIdx.x * SHADE_B, br0 = blockIdx.y * SHADE_BH;       // block origin: pixel column, row within [row0, row0 + nrows)
     const bool broken = f.counters[view * C_COUNT + C_OVERFLOW] != 0;            // incomplete lists: the host renders the frame again
     if (tid == 0) { sh.count = 0; sh.n_tri = 0; }
     const size_t vbase = (size_t)view * f.out_view_stride;
@@ -2033,7 +2040,7 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
     const bool any = __syncthreads_or(mask != 0u);
     if (any) {
 #pragma unroll
-        for (int k = 0; k < (int)(SHADE_TAB / 256u); k++) { sh.tab[k * 256u + tid] = SHADE_EMPTY; }
+        for (int k = 0; k < (int)(SHADE_TAB / SHADE_THREADS); k++) { sh.tab[k * SHADE_THREADS + tid] = SHADE_EMPTY; }
         __syncthreads();
         // warp-aggregated append (keeps the row-major order inside a warp: neighbours share triangles)
         const uint32_t n = __popc(mask);
@@ -2050,7 +2057,7 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
             if (mask & (1u << k)) {
                 uint32_t h = last_slot;
                 if (ord[k] != last_order) {   // insert into the hash set (linear probing)
-                    h = (ord[k] * 2654435761u) >> 21;
+                    h = (ord[k] * 2654435761u) >> SHADE_TAB_SHIFT;
                     while (true) {
                         const uint32_t prev = atomicCAS(&sh.tab[h], SHADE_EMPTY, ord[k]);
                         if (prev == SHADE_EMPTY || prev == ord[k]) { break; }
@@ -2064,8 +2071,8 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
         __syncthreads();
         // number the distinct triangles
 #pragma unroll
-        for (int k = 0; k < (int)(SHADE_TAB / 256u); k++) {
-            const uint32_t slot = k * 256u + tid, o = sh.tab[slot];
+        for (int k = 0; k < (int)(SHADE_TAB / SHADE_THREADS); k++) {
+            const uint32_t slot = k * SHADE_THREADS + tid, o = sh.tab[slot];
             if (o != SHADE_EMPTY) { const uint32_t id = atomicAdd(&sh.n_tri, 1u); sh.tri_order[id] = o; sh.tab[slot] = id; }
         }
         __syncthreads();
@@ -2125,7 +2132,7 @@ __global__ void __launch_bounds__(256, SHADE_CTAS) shade_tiles(const __grid_cons
             __syncthreads();
             // ---- 3. shade, one covered pixel per lane ---------------------------------------------
 #pragma unroll 1
-            for (uint32_t i = tid; i < count; i += 256u) {
+            for (uint32_t i = tid; i < count; i += SHADE_THREADS) {
                 const uint32_t id = sh.tab[sh.pslot[i]] - tb;
                 if (id >= SHADE_TRIS) { continue; }
                 const uint32_t *src = sh.setup[id];
@@ -2302,9 +2309,9 @@ int launch_raster(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         row0 = f.raster_row0 * TILE_H; nrows = f.raster_rows * TILE_H;
     }
     if (nrows) {
-        const dim3 grid(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_B), f.n_views);
-        if (f.rv) { launch_chain(shade_tiles<true>, grid, dim3(256), sizeof(ShadeShared), s, true, f, row0, nrows); }
-        else { launch_chain(shade_tiles<false>, grid, dim3(256), sizeof(ShadeShared), s, true, f, row0, nrows); }
+        const dim3 grid(ceil_div(f.W, SHADE_B), ceil_div(nrows, SHADE_BH), f.n_views);
+        if (f.rv) { launch_chain(shade_tiles<true>, grid, dim3(SHADE_THREADS), sizeof(ShadeShared), s, true, f, row0, nrows); }
+        else { launch_chain(shade_tiles<false>, grid, dim3(SHADE_THREADS), sizeof(ShadeShared), s, true, f, row0, nrows); }
         mark(m, "shade_tiles");
         launches++;
     }
