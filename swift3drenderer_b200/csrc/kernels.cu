@@ -927,10 +927,12 @@ constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front
 // exactly what the reference's per-triangle tests would have said).  The front kernel's work is then proportional to what
 // may actually be visible to this submission: on an n-GPU screen partition, 1/n of it.  (A coarser test on spheres around
 // batches of 64 clusters in front of this one was measured: the 32-byte headers it saves cost less than its extra step.)
-// (Persistent CTAs: a round of 256 clusters reserves its list slots with one atomic, and the statistics leave with one
-// atomic per CTA and counter — a global atomic per warp put tens of thousands of operations on two addresses.  Reserving
-// the list in larger chunks per CTA was measured too: the empty slots it leaves cost the front kernel more than the
-// atomics it saves.)
+// (Each CTA judges CULL_ROUNDS x 256 consecutive clusters with no barrier and no atomic between the rounds, so the header loads
+// of one round overlap the arithmetic of another; then one block scan and ONE global atomic reserve the CTA's list slots, and
+// the survivors' entries are rebuilt from their headers, which are still in L1/L2.  One list atomic per 256 clusters kept a
+// dependent round trip in every round — 23 us for the benchmark field —, a global atomic per warp for the statistics put tens
+// of thousands of operations on two addresses — 36 us.)
+constexpr uint32_t CULL_ROUNDS = 8;
 
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
     wait_for_predecessor();
@@ -943,36 +945,45 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
     if (lane == 0) { vb = view_bounds(cam); }
     vb.norm[0] = __shfl_sync(0xFFFFFFFFu, vb.norm[0], 0); vb.norm[1] = __shfl_sync(0xFFFFFFFFu, vb.norm[1], 0);
     vb.norm[2] = __shfl_sync(0xFFFFFFFFu, vb.norm[2], 0); vb.sigma = __shfl_sync(0xFFFFFFFFu, vb.sigma, 0);
-    if (tid == 0) { s_stats[0] = 0; s_stats[1] = 0; }
-    uint32_t near = 0, cull = 0;
-    __syncthreads();
-    for (uint32_t c0 = blockIdx.x * 256u; c0 < f.n_clusters; c0 += gridDim.x * 256u) {
-        const uint32_t c = c0 + tid;
-        uint32_t verdict = 3u, n_tris = 0;   // 3: no cluster
-        uint4 entry = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 2) { s_stats[tid] = 0; }
+    const uint32_t c_first = blockIdx.x * (CULL_ROUNDS * 256u) + tid;
+    uint32_t alive = 0, near = 0, cull = 0;   // alive: bit k = the cluster of round k survives
+#pragma unroll 2
+    for (uint32_t k = 0; k < CULL_ROUNDS; k++) {
+        const uint32_t c = c_first + k * 256u;
         if (c < f.n_clusters) {
-            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)c), h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1), nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3);
-            n_tris = nx.w - h1.w;
-            entry = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | (n_tris << 16));
-            verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+            const uint4 h0 = __ldg(f.cl_hdr + 2 * (size_t)c), h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1);
+            const uint32_t n_tris = __ldg(f.cl_hdr + 2 * (size_t)c + 3).w - h1.w;
+            const uint32_t verdict = f.cluster_cull ? cluster_verdict(f, cam, vb, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w), __uint_as_float(h1.x)) : 0u;
+            alive |= (verdict == 0u ? 1u : 0u) << k;
+            near += verdict == 1u ? n_tris : 0u; cull += verdict == 2u ? n_tris : 0u;
         }
-        near += verdict == 1u ? n_tris : 0u; cull += verdict == 2u ? n_tris : 0u;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, verdict == 0u);
-        if (lane == 0) { s_wsum[warp] = (uint32_t)__popc(m); }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { const uint32_t k = s_wsum[w]; s_wsum[w] = run; run += k; }
-            s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;   // this round's first slot
-        }
-        __syncthreads();
-        if (verdict == 0u) { list[s_base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = entry; }
-        __syncthreads();   // s_wsum / s_base are rewritten by the next round
     }
+    // list slots: block-wide exclusive scan of the survivor counts, one global atomic per CTA
+    const uint32_t mine = (uint32_t)__popc(alive);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) { incl += v; } }
+    if (lane == 31) { s_wsum[warp] = incl; }
     near = __reduce_add_sync(0xFFFFFFFFu, near); cull = __reduce_add_sync(0xFFFFFFFFu, cull);
-    if (lane == 0) { if (near) { atomicAdd(&s_stats[0], near); } if (cull) { atomicAdd(&s_stats[1], cull); } }
     __syncthreads();
+    if (lane == 0) { if (near) { atomicAdd(&s_stats[0], near); } if (cull) { atomicAdd(&s_stats[1], cull); } }
+    if (tid == 0) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t n = s_wsum[w]; s_wsum[w] = run; run += n; }
+        s_base = run ? atomicAdd(counters + C_CLUSTERS, run) : 0u;
+    }
+    __syncthreads();
+    uint32_t at = s_base + s_wsum[warp] + incl - mine;
+#pragma unroll 2
+    for (uint32_t k = 0; k < CULL_ROUNDS; k++) {
+        if (alive & (1u << k)) {
+            const uint32_t c = c_first + k * 256u;
+            const uint4 h1 = __ldg(f.cl_hdr + 2 * (size_t)c + 1), nx = __ldg(f.cl_hdr + 2 * (size_t)c + 3);
+            list[at++] = make_uint4(h1.z, h1.w, h1.y, (nx.z - h1.z) | ((nx.w - h1.w) << 16));
+        }
+    }
     if (tid == 0) {
         if (s_stats[0]) { atomicAdd(counters + C_NEAR, s_stats[0]); }
         if (s_stats[1]) { atomicAdd(counters + C_CULLED, s_stats[1]); }
@@ -1829,6 +1840,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, S3R_QUEUE_CTAS) tile_raster_qu
     const uint32_t view = blockIdx.y;
     uint32_t *c = f.counters + view * C_COUNT;
     const uint32_t n_items = min(c[C_ITEMS], f.items_cap);
+    if (n_items == 0u) { return; }   // no triangle over 128 pixels this frame: not even the queue counter is touched
     while (true) {
         __syncthreads();   // the previous item's shared-memory state is dead
         if (threadIdx.x == 0) { sh.n_list = atomicAdd(c + C_QHEAD, 1u); }
@@ -1855,6 +1867,17 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
     __shared__ float s_ck[FLAT_ROUND][FLAT_CK][3];
     __shared__ uint4 s_head[FLAT_ROUND], s_rec[FLAT_ROUND][4];   // the round's survivors, staged once (the items are latency-bound otherwise)
     const uint32_t view = blockIdx.y;
+    if (f.counters[view * C_COUNT + C_SETUPS] == 0u && f.counters[view * C_COUNT + C_BIG] == 0u) {
+        // no recorded triangle at all (every survivor took the record-free direct walk): nothing to bin, nothing to walk, all
+        // tile lists empty — one thread closes the frame's geometry, and 591 CTAs skip their two global atomics
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            uint32_t *c = f.counters + view * C_COUNT;
+            const uint32_t overflow = c[C_OVERFLOW];
+            c[C_ENTRIES] = 0;
+            if (overflow) { atomicOr(f.sticky + 0, overflow); }
+        }
+        return;
+    }
     bin_big_body(f, view);   // K3 for the triangles the setup kernel left to a whole CTA
     if (f.rowtab) {
         // row starts of the tile-path triangles: one thread per triangle takes a block of the table and walks its own
@@ -2271,7 +2294,7 @@ int launch_geometry(const Frame &f, cudaStream_t s, const LaunchMarks *m) {
         // and tile histograms (zeroed by vertex_stage on the other path) are cleared by one small memset
         cudaMemsetAsync(f.counters, 0, ((size_t)(f.tile_count - f.counters) + (size_t)f.n_views * f.tile_stride) * sizeof(uint32_t), s);   // (the histograms follow the counters)
         const bool chain = true;
-        launch_chain(cluster_cull, dim3(max(1u, min(ceil_div(f.n_clusters, 256u), (uint32_t)g_sm_count * 4u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
+        launch_chain(cluster_cull, dim3(max(1u, ceil_div(f.n_clusters, CULL_ROUNDS * 256u)), f.n_views), dim3(256), 0, s, false, f); launches++; mark(m, "cluster_cull");
         launch_chain(cluster_front, dim3((uint32_t)g_sm_count * (uint32_t)S3R_FRONT_CTAS, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "cluster_front");
         launch_chain(direct_walk, dim3((uint32_t)g_sm_count * 6u, f.n_views), dim3(256), 0, s, chain, f); launches++; mark(m, "direct_walk");
     } else {
