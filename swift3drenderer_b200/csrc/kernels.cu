@@ -2281,7 +2281,9 @@ static void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (g_pdl && after_kernel) ? 1u : 0u;
+    // (not on the legacy / per-thread default streams: their implicit synchronisation and the programmatic edge do not mix)
+    const bool real_stream = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+    cfg.attrs = attr; cfg.numAttrs = (g_pdl && after_kernel && real_stream) ? 1u : 0u;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 void set_dependent_launch(int on) { g_pdl = on; }
