@@ -1286,7 +1286,7 @@ struct MultiGpu {
     std::atomic<int> done{0};
     bool stop = false;
     MultiJob job{};
-    int pin = 1;
+    int pin = 1, bands = 3;   // bands: raster / shading launches per GPU and frame, each followed by its rows' copy
     std::vector<HostPin> pins;
 };
 MultiGpu *g_multi = nullptr;
@@ -1308,23 +1308,34 @@ int multi_worker_frame(MultiGpu *mg, int k) {
     }
     r->factor_override = j.factor;
     for (int attempt = 0; attempt < 8; attempt++) {
-        int rc = render_chunk(r, j.matrix, 1, j.W, j.H, 0, j.H, r->frame.p, r->stream, 1, nullptr, false, n, (uint32_t)k);
+        // The GPU's tile rows are rendered in a few bands; band b's rows leave over PCIe (copy stream) while band b + 1 is
+        // rasterised / shaded.  Owned tile row l = frame tile row l * n + k: TILE_H contiguous pixel rows, i.e. one "row" of a
+        // 2-D copy whose destination pitch is n tile rows — one DMA descriptor per band, one more for a cut last tile row.
+        const size_t tile_bytes = (size_t)TILE_H * j.W * 4;
+        const uint32_t last_y = ((owned - 1u) * n + (uint32_t)k) * TILE_H, last_rows = std::min<uint32_t>(TILE_H, j.H - last_y);
+        uint8_t *dst0 = j.pinned ? reinterpret_cast<uint8_t *>(j.host_out + (size_t)k * TILE_H * j.W) : me.staging;
+        const size_t dpitch = j.pinned ? tile_bytes * n : tile_bytes;
+        uint32_t band_rows[S3RRenderer::MAX_SLICES] = {};
+        uint32_t done_tiles = 0;
+        const std::function<int(int)> copy_band = [&](int b) -> int {
+            const uint32_t upto = std::min(owned, (band_rows[b] + TILE_H - 1u) / TILE_H);   // owned tile rows finished after band b
+            CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[b], 0));
+            const uint32_t full_end = (upto == owned && last_rows != (uint32_t)TILE_H) ? owned - 1u : upto;
+            if (full_end > done_tiles) {
+                CUDA_TRY(cudaMemcpy2DAsync(dst0 + dpitch * done_tiles, dpitch, reinterpret_cast<const uint8_t *>(r->frame.p) + tile_bytes * done_tiles,
+                                           tile_bytes, tile_bytes, full_end - done_tiles, cudaMemcpyDeviceToHost, r->copy_stream));
+            }
+            if (upto == owned && full_end < owned && done_tiles < owned) {
+                CUDA_TRY(cudaMemcpyAsync(dst0 + dpitch * full_end, reinterpret_cast<const uint8_t *>(r->frame.p) + tile_bytes * full_end,
+                                         (size_t)last_rows * j.W * 4, cudaMemcpyDeviceToHost, r->copy_stream));
+            }
+            done_tiles = upto;
+            return S3R_OK;
+        };
+        int rc = render_chunk(r, j.matrix, 1, j.W, j.H, 0, j.H, r->frame.p, r->stream, mg->bands, band_rows, false, n, (uint32_t)k, &copy_band);
         if (rc) { return rc; }
         r->last_views = 1; r->last_W = j.W; r->last_H = j.H; r->last_stream = r->stream;
-        {
-            // owned tile row l = frame tile row l * n + k: TILE_H contiguous pixel rows, i.e. one "row" of a 2-D copy whose
-            // destination pitch is n tile rows — one DMA descriptor for all full tile rows, one more for a cut last one
-            const size_t tile_bytes = (size_t)TILE_H * j.W * 4;
-            const uint32_t last_y = ((owned - 1u) * n + (uint32_t)k) * TILE_H, last_rows = std::min<uint32_t>(TILE_H, j.H - last_y);
-            const uint32_t full = last_rows == (uint32_t)TILE_H ? owned : owned - 1u;
-            uint8_t *dst0 = j.pinned ? reinterpret_cast<uint8_t *>(j.host_out + (size_t)k * TILE_H * j.W) : me.staging;
-            const size_t dpitch = j.pinned ? tile_bytes * n : tile_bytes;
-            if (full) { CUDA_TRY(cudaMemcpy2DAsync(dst0, dpitch, r->frame.p, tile_bytes, tile_bytes, full, cudaMemcpyDeviceToHost, r->stream)); }
-            if (full < owned) {
-                CUDA_TRY(cudaMemcpyAsync(dst0 + dpitch * full, reinterpret_cast<const uint8_t *>(r->frame.p) + tile_bytes * full,
-                                         (size_t)last_rows * j.W * 4, cudaMemcpyDeviceToHost, r->stream));
-            }
-        }
+        CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
         rc = finish_on(r, r->stream);   // waits for the launches and the copies; 1 = a capacity was regrown, render again
         if (rc < 0) { return rc; }
         if (rc == 0) {
@@ -1456,6 +1467,7 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
         MultiGpu *mg = new MultiGpu();
         mg->w.resize(devices.size());
         if (const char *env = getenv("S3R_PIN_HOST")) { mg->pin = atoi(env) != 0; }
+        if (const char *env = getenv("S3R_MULTI_BANDS")) { mg->bands = std::max(1, std::min(atoi(env), 16)); }
         std::vector<std::thread> loaders;
         std::vector<int> rcs(devices.size(), 0);
         std::vector<std::string> errs(devices.size());
