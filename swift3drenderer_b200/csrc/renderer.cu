@@ -1286,7 +1286,7 @@ struct MultiGpu {
     std::atomic<int> done{0};
     bool stop = false;
     MultiJob job{};
-    int pin = 1, bands = 3;   // bands: raster / shading launches per GPU and frame, each followed by its rows' copy
+    int pin = 1, bands = 4;   // bands: raster / shading launches per GPU and frame, each followed by its rows' copy
     std::vector<HostPin> pins;
 };
 MultiGpu *g_multi = nullptr;
