@@ -289,6 +289,10 @@ __device__ __forceinline__ size_t out_row(const Frame &f, uint32_t yy, uint32_t 
 __device__ __forceinline__ uint32_t pixel_y(const Frame &f, uint32_t r) {
     return f.row_stride == 1u ? r + f.y0 : ((r / TILE_H) * f.row_stride + f.row_phase) * TILE_H + r % TILE_H;
 }
+// position of the key of output row r, column x inside a view's key plane (see Frame::keys): columns of 4 rows per sector;
+// one step along x is 4 keys
+constexpr uint32_t KEY_STEP = 4;
+__device__ __forceinline__ size_t key_at(const Frame &f, size_t r, uint32_t x) { return ((r >> 2) * f.W + x) * KEY_STEP + (r & 3u); }
 __device__ __forceinline__ uint32_t owned_rows_in(const Frame &f, uint32_t a0, uint32_t a1) {   // #owned rows in [a0, a1]
     if (f.row_stride == 1u) { return a1 - a0 + 1u; }
     const uint32_t first = a0 + mod_stride(f, f.row_phase + f.row_stride - mod_stride(f, a0));
@@ -663,7 +667,7 @@ template <bool PAIR>
 __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkShared &wsh, FrontCounts &n, bool valid, uint32_t item,
                                            const float4 &r0, const float4 &r1, const float4 &r2) {
     const uint32_t tid = threadIdx.x, lane = lane_id();
-    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
+    unsigned long long *keys = f.keys + (size_t)view * f.key_view_stride;
     if (tid < SMALL_MAX) { wsh.cls_count[tid] = 0; }
     __syncthreads();
     uint32_t route = 0;   // 1 work item for K2b, 3 walked here
@@ -733,14 +737,14 @@ __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkSh
             else { w0 = wsh.ck[3 * g - 3][ow]; w1 = wsh.ck[3 * g - 2][ow]; w2 = wsh.ck[3 * g - 1][ow]; }
             for (uint32_t q = 0; q < (r & 3u); q++) { w0 = add_rn(w0, dy0); w1 = add_rn(w1, dy1); w2 = add_rn(w2, dy2); }   // render.cpp:378
             const uint32_t y = (xy >> 16) + r, a = y / TILE_H;
-            unsigned long long *krow = keys + out_row(f, y, a) * f.W + (xy & 0xFFFFu);
+            unsigned long long *krow = keys + key_at(f, out_row(f, y, a), xy & 0xFFFFu);   // neighbouring lanes: neighbouring rows, same x
             // (leaving the row once it has left its run of inside pixels — the weights are monotone along a row — was
             // measured and does not pay: the warp's longest row decides, and the test costs every lane)
             for (uint32_t x = 0; x <= bw; x++) {
                 const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                if (inside && ooz > 0.f) { red_max_u64(krow + KEY_STEP * x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
@@ -1675,7 +1679,8 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
         // on this tile have published.  Shading (shade_tiles) finds the triangle through the key's order and re-derives
         // the weights at the pixel with the exact jump, so nothing but the key has to be stored.
         if (y >= ylo_t && y < yhi_t) {
-            unsigned long long *krow = f.keys + (size_t)view * f.out_view_stride + out_row(f, y, tile_a) * f.W;
+            const size_t orow = out_row(f, y, tile_a);
+            unsigned long long *krow = f.keys + (size_t)view * f.key_view_stride + key_at(f, orow, 0u);
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const uint32_t x = sx0 + j;
@@ -1687,8 +1692,8 @@ __device__ __forceinline__ void raster_one_tile(const Frame &f, RasterShared &sh
                     // tags whether all of them belong to the triangle that holds the key.  A later, better candidate (this
                     // tile's list may be shared by several CTAs) overwrites them in any order; shading checks the tags and
                     // falls back to the exact jump on any mismatch.
-                    if (atomicMax(krow + x, key) < key) {
-                        unsigned long long *ps = f.pstate + 3u * ((size_t)(krow - f.keys) + x);
+                    if (atomicMax(krow + KEY_STEP * x, key) < key) {
+                        unsigned long long *ps = f.pstate + 3u * ((size_t)view * f.out_view_stride + orow * f.W + x);
                         const unsigned long long tag = (unsigned long long)win[j] << 32;
                         ps[0] = tag | __float_as_uint(bw0[j]); ps[1] = tag | __float_as_uint(bw1[j]); ps[2] = tag | __float_as_uint(bw2[j]);
                     }
@@ -1912,7 +1917,7 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
     // one row whatever the mix of box sizes.  Exactly the reference's own additions (render.cpp:374-379).  Rounds are
     // small and handed out by an atomic counter: their cost varies by orders of magnitude with the box sizes, and a
     // static deal of 256-survivor rounds left two thirds of the CTAs without work on the clipping-stress scene.
-    unsigned long long *keys = f.keys + (size_t)view * f.out_view_stride;
+    unsigned long long *keys = f.keys + (size_t)view * f.key_view_stride;
     const uint32_t n = min(f.counters[view * C_COUNT + C_SETUPS], f.setup_cap);
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     while (true) {
@@ -1973,12 +1978,12 @@ __global__ void __launch_bounds__(256) post_setup(const __grid_constant__ Frame 
             float w1 = walk_near(s_ck[lo][ck][1], __uint_as_float(q2.w), more);
             float w2 = walk_near(s_ck[lo][ck][2], __uint_as_float(q3.x), more);
             const unsigned long long key_lo = (unsigned long long)(~head.z);
-            unsigned long long *krow = keys + out_row(f, y, a) * f.W;
+            unsigned long long *krow = keys + key_at(f, out_row(f, y, a), 0u);
             for (uint32_t x = xmin; x <= xmax; x++) {
                 const bool inside = w0 >= 0 && w1 >= 0 && w2 >= 0;                    // render.cpp:362
                 const float ooz = (rz0 * w0 + rz1 * w1) + rz2 * w2;                   // render.cpp:363
                 // depth starts at 0, strict '>' (render.cpp:364); fire-and-forget red.max, nothing waits for it
-                if (inside && ooz > 0.f) { red_max_u64(krow + x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
+                if (inside && ooz > 0.f) { red_max_u64(krow + KEY_STEP * x, ((unsigned long long)__float_as_uint(ooz) << 32) | key_lo); }
                 w0 = add_rn(w0, dx0); w1 = add_rn(w1, dx1); w2 = add_rn(w2, dx2);     // render.cpp:374
             }
         }
@@ -2046,15 +2051,30 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_CTAS) shade_tiles(const _
     if (tid == 0) { sh.count = 0; sh.n_tri = 0; }
     const size_t vbase = (size_t)view * f.out_view_stride;
     // ---- 1. keys -> compacted list of covered pixels + distinct triangles ---------------------------
-    const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u;   // this thread's 4 pixels: block row pr, columns pc .. pc + 3
+    // A thread reads (and clears) the keys of one column of 4 rows — one 32-byte sector of the key plane where the block
+    // starts on a multiple of 4 output rows (always, except in bands that begin inside a tile row).
+    const uint32_t pr = tid >> 3, pc = (tid & 7u) * 4u;   // write-out (step 4): block row pr, columns pc .. pc + 3
+    const uint32_t kr = (tid >> 5) * 4u, kc = tid & 31u;   // keys: block rows kr .. kr + 3 of block column kc
     uint32_t ord[4] = {0u, 0u, 0u, 0u}, mask = 0;
-    if (br0 + pr < nrows) {
-        unsigned long long *kp = f.keys + vbase + (size_t)(row0 + br0 + pr) * f.W + bx0 + pc;
+    if (bx0 + kc < f.W && br0 + kr < nrows) {
+        unsigned long long *plane = f.keys + (size_t)view * f.key_view_stride;
+        const size_t r_first = (size_t)row0 + br0 + kr;
+        if ((r_first & 3u) == 0u && br0 + kr + 3u < nrows) {
+            ulonglong2 *kp = reinterpret_cast<ulonglong2 *>(plane + key_at(f, r_first, bx0 + kc));
+            const ulonglong2 lo = kp[0], hi = kp[1];
+            const unsigned long long key[4] = {lo.x, lo.y, hi.x, hi.y};
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (bx0 + pc + k < f.W) {
-                const unsigned long long key = kp[k];
-                if (key != 0ull) { kp[k] = 0ull; ord[k] = ~(uint32_t)key; mask |= 1u << k; }
+            for (int k = 0; k < 4; k++) { if (key[k] != 0ull) { ord[k] = ~(uint32_t)key[k]; mask |= 1u << k; } }
+            if (mask & 3u) { kp[0] = make_ulonglong2(0ull, 0ull); }
+            if (mask & 12u) { kp[1] = make_ulonglong2(0ull, 0ull); }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (br0 + kr + k < nrows) {
+                    unsigned long long *kp = plane + key_at(f, r_first + k, bx0 + kc);
+                    const unsigned long long key = *kp;
+                    if (key != 0ull) { *kp = 0ull; ord[k] = ~(uint32_t)key; mask |= 1u << k; }
+                }
             }
         }
     }
@@ -2065,7 +2085,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_CTAS) shade_tiles(const _
 #pragma unroll
         for (int k = 0; k < (int)(SHADE_TAB / SHADE_THREADS); k++) { sh.tab[k * SHADE_THREADS + tid] = SHADE_EMPTY; }
         __syncthreads();
-        // warp-aggregated append (keeps the row-major order inside a warp: neighbours share triangles)
+        // warp-aggregated append (a warp's pixels stay together in the list, column by column: neighbours share triangles)
         const uint32_t n = __popc(mask);
         uint32_t incl = n;
 #pragma unroll
@@ -2088,7 +2108,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_CTAS) shade_tiles(const _
                     }
                     last_order = ord[k]; last_slot = h;
                 }
-                sh.pix[j] = (uint16_t)(pr * SHADE_B + pc + k); sh.pslot[j] = (uint16_t)h; j++;
+                sh.pix[j] = (uint16_t)((kr + k) * SHADE_B + kc); sh.pslot[j] = (uint16_t)h; j++;
             }
         }
         __syncthreads();

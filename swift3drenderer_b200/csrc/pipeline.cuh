@@ -141,8 +141,13 @@ struct Frame {
     uint32_t tile_cap;          // capacity of every tile's list
     uint32_t *big_list;
     uint32_t big_cap;
-    // general path: per-pixel depth keys (depth << 32 | ~order), indexed like `out`; the tile kernel's work queue
+    // general path: per-pixel depth keys (depth << 32 | ~order); the tile kernel's work queue.
+    // Key layout (key_at in kernels.cu): the keys of 4 vertically adjacent pixels — output rows 4g .. 4g + 3 of one column —
+    // share one 32-byte sector.  The L2 reduction path works per (instruction, sector), not per lane
+    // (tools/probes/red_sector_probe.cu: 191 G reductions/s with one lane per sector, 381 G with two, 468 G with four),
+    // and the walks' neighbouring lanes are neighbouring rows of one triangle at the same x.
     unsigned long long *keys;
+    unsigned long long key_view_stride;   // keys per view: W * (output rows rounded up to 4)
     unsigned long long *pstate;   // [pixels][3] {slot << 32 | weight bits}: exact weights of the tile kernel's best candidate, each word tagged
     uint2 *raster_items;   // [views][items_cap] {tile, first entry of the chunk}
     uint32_t items_cap;

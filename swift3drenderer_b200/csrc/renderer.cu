@@ -702,11 +702,12 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
     for (uint32_t k = 0; k < r->n_peers; k++) { f.peer_out[k] = r->peer_out[k]; }
     f.keys = r->keys.p;
     f.out_view_stride = row_stride == 1 ? (unsigned long long)W * (y1 - y0) : (unsigned long long)W * f.tiles_y * TILE_H;
+    f.key_view_stride = (unsigned long long)W * (((f.out_view_stride / W) + 3u) & ~3ull);   // key plane: columns of 4 output rows
     if (!uses_direct_bin(r)) {   // general path: per-pixel keys and winners for the flat passes
         // keys are all zero between frames: allocation clears them, shade_tiles clears what a frame has set
-        if ((size_t)n_views * f.out_view_stride + 2 > r->keys.n) {
+        if ((size_t)n_views * f.key_view_stride + 2 > r->keys.n) {
             CUDA_TRY(cudaStreamSynchronize(s));
-            CUDA_TRY(r->keys.ensure((size_t)n_views * f.out_view_stride + 2));
+            CUDA_TRY(r->keys.ensure((size_t)n_views * f.key_view_stride + 2));
             CUDA_TRY(cudaMemsetAsync(r->keys.p, 0, r->keys.n * sizeof(unsigned long long), s));
         }
         f.keys = r->keys.p;
