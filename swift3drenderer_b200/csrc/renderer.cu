@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <exception>
 #include <mutex>
@@ -1289,7 +1290,22 @@ struct MultiGpu {
     MultiJob job{};
     int pin = 1, bands = 4;   // bands: raster / shading launches per GPU and frame, each followed by its rows' copy
     std::vector<HostPin> pins;
+    // S3R_MULTI_TRACE=1: where a frame's wall time goes (microseconds, summed; printed every 256 frames to stderr)
+    int trace = 0;
+    uint64_t traced = 0;
+    std::chrono::steady_clock::time_point t_publish;
+    double us_total = 0, us_pin = 0, us_tail = 0;   // main thread: whole call, registration + sentinels, last worker done -> return
+    struct Trace {
+        double wake = 0, launch = 0, copies = 0, finish = 0;
+        std::chrono::steady_clock::time_point done;
+        cudaEvent_t e0 = nullptr, eb[16] = {}, ee[16] = {};   // device timeline: frame start (render stream), every band's copy begin / end (copy stream)
+        double begin_us[16] = {}, end_us[16] = {};
+    };
+    std::vector<Trace> tr;
 };
+static inline double us_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
 MultiGpu *g_multi = nullptr;
 
 int multi_worker_frame(MultiGpu *mg, int k) {
@@ -1308,7 +1324,9 @@ int multi_worker_frame(MultiGpu *mg, int k) {
         me.staging_bytes = compact_px * 4;
     }
     r->factor_override = j.factor;
+    if (mg->trace) { mg->tr[(size_t)k].wake += us_since(mg->t_publish); }
     for (int attempt = 0; attempt < 8; attempt++) {
+        const auto t_begin = std::chrono::steady_clock::now();
         // The GPU's tile rows are rendered in a few bands; band b's rows leave over PCIe (copy stream) while band b + 1 is
         // rasterised / shaded.  Owned tile row l = frame tile row l * n + k: TILE_H contiguous pixel rows, i.e. one "row" of a
         // 2-D copy whose destination pitch is n tile rows — one DMA descriptor per band, one more for a cut last tile row.
@@ -1318,9 +1336,16 @@ int multi_worker_frame(MultiGpu *mg, int k) {
         const size_t dpitch = j.pinned ? tile_bytes * n : tile_bytes;
         uint32_t band_rows[S3RRenderer::MAX_SLICES] = {};
         uint32_t done_tiles = 0;
+        MultiGpu::Trace *tr = mg->trace ? &mg->tr[(size_t)k] : nullptr;
+        int n_bands = 0;
+        if (tr) {
+            if (!tr->e0) { cudaEventCreate(&tr->e0); for (int b = 0; b < 16; b++) { cudaEventCreate(&tr->eb[b]); cudaEventCreate(&tr->ee[b]); } }
+            CUDA_TRY(cudaEventRecord(tr->e0, r->stream));
+        }
         const std::function<int(int)> copy_band = [&](int b) -> int {
             const uint32_t upto = std::min(owned, (band_rows[b] + TILE_H - 1u) / TILE_H);   // owned tile rows finished after band b
             CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->ev_raster[b], 0));
+            if (tr && b < 16) { CUDA_TRY(cudaEventRecord(tr->eb[b], r->copy_stream)); n_bands = b + 1; }
             const uint32_t full_end = (upto == owned && last_rows != (uint32_t)TILE_H) ? owned - 1u : upto;
             if (full_end > done_tiles) {
                 CUDA_TRY(cudaMemcpy2DAsync(dst0 + dpitch * done_tiles, dpitch, reinterpret_cast<const uint8_t *>(r->frame.p) + tile_bytes * done_tiles,
@@ -1331,13 +1356,27 @@ int multi_worker_frame(MultiGpu *mg, int k) {
                                          (size_t)last_rows * j.W * 4, cudaMemcpyDeviceToHost, r->copy_stream));
             }
             done_tiles = upto;
+            if (tr && b < 16) { CUDA_TRY(cudaEventRecord(tr->ee[b], r->copy_stream)); }
             return S3R_OK;
         };
         int rc = render_chunk(r, j.matrix, 1, j.W, j.H, 0, j.H, r->frame.p, r->stream, mg->bands, band_rows, false, n, (uint32_t)k, &copy_band);
         if (rc) { return rc; }
         r->last_views = 1; r->last_W = j.W; r->last_H = j.H; r->last_stream = r->stream;
+        const auto t_launched = std::chrono::steady_clock::now();
         CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
+        const auto t_copied = std::chrono::steady_clock::now();
         rc = finish_on(r, r->stream);   // waits for the launches and the copies; 1 = a capacity was regrown, render again
+        if (mg->trace) {
+            MultiGpu::Trace &t = mg->tr[(size_t)k];
+            t.launch += std::chrono::duration<double, std::micro>(t_launched - t_begin).count();
+            t.copies += std::chrono::duration<double, std::micro>(t_copied - t_launched).count();
+            t.finish += us_since(t_copied);
+            for (int b = 0; b < n_bands; b++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, t.e0, t.eb[b]) == cudaSuccess) { t.begin_us[b] += ms * 1e3; }
+                if (cudaEventElapsedTime(&ms, t.e0, t.ee[b]) == cudaSuccess) { t.end_us[b] += ms * 1e3; }
+            }
+        }
         if (rc < 0) { return rc; }
         if (rc == 0) {
             if (!j.pinned) {
@@ -1366,6 +1405,7 @@ void multi_worker(MultiGpu *mg, int k) {
         MultiGpu::Worker &me = mg->w[(size_t)k];
         me.rc = multi_worker_frame(mg, k);
         if (me.rc) { me.error = g_error; }
+        if (mg->trace) { mg->tr[(size_t)k].done = std::chrono::steady_clock::now(); }
         if (mg->done.fetch_add(1, std::memory_order_acq_rel) + 1 == (int)mg->w.size()) {
             std::lock_guard<std::mutex> g(mg->m);
             mg->cv_done.notify_one();
@@ -1390,11 +1430,13 @@ bool multi_pin(MultiGpu *mg, const void *ptr, size_t bytes) {
 int multi_render(MultiGpu *mg, const float *matrix, float factor, uint32_t W, uint32_t H, uint32_t *host_out) {
     if (W == 0 || H == 0 || W > 65535 || H > 65535) { return fail(S3R_E_ARG, "bad frame geometry"); }
     const size_t px = (size_t)W * H;
+    const auto t_call = std::chrono::steady_clock::now();
     for (int pass = 0; pass < 2; pass++) {
         cudaSetDevice(mg->w[0].r->device);
         const bool pinned = pass == 0 && multi_pin(mg, host_out, px * 4);
         if (pinned) { plant_sentinels(host_out, px); }
         mg->job = MultiJob{matrix, factor, W, H, host_out, pinned};
+        if (mg->trace) { mg->us_pin += us_since(t_call); mg->t_publish = std::chrono::steady_clock::now(); }
         mg->done.store(0, std::memory_order_release);
         {
             std::lock_guard<std::mutex> g(mg->m);
@@ -1407,7 +1449,30 @@ int multi_render(MultiGpu *mg, const float *matrix, float factor, uint32_t W, ui
             mg->cv_done.wait(g, [&] { return mg->done.load(std::memory_order_acquire) >= (int)mg->w.size(); });
         }
         for (auto &wk : mg->w) { if (wk.rc) { return fail(wk.rc, wk.error); } }
-        if (!pinned || sentinels_gone(host_out, px)) { return S3R_OK; }
+        if (mg->trace) {
+            auto last = mg->tr[0].done;
+            for (auto &t : mg->tr) { last = std::max(last, t.done); }
+            mg->us_tail += us_since(last);
+        }
+        if (!pinned || sentinels_gone(host_out, px)) {
+            if (mg->trace) {
+                mg->us_total += us_since(t_call);
+                if (++mg->traced % 256 == 0) {
+                    const double n = 256.0;
+                    fprintf(stderr, "[s3r multi] per frame: call %.0f us, pin+sentinels %.0f, tail %.0f |", mg->us_total / n, mg->us_pin / n, mg->us_tail / n);
+                    for (size_t i = 0; i < mg->tr.size(); i++) {
+                        MultiGpu::Trace &t = mg->tr[i];
+                        fprintf(stderr, " gpu%zu: wake %.0f launch %.0f copies %.0f finish %.0f, band copies on the device clock", i, t.wake / n, t.launch / n, t.copies / n, t.finish / n);
+                        for (int b = 0; b < 16 && t.end_us[b] > 0; b++) { fprintf(stderr, " [%.0f-%.0f]", t.begin_us[b] / n, t.end_us[b] / n); t.begin_us[b] = t.end_us[b] = 0; }
+                        fprintf(stderr, " |");
+                        t.wake = t.launch = t.copies = t.finish = 0;
+                    }
+                    fprintf(stderr, "\n");
+                    mg->us_total = mg->us_pin = mg->us_tail = 0;
+                }
+            }
+            return S3R_OK;
+        }
         // the DMA went to pages the CPU no longer sees (a registration outlived its allocation): drop every pin, go again through staging
         for (auto &p : mg->pins) { cudaHostUnregister(const_cast<void *>(p.ptr)); }
         mg->pins.clear();
@@ -1469,6 +1534,8 @@ void drop_in_initialize() {  // render.cpp:160-176 (data.bin next to this shared
         mg->w.resize(devices.size());
         if (const char *env = getenv("S3R_PIN_HOST")) { mg->pin = atoi(env) != 0; }
         if (const char *env = getenv("S3R_MULTI_BANDS")) { mg->bands = std::max(1, std::min(atoi(env), 16)); }
+        if (const char *env = getenv("S3R_MULTI_TRACE")) { mg->trace = atoi(env); }
+        mg->tr.resize(devices.size());
         std::vector<std::thread> loaders;
         std::vector<int> rcs(devices.size(), 0);
         std::vector<std::string> errs(devices.size());

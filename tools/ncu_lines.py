@@ -1,4 +1,5 @@
-"""tools/ncu_lines.py <report.ncu-rep> <kernel-substring> [top] — warp instructions per CUDA source line.
+"""tools/ncu_lines.py <report.ncu-rep> <kernel-substring> [top] [stall] — warp instructions per CUDA source line (sorted by
+instructions, or by stall samples with a fourth argument `stall`).
 
 Joins the SASS page of an `ncu --set full` capture (instructions executed, thread instructions, stall samples per
 SASS instruction) with the line table of the shipped cubin (`nvdisasm --print-line-info`; the library is built
@@ -65,7 +66,8 @@ def main():
     tot_smp = sum(a[2] for a in agg.values()) or 1
     print(f"{kernel}: {total} warp instructions, {len(data)} SASS instructions, {len(agg)} source lines")
     print(f"{'file:line':<22}{'warp inst':>12}{'%':>7}{'lanes':>7}{'stall %':>9}{'sass':>6}  source")
-    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    by = 2 if len(sys.argv) > 4 and sys.argv[4] == "stall" else 0
+    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         fn, ln = key
         if fn not in src:
             path = os.path.join(ROOT, "swift3drenderer_b200", "csrc", fn)
