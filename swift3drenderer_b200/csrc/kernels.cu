@@ -660,9 +660,16 @@ __device__ __forceinline__ BoxRoute route_candidate(const Frame &f, const float4
 // fire-and-forget 64-bit red.max.  Everything else becomes a work item of K2b.  All 256 threads call.
 // PAIR: a work item is a pair of owned rows of one box, row i and row i + half — a triangle's rows are short at its tips and
 // long in the middle, so the pairs' lengths are more alike than the rows' (the lanes of a warp run in lockstep) and the box's
-// parameters are fetched once for two rows.  Measured on the benchmark field (profiles/r02_experiments.md): pairs win in the
-// walk-only kernel (direct_walk 332 -> 316 us), single rows in the fused classify kernel (509 -> 452 us), where the walk
-// shares its warps with the front tests.
+// parameters are fetched once for two rows.  Measured on the benchmark field (profiles/r02_experiments.md): with row-major
+// keys pairs won in the walk-only kernel (332 -> 316 us) and lost in the fused classify kernel (452 -> 509 us); with the keys
+// in columns of 4 rows single rows win in both (direct_walk 297 -> 289 us, classify 394 vs 440 us) — neighbouring lanes on
+// neighbouring rows share a sector of the key plane, lanes on rows i and i + half do not.  Kept as a build switch.
+#ifndef S3R_CLASSIFY_PAIR
+#define S3R_CLASSIFY_PAIR 0
+#endif
+#ifndef S3R_WALK_PAIR
+#define S3R_WALK_PAIR 0
+#endif
 template <bool PAIR>
 __device__ __forceinline__ void walk_round(const Frame &f, uint32_t view, WalkShared &wsh, FrontCounts &n, bool valid, uint32_t item,
                                            const float4 &r0, const float4 &r1, const float4 &r2) {
@@ -810,7 +817,7 @@ __global__ void __launch_bounds__(256) triangle_classify(const __grid_constant__
             item = csh.cand[cbase + tid];
             if (!(item & ITEM_STRADDLE)) { r0 = rv[__ldg(f.vi0 + item)]; r1 = rv[__ldg(f.vi1 + item)]; r2 = rv[__ldg(f.vi2 + item)]; }
         }
-        walk_round<false>(f, view, wsh, n, valid, item, r0, r1, r2);
+        walk_round<S3R_CLASSIFY_PAIR != 0>(f, view, wsh, n, valid, item, r0, r1, r2);
     }
     publish_front_counts(f, view, wsh, n);
 }
@@ -936,7 +943,14 @@ constexpr uint32_t WALK_CHUNK = 64;           // queue slots a warp of the front
 // the survivors' entries are rebuilt from their headers, which are still in L1/L2.  One list atomic per 256 clusters kept a
 // dependent round trip in every round — 23 us for the benchmark field —, a global atomic per warp for the statistics put tens
 // of thousands of operations on two addresses — 36 us.)
-constexpr uint32_t CULL_ROUNDS = 8;
+#ifndef S3R_CULL_ROUNDS
+#define S3R_CULL_ROUNDS 8
+#endif
+#ifndef S3R_CULL_UNROLL
+#define S3R_CULL_UNROLL 2
+#endif
+constexpr uint32_t CULL_ROUNDS = S3R_CULL_ROUNDS;
+constexpr int CULL_UNROLL = S3R_CULL_UNROLL;
 
 __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Frame f) {
     wait_for_predecessor();
@@ -952,7 +966,7 @@ __global__ void __launch_bounds__(256) cluster_cull(const __grid_constant__ Fram
     if (tid < 2) { s_stats[tid] = 0; }
     const uint32_t c_first = blockIdx.x * (CULL_ROUNDS * 256u) + tid;
     uint32_t alive = 0, near = 0, cull = 0;   // alive: bit k = the cluster of round k survives
-#pragma unroll 2
+#pragma unroll CULL_UNROLL
     for (uint32_t k = 0; k < CULL_ROUNDS; k++) {
         const uint32_t c = c_first + k * 256u;
         if (c < f.n_clusters) {
@@ -1187,7 +1201,7 @@ __global__ void __launch_bounds__(256, 6) direct_walk(const __grid_constant__ Fr
             item = e.y;
             valid = item != WALK_HOLE;   // a slot reserved for a candidate that went elsewhere
         }
-        walk_round<true>(f, view, wsh, n, valid, item, r0, r1, r2);
+        walk_round<S3R_WALK_PAIR != 0>(f, view, wsh, n, valid, item, r0, r1, r2);
     }
     publish_front_counts(f, view, wsh, n);
 }
@@ -2116,7 +2130,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_CTAS) shade_tiles(const _
 #pragma unroll
         for (int k = 0; k < (int)(SHADE_TAB / SHADE_THREADS); k++) {
             const uint32_t slot = k * SHADE_THREADS + tid, o = sh.tab[slot];
-            if (o != SHADE_EMPTY) { const uint32_t id = atomicAdd(&sh.n_tri, 1u); sh.tri_order[id] = o; sh.tab[slot] = id; }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, o != SHADE_EMPTY);   // one shared-memory atomic per warp, not per triangle
+            uint32_t first = 0;
+            if (lane == 0 && m) { first = atomicAdd(&sh.n_tri, (uint32_t)__popc(m)); }
+            first = __shfl_sync(0xFFFFFFFFu, first, 0);
+            if (o != SHADE_EMPTY) { const uint32_t id = first + (uint32_t)__popc(m & ((1u << lane) - 1u)); sh.tri_order[id] = o; sh.tab[slot] = id; }
         }
         __syncthreads();
         const uint32_t count = sh.count, n_tri = sh.n_tri;
