@@ -14,7 +14,8 @@ drift path.  One *step* = those 8 frames, one pose per launch set.
            on a private render.so beside C3's data.bin with the caller's pageable double buffer (host camera step,
            48 B H2D, render, D2H of the frame inside the timed region).  N > 1: ONE caller (rank 0) whose updateAndRender
            drives all N GPUs from one process (S3R_DEVICES; every GPU copies its rows over its own PCIe link).
-  roofline per kernel from CUDA events recorded after every launch of the timed region (option "timing") and for the
+  roofline per kernel from CUDA events recorded after every launch of every fifth frame of the timed region (option
+           "timing" = --timing-stride; timing every frame costs the launch overlap of the frames it measures) and for the
            frame (B_alg = 12V + 28A + 8I + 4WH); `traffic` from the committed ncu capture.
   cpu_baseline / --impl reference: the reference's own render.cpp (oracle/_ref, compiled unmodified; falls back to the C
            port) on the host cores: one single-threaded replica process per core (bounded by memory: each replica maps
@@ -361,6 +362,7 @@ def main():
                     help="N > 1: interleaved tile rows stored straight into every rank's frame over NVLink peer memory (fused), "
                          "interleaved tile rows + NCCL all-gather (rows), contiguous bands + NCCL all-gather (bands)")
     ap.add_argument("--ring", type=int, default=4, help="assembled frames kept per rank (ring slots)")
+    ap.add_argument("--timing-stride", type=int, default=5, help="per-kernel CUDA events on every n-th frame of the timed region (1 = every frame)")
     ap.add_argument("--c2-frames", type=int, default=600, help="frames per step of the secondary record (the recorded fly-through)")
     ap.add_argument("--c2-views-per-launch", type=int, default=24)
     ap.add_argument("--cpu-replicas", type=int, default=0, help="cap on CPU reference replicas (0 = cores, bounded by memory)")
@@ -531,7 +533,10 @@ def main():
         while max_over_ranks(1.0 if r.finish() else 0.0) > 0:   # capacity regrowth happens here, outside the timed region
             run_step()
             drain()
-    r.set_option("timing", 1)
+    # per-kernel CUDA events on every args.timing_stride-th frame of the timed region: an event after every launch keeps a
+    # kernel from being placed while its predecessor drains (programmatic dependent launch), so timing every frame would
+    # slow down what it measures; 5 is coprime to the 8 poses, every pose is sampled equally often
+    r.set_option("timing", max(1, args.timing_stride))
     r.timing(reset=True)
     clocks = ClockSampler(local_rank)
     barrier()
@@ -591,7 +596,9 @@ def main():
         n = max(rec["launches"], 1)
         us = rec["ms"] * 1e3 / n
         alg = kernel_alg_bytes(name, counts, px_rank, world, stats_last["setups"])
-        kernels[name] = {"avg_launch_us": us, "launches": rec["launches"], "share_of_step": rec["ms"] / ms_total if ms_total else None,
+        # share of the timed region: the kernel's average duration x its launches in the whole region (timed frames are a sample)
+        scale = frames_total / max(stage["chunks"], 1)
+        kernels[name] = {"avg_launch_us": us, "launches": rec["launches"], "share_of_step": rec["ms"] * scale / ms_total if ms_total else None,
                          "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / us / 1e3 if us > 0 else None,
                          "frac": alg / us / 1e3 / peak if us > 0 else None,
                          "ncu_dram_bytes_per_launch": traffic.get(name if world == 1 else name + f"@{world}")}

@@ -153,7 +153,7 @@ S3R_API int s3r_set_option(S3RRenderer *r, const char *name, int64_t value);
 /* options: "tma_store" (1 = cp.async.bulk tile write-out, default; 0 = plain stores),
  *          "pin_host" (1 = cudaHostRegister the caller's frame buffers; default 0 — only for callers that
  *                      keep the buffer mapped while they pass it; drop-in: env S3R_PIN_HOST=1),
- *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage events),
+ *          "views_per_chunk" (views per kernel launch set, default 256), "timing" (per-stage and per-kernel events; n > 1: on every n-th submission only),
  *          "fused_small" (1 = one fused geometry CTA per view for scenes of at most 1920 triangles, default),
  *          "tensor_store" (1 = tile_raster writes each tile with one TMA tensor store instead of 32 bulk row copies, default),
  *          "spans" (1 = small scenes, whole-frame launches: the row walks of the largest survivors are done once per

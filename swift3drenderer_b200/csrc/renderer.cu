@@ -125,7 +125,8 @@ struct S3RRenderer {
     struct KernelAcc { const char *name; double ms; uint64_t launches; };
     std::vector<KernelAcc> kernel_acc;
     uint64_t chunk_counter = 0;
-    int opt_timing = 0;
+    int opt_timing = 0;          // 0 off, n > 0: every n-th submission is timed (events after every launch cost launch overlap)
+    uint64_t timing_phase = 0;
     double geometry_ms = 0, raster_ms = 0;
     uint64_t timed_chunks = 0;
     // last render (for finish / dumps)
@@ -660,7 +661,7 @@ static int render_chunk(S3RRenderer *r, const float *cams, uint32_t n_views, uin
         CUDA_TRY(cudaEventRecord(r->ev_cams[slot], s));
         r->slot_used[slot] = true;
     }
-    const bool timed = r->opt_timing != 0;
+    const bool timed = r->opt_timing > 0 && (r->timing_phase++ % (uint64_t)r->opt_timing) == 0;
     MarkCtx mark_ctx{r, slot, s};
     const LaunchMarks marks{mark_kernel, &mark_ctx};
     const LaunchMarks *mk = timed ? &marks : nullptr;
@@ -1236,7 +1237,7 @@ extern "C" int s3r_set_option(S3RRenderer *r, const char *name, int64_t value) {
         r->opt_copy_threads = (int)value;
         return S3R_OK;
     }
-    if (!strcmp(name, "timing")) { r->opt_timing = value != 0; return S3R_OK; }
+    if (!strcmp(name, "timing")) { r->opt_timing = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); r->timing_phase = 0; return S3R_OK; }
     if (!strcmp(name, "pin_host")) { r->opt_pin_host = value != 0; if (!value) { unpin_all(r); } return S3R_OK; }
     if (!strcmp(name, "views_per_chunk")) {
         if (value < 1) { return fail(S3R_E_ARG, "views_per_chunk < 1"); }
